@@ -1,0 +1,129 @@
+/*
+ * jpegqs_cuda.h - C ABI of the B200 (sm_100a) back end of libjpegqs.
+ *
+ * This is the boundary between the libjpeg-facing host code (csrc/do_quantsmooth.c, which
+ * keeps the reference's own entry points of libjpegqs.h) and the CUDA implementation.  It
+ * occupies the slot of the reference's per-ISA workers do_quantsmooth_{base,sse2,avx2,avx512}
+ * (reference libjpegqs.c:38-58, selected at libjpegqs.c:80-156): plain pointers and sizes,
+ * no libjpeg types, no C++/torch types.  Every entry point cites the reference code it
+ * replaces.  There is NO CPU fallback behind these calls: without a usable CUDA device they
+ * fail with a negative return code.
+ *
+ * Layouts
+ *   coefficients  int16 [hblk][wblk][64], natural (row-major) order inside a block - exactly
+ *                 libjpeg's JBLOCKROW rows laid end to end (jpeglib.h JBLOCK / JCOEF).
+ *   quant         the raw UINT16 quantval[64] of the component's JQUANT_TBL.
+ */
+#ifndef JPEGQS_CUDA_H
+#define JPEGQS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPEGQS_CUDA_MAX_COMP 10        /* libjpeg MAX_COMPONENTS */
+
+/* error codes (all negative); >= 0 return values are the reference's `stop` value */
+#define JPEGQS_ERR_CUDA  (-1)          /* CUDA runtime failure, see jpegqs_cuda_last_error */
+#define JPEGQS_ERR_ARG   (-2)          /* malformed arguments */
+#define JPEGQS_ERR_UNSUPPORTED (-3)    /* JPEGQS_LOW_QUALITY is not implemented on the device */
+
+typedef struct jpegqs_cuda_ctx jpegqs_cuda_ctx;
+
+/* One colour component as do_quantsmooth sees it: fields of jpeg_component_info that the
+ * reference reads at quantsmooth.h:2484-2494 plus its coefficient array. */
+typedef struct {
+	int16_t *coef;          /* in: quantized; out: de-quantized + smoothed (in place)     */
+	uint32_t wblk, hblk;    /* width_in_blocks, height_in_blocks                          */
+	int32_t h_samp, v_samp; /* h_samp_factor, v_samp_factor                               */
+	int32_t has_qtbl;       /* 0 when compptr->quant_table == NULL (component skipped)    */
+	uint16_t quant[64];     /* raw quantval; overwritten with 1 on return (2851-2859)     */
+	int16_t *coef_up;       /* out, comps 1..2 only: luma-sized array filled when
+	                           UPSAMPLE_UV replaces the chroma arrays (2691-2752); may be
+	                           NULL when UPSAMPLE_UV cannot trigger                        */
+} jpegqs_cuda_comp;
+
+typedef struct {
+	int32_t ncomp;
+	int32_t is_ycbcr;                   /* jpeg_color_space == JCS_YCbCr                   */
+	uint32_t image_width, image_height;
+	jpegqs_cuda_comp comp[JPEGQS_CUDA_MAX_COMP];
+	int32_t upsampled;                  /* out: 1 = comps 1,2 now live in coef_up at the
+	                                       luma geometry with 1x1 sampling (2835-2849)     */
+} jpegqs_cuda_image;
+
+typedef int (*jpegqs_cuda_progress_fn)(void *userdata, int cur, int max);
+
+/* ---- context -------------------------------------------------------------------------- */
+/* device < 0: the current CUDA device.  Returns 0 or a negative error code. */
+int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out);
+void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx);
+const char *jpegqs_cuda_last_error(const jpegqs_cuda_ctx *ctx);   /* ctx may be NULL */
+const char *jpegqs_cuda_device_name(const jpegqs_cuda_ctx *ctx);
+/* device time (CUDA events) of the kernels of the last run_* call, milliseconds */
+float jpegqs_cuda_last_device_ms(const jpegqs_cuda_ctx *ctx);
+/* number of kernel launches issued by the last run_* call */
+int jpegqs_cuda_last_launches(const jpegqs_cuda_ctx *ctx);
+
+/* pinned host memory for coefficient arrays (fast H2D/D2H); plain malloc'd memory works too */
+void *jpegqs_cuda_host_alloc(size_t bytes);
+void jpegqs_cuda_host_free(void *p);
+
+/* ---- whole-image entry points: the body of do_quantsmooth (quantsmooth.h:2404-2878) ----
+ * flags/niter/progprec/progress/userdata = jpegqs_control_t fields (libjpegqs.h:41-45).
+ * With progress == NULL independent components are processed in the same kernel launches;
+ * with a callback components run one after another so the callback sequence (cur, max) is
+ * the reference's (quantsmooth.h:2656-2664).
+ * Return: the reference's `stop` (0 = done, non-zero = stopped early) or a negative error. */
+int jpegqs_cuda_run_host(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *img, int flags, int niter,
+		int progprec, jpegqs_cuda_progress_fn progress, void *userdata);
+/* same, but comp[].coef / coef_up are DEVICE pointers; stream = cudaStream_t or NULL */
+int jpegqs_cuda_run_device(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *img, int flags, int niter,
+		int progprec, jpegqs_cuda_progress_fn progress, void *userdata, void *stream);
+/* n independent images in shared launches (no progress callback); host or device pointers.
+ * ret[i] receives each image's stop value.  Returns 0 or a negative error. */
+int jpegqs_cuda_run_batch(jpegqs_cuda_ctx *ctx, int nimages, jpegqs_cuda_image *imgs, int flags,
+		int niter, int on_device, int *ret, void *stream);
+
+/* ---- pass-level entry points (multi-GPU slabs: the caller exchanges halo rows between
+ *      the passes).  All pointers are DEVICE pointers. ---------- */
+typedef struct {
+	int16_t *coef;             /* [hblk][wblk][64] of this slab                            */
+	uint8_t *plane;            /* jpegqs_cuda_plane_bytes(wblk, hblk) bytes                */
+	const uint8_t *plane2;     /* down-sampled luma plane of the same geometry, or NULL    */
+	uint32_t wblk, hblk;       /* hblk = block rows held by this slab                      */
+	uint16_t quant[64];        /* raw quantval                                             */
+	int32_t luma;              /* !ci || colour space != YCbCr (quantsmooth.h:2639)        */
+	int32_t top_edge;          /* slab touches the image top / bottom: replicate the       */
+	int32_t bottom_edge;       /* border row there (2618-2619) instead of expecting a halo */
+} jpegqs_cuda_job;
+
+size_t jpegqs_cuda_plane_bytes(uint32_t wblk, uint32_t hblk);
+int jpegqs_cuda_plane_stride(uint32_t wblk);
+int jpegqs_cuda_plane_pad(void);   /* byte offset of pixel column 0 inside a plane row */
+
+#define JPEGQS_PASS_DEQUANT 1      /* iteration 0: coef *= quantval, range check (2596-2603) */
+#define JPEGQS_PASS_CLAMP   2      /* write coefficients back clamped to +-1023 (2670-2689)  */
+/* IDCT pass (2589-2620): renders each job's plane (+ replicated borders).  *bad receives
+ * non-zero if a de-quantized coefficient left [-2048, 2047] (host sync).  bad may be NULL. */
+int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int mode,
+		int *bad, void *stream);
+/* smoothing pass (2627-2640): quantsmooth_block on every block of every job */
+int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int flags,
+		int clamp_out, void *stream);
+
+/* ---- introspection used by the parity tests ------------------------------------------- */
+/* the 64 weight tables exactly as the device consumes them but WITHOUT the power-of-two
+ * pre-scale, natural coefficient order, 160 (or 272 with JPEGQS_DIAGONALS) floats each;
+ * replaces quantsmooth_init (quantsmooth.h:251-301).  Returns floats per coefficient. */
+int jpegqs_cuda_tables(int flags, float *out);
+/* host evaluation of the device's exact-division helper (GET_ORIG_COEF, 324-341) */
+int jpegqs_cuda_orig_coef(int coef, int q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -40,7 +40,8 @@ def __getattr__(name):
     # the CUDA binding is imported lazily so that the host-only helpers
     # (synth, image) work on a machine without the built extension
     if name in ("cuda", "do_quantsmooth", "QsContext", "lib_path"):
-        from . import cuda as _cuda
+        import importlib
+        _cuda = importlib.import_module(__name__ + ".cuda")
         if name == "cuda":
             return _cuda
         return getattr(_cuda, name)

@@ -1,0 +1,74 @@
+/*
+ * qs_common.h - types shared by the host driver (qs_cuda.cu) and the sm_100a kernels
+ * (qs_kernels.cu).  Nothing here is visible through the C ABI (include/jpegqs_cuda.h).
+ */
+#ifndef QS_COMMON_H
+#define QS_COMMON_H
+
+#include <stdint.h>
+
+/* flag bits, numerically equal to the public JPEGQS_* enum (include/libjpegqs.h) */
+#define QS_DIAGONALS 1
+#define QS_JOINT_YUV 2
+#define QS_UPSAMPLE_UV 4
+#define QS_LOW_QUALITY 8
+#define QS_NO_REBALANCE 16
+#define QS_NO_REBALANCE_UV 32
+
+/* Sample planes.  Pixel (x, y) of a component (or of a slab of it) lives at
+ * plane[(y + 1) * stride + QS_PLANE_PAD + x]; row 0 / row h+1 and columns -1 / w are the
+ * replicated 1-px border of reference quantsmooth.h:2612-2620 (or, at an interior slab
+ * edge of a multi-GPU run, the neighbour's halo row).  stride = wblk*8 + 2*QS_PLANE_PAD. */
+#define QS_PLANE_PAD 16
+#define QS_PLANE_STRIDE(wblk) ((int)(wblk) * 8 + 2 * QS_PLANE_PAD)
+#define QS_PLANE_BYTES(wblk, hblk) ((size_t)QS_PLANE_STRIDE(wblk) * ((size_t)(hblk) * 8 + 2))
+
+/* Pixel differences enter the float pipeline pre-scaled by 2^-QS_SCALE_BITS (exact), the
+ * weight tables pre-scaled by 2^(2*QS_SCALE_BITS); see DESIGN.md "exact rescaling". */
+#define QS_SCALE_BITS 15
+
+#define QS_TAB_PLAIN 160
+#define QS_TAB_DIAG 272
+
+/* per-quant-table constants, device resident */
+typedef struct {
+	float Rs[64];        /* 2*q[i] * 2^-QS_SCALE_BITS  (range of quantsmooth.h:1406, scaled) */
+	uint32_t m31[64];    /* ceil(2^31 / q[i]): exact floor-division magic, see qs_orig_coef */
+	uint16_t q[64];      /* quantval with 0 -> 1 (quantsmooth.h:2508-2511) */
+	uint16_t qraw[64];   /* raw quantval, used only by the iteration-0 dequantize (2598) */
+} QsQuantDev;
+
+/* one component (or one slab of block rows of it) taking part in a launch */
+typedef struct {
+	int16_t *coef;           /* [hblk][wblk][64] */
+	uint8_t *plane;          /* sample plane of this component */
+	const uint8_t *plane2;   /* down-sampled luma plane (JOINT_YUV predictor) or NULL */
+	const QsQuantDev *quant;
+	int32_t wblk, hblk;      /* blocks; hblk = rows present in this slab */
+	int32_t stride;          /* bytes per plane row */
+	int32_t nblocks;         /* wblk * hblk */
+	int32_t tile_begin;      /* first 32-block tile of this job inside the launch */
+	int32_t luma;            /* rebalance class (quantsmooth.h:2639) */
+	int32_t top_edge;        /* 1: slab top is the image top -> replicate row -1 */
+	int32_t bottom_edge;     /* 1: slab bottom is the image bottom */
+	int32_t bad_slot;        /* index into the per-launch "coefficient out of range" flags */
+} QsJob;
+
+#define QS_MAX_JOBS 1024
+
+/* IDCT-pass modes */
+#define QS_IDCT_DEQUANT 1     /* multiply by qraw, range-check (iteration 0) */
+#define QS_IDCT_CLAMP 2       /* write coefficients back clamped to +-1023 (2670-2689) */
+#define QS_IDCT_NOPLANE 4     /* do not render pixels (dequantize/clamp only) */
+
+/* chunk schedule of the 63 AC coefficients: 14 anti-diagonal groups (reverse zig-zag,
+ * quantsmooth.h:313-322, 1403-1409) split into chunks of <= 4 coefficients that share the
+ * pixel-difference work.  type 1 = the group's two edge coefficients (row 0: no vertical
+ * terms; column 0: no horizontal terms; quantsmooth.h:1527, 1531). */
+typedef struct {
+	uint8_t type, n, first, pad;
+	uint8_t idx[4];
+} QsChunk;
+#define QS_MAX_CHUNKS 32
+
+#endif

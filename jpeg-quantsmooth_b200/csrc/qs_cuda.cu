@@ -1,0 +1,641 @@
+/*
+ * qs_cuda.cu - host side of the CUDA back end: context, device memory, launch sequencing
+ * and the C ABI declared in include/jpegqs_cuda.h.
+ *
+ * The sequencing restates the reference driver do_quantsmooth (reference
+ * quantsmooth.h:2404-2878) as a schedule of kernel launches; the arithmetic itself lives in
+ * qs_kernels.cu.  Independent components (and, in the batch entry point, independent
+ * images) share launches; the luma -> chroma dependency of JOINT_YUV / UPSAMPLE_UV
+ * (quantsmooth.h:2495, 2691-2815) splits a run into two phases.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "qs_common.h"
+#include "qs_kernels.h"
+#include "../../include/jpegqs_cuda.h"
+
+/* ------------------------------------------------------------------------------------------
+ * weight tables: quantsmooth_init, reference quantsmooth.h:251-301, built from the float
+ * LL&M IDCT of reference idct.h:565-604.  Host code; this TU is compiled without FMA
+ * contraction so the values are the reference's bits (tests compare them
+ * against the reference's own table builder).
+ * ------------------------------------------------------------------------------------------ */
+static void tab_idct_1d(const float *in, int is, float *out, int os, bool scale) {
+	float t0, t1, t2, t3, t4, t5, t6, t7, z1, z2, z3, z4, z5, r[8];
+	z2 = in[2 * is]; z3 = in[6 * is];
+	z1 = (z2 + z3) * 0.541196100f;
+	t2 = z1 - z3 * 1.847759065f;
+	t3 = z1 + z2 * 0.765366865f;
+	z2 = in[0]; z3 = in[4 * is];
+	t0 = z2 + z3; t1 = z2 - z3;
+	t4 = t0 + t3; t7 = t0 - t3; t5 = t1 + t2; t6 = t1 - t2;
+	t0 = in[7 * is]; t1 = in[5 * is]; t2 = in[3 * is]; t3 = in[1 * is];
+	z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;
+	z5 = (z3 + z4) * 1.175875602f;
+	t0 *= 0.298631336f; t1 *= 2.053119869f; t2 *= 3.072711026f; t3 *= 1.501321110f;
+	z1 *= 0.899976223f; z2 *= 2.562915447f; z3 *= 1.961570560f; z4 *= 0.390180644f;
+	z3 -= z5; t0 -= z1 + z3; t2 -= z2 + z3;
+	z4 -= z5; t1 -= z2 + z4; t3 -= z1 + z4;
+	r[0] = t4 + t3; r[7] = t4 - t3; r[1] = t5 + t2; r[6] = t5 - t2;
+	r[2] = t6 + t1; r[5] = t6 - t1; r[3] = t7 + t0; r[4] = t7 - t0;
+	for (int k = 0; k < 8; k++) out[k * os] = scale ? r[k] * 0.125f : r[k];
+}
+
+static int build_tables(int flags, float *out, float prescale) {
+	const int size = (flags & QS_DIAGONALS) ? QS_TAB_DIAG : QS_TAB_PLAIN;
+	const float bcoef = (flags & QS_DIAGONALS) ? 4.0f : 2.0f;
+	for (int i = 0; i < 64; i++) {
+		float e[64], ws[64], B[64], *t = out + i * size;
+		memset(e, 0, sizeof(e)); e[i] = 1.0f;
+		for (int x = 0; x < 8; x++) tab_idct_1d(e + x, 8, ws + x, 8, false);
+		for (int y = 0; y < 8; y++) tab_idct_1d(ws + y * 8, 1, B + y * 8, 1, true);
+		for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) {
+			t[y * 8 + x] = x < 7 ? B[y * 8 + x] - B[y * 8 + x + 1] : 0.0f;
+			t[96 + y * 8 + x] = y < 7 ? B[y * 8 + x] - B[y * 8 + 8 + x] : 0.0f;
+		}
+		for (int x = 0; x < 8; x++) {
+			t[64 + x] = B[x] * bcoef; t[72 + x] = B[56 + x] * bcoef;
+			t[80 + x] = B[x * 8] * bcoef; t[88 + x] = B[x * 8 + 7] * bcoef;
+		}
+		if (flags & QS_DIAGONALS) for (int y = 0; y < 7; y++) {
+			float *d = t + 160 + y * 16;
+			for (int x = 0; x < 7; x++) {
+				d[x] = B[y * 8 + x] - B[y * 8 + 9 + x];
+				d[8 + x] = B[y * 8 + x + 1] - B[y * 8 + 8 + x];
+			}
+			d[7] = d[15] = 0.0f;
+		}
+		if (prescale != 1.0f) for (int k = 0; k < size; k++) t[k] *= prescale;   /* power of two: exact */
+	}
+	return size;
+}
+
+/* chunk schedule: anti-diagonals s = 14..1 of the 8x8 coefficient grid in the reference's
+ * visiting order (reverse zig-zag, quantsmooth.h:1403 + zigzag_refresh 313-322) */
+static int build_chunks(QsChunk *ch) {
+	int n = 0;
+	for (int s = 14; s >= 1; s--) {
+		int full[8], nf = 0; bool first = true;
+		for (int u = 0; u < 8; u++) {
+			int v = s - u;
+			if (v < 0 || v > 7 || u == 0 || v == 0) continue;
+			full[nf++] = v * 8 + u;
+		}
+		if (s <= 7) {
+			QsChunk c; memset(&c, 0, sizeof(c));
+			c.type = 1; c.n = 2; c.first = 1; first = false;
+			c.idx[0] = (uint8_t)s;          /* row 0:    horizontal + border (+diag) */
+			c.idx[1] = (uint8_t)(s * 8);    /* column 0: border + vertical   (+diag) */
+			ch[n++] = c;
+		}
+		int parts = (nf + 3) / 4, pos = 0;
+		for (int p = 0; p < parts; p++) {
+			int len = (nf - pos + (parts - p) - 1) / (parts - p);
+			QsChunk c; memset(&c, 0, sizeof(c));
+			c.type = 0; c.n = (uint8_t)len; c.first = first; first = false;
+			for (int k = 0; k < len; k++) c.idx[k] = (uint8_t)full[pos + k];
+			pos += len;
+			ch[n++] = c;
+		}
+	}
+	return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+struct jpegqs_cuda_ctx {
+	int device, num_sms;
+	char devname[256];
+	cudaStream_t stream;
+	float *tab_plain, *tab_diag;
+	QsQuantDev *quant_dev; int quant_cap;
+	QsJob *jobs_dev;                       /* two slots of QS_MAX_JOBS */
+	std::vector<QsJob> jobs_cache[2];
+	int *flags_dev;                        /* [QS_MAX_JOBS] bad flags + [1] tile counter */
+	int *flags_host;                       /* pinned */
+	char *arena; size_t arena_cap, arena_pos;
+	cudaEvent_t ev0, ev1;
+	float last_ms; int launches;
+	char err[512];
+};
+
+static char g_err[512] = "";
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	snprintf(ctx ? ctx->err : g_err, 512, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	return JPEGQS_ERR_CUDA; } } while (0)
+
+extern "C" const char *jpegqs_cuda_last_error(const jpegqs_cuda_ctx *ctx) { return ctx ? ctx->err : g_err; }
+extern "C" const char *jpegqs_cuda_device_name(const jpegqs_cuda_ctx *ctx) { return ctx->devname; }
+extern "C" float jpegqs_cuda_last_device_ms(const jpegqs_cuda_ctx *ctx) { return ctx->last_ms; }
+extern "C" int jpegqs_cuda_last_launches(const jpegqs_cuda_ctx *ctx) { return ctx->launches; }
+extern "C" size_t jpegqs_cuda_plane_bytes(uint32_t wblk, uint32_t hblk) { return QS_PLANE_BYTES(wblk, hblk); }
+extern "C" int jpegqs_cuda_plane_stride(uint32_t wblk) { return QS_PLANE_STRIDE(wblk); }
+extern "C" int jpegqs_cuda_plane_pad(void) { return QS_PLANE_PAD; }
+extern "C" int jpegqs_cuda_tables(int flags, float *out) { return build_tables(flags, out, 1.0f); }
+extern "C" int jpegqs_cuda_orig_coef(int coef, int q) { return qs_host_orig_coef(coef, q); }
+
+extern "C" void *jpegqs_cuda_host_alloc(size_t bytes) {
+	void *p = NULL;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return NULL;
+	return p;
+}
+extern "C" void jpegqs_cuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->quant_dev);
+	cudaFree(ctx->jobs_dev); cudaFree(ctx->flags_dev); cudaFree(ctx->arena);
+	if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	delete ctx;
+}
+
+extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
+	jpegqs_cuda_ctx *ctx = NULL;
+	if (!out) return JPEGQS_ERR_ARG;
+	*out = NULL;
+	int ndev = 0;
+	CK(cudaGetDeviceCount(&ndev));
+	if (ndev <= 0) { snprintf(g_err, sizeof(g_err), "no CUDA device"); return JPEGQS_ERR_CUDA; }
+	if (device < 0) CK(cudaGetDevice(&device));
+	CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		snprintf(g_err, sizeof(g_err), "device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; "
+				"this library carries sm_100a code only and has no fallback", device, prop.name, prop.major, prop.minor);
+		return JPEGQS_ERR_CUDA;
+	}
+	ctx = new jpegqs_cuda_ctx();
+	memset(ctx->err, 0, sizeof(ctx->err));
+	ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
+	snprintf(ctx->devname, sizeof(ctx->devname), "%s", prop.name);
+	ctx->stream = NULL; ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
+	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
+	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
+	ctx->last_ms = 0; ctx->launches = 0;
+	int rc = [&]() -> int {
+		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+		std::vector<float> t(64 * QS_TAB_DIAG);
+		const float pre = 1073741824.0f;               /* 2^(2*QS_SCALE_BITS) */
+		build_tables(0, t.data(), pre);
+		CK(cudaMalloc(&ctx->tab_plain, 64 * QS_TAB_PLAIN * sizeof(float)));
+		CK(cudaMemcpy(ctx->tab_plain, t.data(), 64 * QS_TAB_PLAIN * sizeof(float), cudaMemcpyHostToDevice));
+		build_tables(QS_DIAGONALS, t.data(), pre);
+		CK(cudaMalloc(&ctx->tab_diag, 64 * QS_TAB_DIAG * sizeof(float)));
+		CK(cudaMemcpy(ctx->tab_diag, t.data(), 64 * QS_TAB_DIAG * sizeof(float), cudaMemcpyHostToDevice));
+		QsChunk ch[QS_MAX_CHUNKS];
+		int n = build_chunks(ch);
+		CK(qs_set_chunks(ch, n));
+		CK(qs_smooth_configure());
+		CK(cudaMalloc(&ctx->jobs_dev, 2 * QS_MAX_JOBS * sizeof(QsJob)));
+		CK(cudaMalloc(&ctx->flags_dev, (QS_MAX_JOBS + 1) * sizeof(int)));
+		CK(cudaMallocHost(&ctx->flags_host, QS_MAX_JOBS * sizeof(int)));
+		return 0;
+	}();
+	if (rc) { snprintf(g_err, sizeof(g_err), "%s", ctx->err); jpegqs_cuda_destroy(ctx); return rc; }
+	*out = ctx;
+	return 0;
+}
+
+static int arena_reserve(jpegqs_cuda_ctx *ctx, size_t bytes) {
+	if (bytes > ctx->arena_cap) {
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->arena) CK(cudaFree(ctx->arena));
+		ctx->arena = NULL; ctx->arena_cap = 0;
+		size_t cap = bytes + bytes / 8 + (1 << 20);
+		CK(cudaMalloc(&ctx->arena, cap));
+		ctx->arena_cap = cap;
+	}
+	ctx->arena_pos = 0;
+	return 0;
+}
+static void *arena_take(jpegqs_cuda_ctx *ctx, size_t bytes) {
+	size_t p = (ctx->arena_pos + 255) & ~(size_t)255;
+	ctx->arena_pos = p + bytes;
+	return ctx->arena + p;
+}
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out) {
+	int val = 0;
+	for (int i = 0; i < 64; i++) {
+		int v = raw[i]; val |= v;
+		int qq = v ? v : 1;                            /* quantsmooth.h:2508-2511 */
+		q->qraw[i] = (uint16_t)v; q->q[i] = (uint16_t)qq;
+		q->Rs[i] = (float)(2 * qq) * (1.0f / (float)(1 << QS_SCALE_BITS));
+		q->m31[i] = (uint32_t)(((1ull << 31) + (uint32_t)qq - 1) / (uint32_t)qq);
+	}
+	*val_out = val;
+}
+
+static int quant_reserve(jpegqs_cuda_ctx *ctx, int n) {
+	if (n > ctx->quant_cap) {
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->quant_dev) CK(cudaFree(ctx->quant_dev));
+		ctx->quant_dev = NULL; ctx->quant_cap = 0;
+		CK(cudaMalloc(&ctx->quant_dev, (size_t)(n + 16) * sizeof(QsQuantDev)));
+		ctx->quant_cap = n + 16;
+	}
+	return 0;
+}
+
+/* upload a job list into one of the two device slots unless it is already there */
+static int upload_jobs(jpegqs_cuda_ctx *ctx, int slot, std::vector<QsJob> &jobs, cudaStream_t st,
+		const QsJob **dev, int *total_tiles) {
+	int tiles = 0;
+	for (size_t i = 0; i < jobs.size(); i++) {
+		jobs[i].tile_begin = tiles; jobs[i].bad_slot = (int)i;
+		tiles += (jobs[i].nblocks + 31) / 32;
+	}
+	*total_tiles = tiles;
+	*dev = ctx->jobs_dev + (size_t)slot * QS_MAX_JOBS;
+	std::vector<QsJob> &c = ctx->jobs_cache[slot];
+	if (c.size() == jobs.size() && (jobs.empty() || !memcmp(c.data(), jobs.data(), jobs.size() * sizeof(QsJob))))
+		return 0;
+	if (jobs.size() > QS_MAX_JOBS) { snprintf(ctx->err, sizeof(ctx->err), "too many jobs in one launch"); return JPEGQS_ERR_ARG; }
+	/* pageable source: the runtime stages it before returning, so `jobs` may die afterwards */
+	if (!jobs.empty()) CK(cudaMemcpyAsync((void *)*dev, jobs.data(), jobs.size() * sizeof(QsJob), cudaMemcpyHostToDevice, st));
+	c = jobs;
+	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * whole-image driver
+ * ------------------------------------------------------------------------------------------ */
+struct CompWork {
+	int img, ci;
+	jpegqs_cuda_comp *c;
+	int16_t *coef_dev; uint8_t *plane;
+	int W, H, luma, qslot;
+	int niter2, extra;
+	bool iterate;          /* takes part in the IDCT / smoothing iterations */
+	bool dequant_only;     /* stop was already set: quantsmooth.h:2551-2566 */
+	bool done_clamp;
+};
+
+struct ImgState {
+	jpegqs_cuda_image *im;
+	bool skip;             /* early return of quantsmooth.h:2458: image untouched */
+	int need_downsample, stop;
+	uint8_t *image1, *image2;    /* full-res luma plane / down-sampled luma plane */
+	uint8_t *image2_buf, *mem_buf[2];
+	int16_t *coef_up_dev[2];
+	int ngroups;
+};
+
+static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, int flags, int niter,
+		int progprec, jpegqs_cuda_progress_fn progress, void *userdata, bool on_device, int *ret,
+		cudaStream_t st) {
+	if (!ctx || nimg < 0 || (nimg && !imgs)) return JPEGQS_ERR_ARG;
+	if (flags & QS_LOW_QUALITY) {
+		snprintf(ctx->err, sizeof(ctx->err), "JPEGQS_LOW_QUALITY (quality 0-2) is not implemented on the CUDA back end");
+		return JPEGQS_ERR_UNSUPPORTED;
+	}
+	if (progress && nimg != 1) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	ctx->launches = 0; ctx->last_ms = 0;
+	if (niter < 0) niter = 0;
+	if (niter > 100) niter = 100;                       /* quantsmooth.h:2455-2456 */
+
+	std::vector<ImgState> S(nimg);
+	std::vector<CompWork> all;
+	size_t bytes = 0; int nquant = 0, max_groups = 0;
+	for (int n = 0; n < nimg; n++) {
+		jpegqs_cuda_image *im = &imgs[n]; ImgState &s = S[n];
+		memset(&s, 0, sizeof(s)); s.im = im; im->upsampled = 0;
+		if (im->ncomp < 1 || im->ncomp > JPEGQS_CUDA_MAX_COMP) return JPEGQS_ERR_ARG;
+		s.need_downsample = (flags & (QS_JOINT_YUV | QS_UPSAMPLE_UV)) && im->is_ycbcr && im->ncomp >= 3 &&
+				im->comp[1].h_samp == 1 && im->comp[1].v_samp == 1 &&
+				im->comp[2].h_samp == 1 && im->comp[2].v_samp == 1;          /* 2447-2453 */
+		s.skip = niter <= 0 && !((flags & QS_UPSAMPLE_UV) && s.need_downsample);   /* 2458 */
+		if (ret) ret[n] = 0;
+		if (s.skip) continue;
+		if (s.need_downsample && (im->comp[1].wblk != im->comp[2].wblk || im->comp[1].hblk != im->comp[2].hblk))
+			return JPEGQS_ERR_ARG;
+		for (int ci = 0; ci < im->ncomp; ci++) {
+			jpegqs_cuda_comp *c = &im->comp[ci];
+			if (!c->coef && c->wblk && c->hblk) return JPEGQS_ERR_ARG;
+			size_t cb = (size_t)c->wblk * c->hblk * 128;
+			if (!on_device) bytes += align256(cb);
+			bytes += align256(QS_PLANE_BYTES(c->wblk, c->hblk));
+			nquant++;
+		}
+		bool sub = s.need_downsample && !(im->comp[0].h_samp == 1 && im->comp[0].v_samp == 1);
+		if (sub) {
+			bytes += align256(QS_PLANE_BYTES(im->comp[1].wblk, im->comp[1].hblk));
+			if (flags & QS_UPSAMPLE_UV) for (int j = 0; j < 2; j++) {
+				if (!im->comp[1 + j].coef_up) return JPEGQS_ERR_ARG;
+				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk;
+				bytes += align256(yb * 64);                 /* up-sampled pixel plane */
+				if (!on_device) bytes += align256(yb * 128);
+			}
+		}
+		s.ngroups = progress ? im->ncomp : (s.need_downsample ? 2 : 1);
+		if (s.ngroups > max_groups) max_groups = s.ngroups;
+	}
+	if (arena_reserve(ctx, bytes + 4096)) return JPEGQS_ERR_CUDA;
+	if (quant_reserve(ctx, nquant)) return JPEGQS_ERR_CUDA;
+
+	/* carve device memory, upload coefficients and quant constants */
+	std::vector<QsQuantDev> qhost; qhost.reserve(nquant);
+	std::vector<std::vector<CompWork> > W(nimg);
+	std::vector<std::vector<int> > qval(nimg);
+	for (int n = 0; n < nimg; n++) {
+		ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
+		if (s.skip) continue;
+		W[n].resize(im->ncomp); qval[n].resize(im->ncomp);
+		for (int ci = 0; ci < im->ncomp; ci++) {
+			jpegqs_cuda_comp *c = &im->comp[ci]; CompWork &w = W[n][ci];
+			memset(&w, 0, sizeof(w));
+			w.img = n; w.ci = ci; w.c = c; w.W = c->wblk; w.H = c->hblk;
+			w.luma = !ci || !im->is_ycbcr;                                /* 2639 */
+			size_t cb = (size_t)c->wblk * c->hblk * 128;
+			if (on_device) w.coef_dev = c->coef;
+			else {
+				w.coef_dev = (int16_t *)arena_take(ctx, cb);
+				if (cb) CK(cudaMemcpyAsync(w.coef_dev, c->coef, cb, cudaMemcpyHostToDevice, st));
+			}
+			w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
+			w.qslot = (int)qhost.size();
+			QsQuantDev q; quant_prepare(c->quant, &q, &qval[n][ci]); qhost.push_back(q);
+		}
+		bool sub = s.need_downsample && !(im->comp[0].h_samp == 1 && im->comp[0].v_samp == 1);
+		if (sub) {
+			s.image2_buf = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(im->comp[1].wblk, im->comp[1].hblk));
+			if (flags & QS_UPSAMPLE_UV) for (int j = 0; j < 2; j++) {
+				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk;
+				s.mem_buf[j] = (uint8_t *)arena_take(ctx, yb * 64);
+				s.coef_up_dev[j] = on_device ? im->comp[1 + j].coef_up : (int16_t *)arena_take(ctx, yb * 128);
+			}
+		}
+	}
+	if (!qhost.empty())
+		CK(cudaMemcpyAsync(ctx->quant_dev, qhost.data(), qhost.size() * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
+	ctx->jobs_cache[0].clear(); ctx->jobs_cache[1].clear();
+
+	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
+	int *bad_dev = ctx->flags_dev, *tile_counter = ctx->flags_dev + QS_MAX_JOBS;
+	CK(cudaEventRecord(ctx->ev0, st));
+
+	/* progress bookkeeping, quantsmooth.h:2474-2482 (single image only) */
+	int prog_next = 0, prog_max = 0, prog_thr = 0;
+	if (progress && !S[0].skip) {
+		jpegqs_cuda_image *im = S[0].im;
+		for (int ci = 0; ci < im->ncomp; ci++) prog_max += im->comp[ci].hblk * im->comp[ci].v_samp * niter;
+		if (progprec == 0) progprec = 20;
+		if (progprec < 0) progprec = prog_max;
+		prog_thr = progprec ? (int)((unsigned)(prog_max + progprec - 1) / (unsigned)progprec) : 0;
+	}
+
+	auto make_job = [&](const CompWork &w, const uint8_t *plane2) {
+		QsJob j; memset(&j, 0, sizeof(j));
+		j.coef = w.coef_dev; j.plane = w.plane; j.plane2 = plane2;
+		j.quant = ctx->quant_dev + w.qslot;
+		j.wblk = w.W; j.hblk = w.H; j.stride = QS_PLANE_STRIDE(w.W); j.nblocks = w.W * w.H;
+		j.luma = w.luma; j.top_edge = 1; j.bottom_edge = 1;
+		return j;
+	};
+
+	for (int g = 0; g < max_groups; g++) {
+		/* ---- which components belong to this phase; per-component prelude 2484-2566 ---- */
+		std::vector<CompWork *> works;
+		int prog_cur = 0, prog_inc = 0;
+		for (int n = 0; n < nimg; n++) {
+			ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
+			if (s.skip || g >= s.ngroups) continue;
+			int c0, c1;
+			if (progress) { c0 = g; c1 = g + 1; }
+			else if (s.ngroups == 2) { c0 = g ? 1 : 0; c1 = g ? im->ncomp : 1; }
+			else { c0 = 0; c1 = im->ncomp; }
+			for (int ci = c0; ci < c1; ci++) {
+				CompWork &w = W[n][ci];
+				if (progress) { prog_cur = prog_next; prog_inc = w.c->v_samp; prog_next += w.H * prog_inc * niter; }
+				if (!w.c->has_qtbl) continue;                              /* 2494 */
+				w.extra = (s.image1 || (!ci && s.need_downsample)) ? 1 : 0;      /* 2495 */
+				w.niter2 = qval[n][ci] <= 1 ? 0 : niter;                   /* 2501 */
+				if (qval[n][ci] >= 0x800) s.stop = 1;                      /* 2504 */
+				if (w.niter2 + w.extra == 0) continue;                     /* 2542 */
+				if (s.stop) {                                              /* 2551-2566 */
+					CK(qs_launch_scale_clamp(w.coef_dev, (size_t)w.W * w.H * 64, ctx->quant_dev + w.qslot, 1, 0, st));
+					ctx->launches++;
+					continue;
+				}
+				if (!(w.W * w.H)) continue;
+				w.iterate = true;
+				works.push_back(&w);
+			}
+		}
+
+		int max_pass = 0;
+		for (CompWork *w : works) if (w->niter2 + w->extra > max_pass) max_pass = w->niter2 + w->extra;
+		for (int iter = 0; iter < max_pass; iter++) {
+			/* ---- IDCT pass, 2589-2620.  The extra (render-only) pass also applies the
+			 *      final +-1023 clamp of 2670-2689 after rendering from unclamped values. */
+			for (int clampv = 0; clampv < 2; clampv++) {
+				std::vector<QsJob> jobs; std::vector<CompWork *> who;
+				for (CompWork *w : works) {
+					if (!w->iterate || iter >= w->niter2 + w->extra) continue;
+					int cl = (iter == w->niter2) ? 1 : 0;
+					if (cl != clampv) continue;
+					jobs.push_back(make_job(*w, NULL)); who.push_back(w);
+				}
+				if (jobs.empty()) continue;
+				const QsJob *jd; int tiles;
+				if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+				int mode = (iter == 0 ? QS_IDCT_DEQUANT : 0) | (clampv ? QS_IDCT_CLAMP : 0);
+				if (iter == 0) CK(cudaMemsetAsync(bad_dev, 0, jobs.size() * sizeof(int), st));
+				CK(qs_launch_idct_pass(jd, (int)jobs.size(), tiles, mode, bad_dev, st));
+				ctx->launches++;
+				if (clampv) for (CompWork *w : who) w->done_clamp = true;
+				if (iter == 0) {                                           /* bad_coef, 2602-2610 */
+					CK(cudaMemcpyAsync(ctx->flags_host, bad_dev, jobs.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+					CK(cudaStreamSynchronize(st));
+					for (size_t k = 0; k < who.size(); k++) {
+						CompWork *w = who[k]; ImgState &s = S[w->img];
+						if (s.stop) {
+							/* an earlier component of this image already failed: the reference
+							 * would only have de-quantized this one - which the pass just did */
+							w->iterate = false; w->done_clamp = true;
+						} else if (ctx->flags_host[k]) {
+							s.stop = 1; w->iterate = false;               /* falls to the clamp below */
+						}
+					}
+				}
+			}
+			/* ---- smoothing pass, 2627-2640 ---- */
+			for (int clampv = 0; clampv < 2; clampv++) {
+				std::vector<QsJob> jobs; std::vector<CompWork *> who;
+				for (CompWork *w : works) {
+					if (!w->iterate || iter >= w->niter2) continue;
+					int cl = (iter == w->niter2 - 1 && !w->extra) ? 1 : 0;
+					if (cl != clampv) continue;
+					ImgState &s = S[w->img];
+					const uint8_t *p2 = (s.image2 && (flags & QS_JOINT_YUV) && w->ci > 0) ? s.image2 : NULL;
+					jobs.push_back(make_job(*w, p2)); who.push_back(w);
+				}
+				if (jobs.empty()) continue;
+				const QsJob *jd; int tiles;
+				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, st));
+				ctx->launches++;
+				if (clampv) for (CompWork *w : who) w->done_clamp = true;
+			}
+			if (progress && works.size() == 1 && works[0]->iterate && iter < works[0]->niter2) {   /* 2656-2664 */
+				CompWork *w = works[0]; ImgState &s = S[0];
+				int cur = prog_cur += w->H * prog_inc;
+				if (cur >= prog_thr) {
+					CK(cudaStreamSynchronize(st));
+					cur = (int)((int64_t)progprec * cur / prog_max);
+					prog_thr = (int)(((int64_t)(cur + 1) * prog_max + progprec - 1) / progprec);
+					s.stop = progress(userdata, cur, progprec);
+				}
+				if (s.stop) w->iterate = false;
+			}
+		}
+		/* ---- components that left the loop early still get the clamp of 2670-2689 ---- */
+		for (CompWork *w : works) if (!w->done_clamp) {
+			CK(qs_launch_scale_clamp(w->coef_dev, (size_t)w->W * w->H * 64, ctx->quant_dev + w->qslot, 0, 1, st));
+			ctx->launches++; w->done_clamp = true;
+		}
+		/* ---- post steps: chroma up-sampling (2691-2752), luma planes (2753-2815) ---- */
+		for (CompWork *w : works) {
+			ImgState &s = S[w->img]; jpegqs_cuda_image *im = s.im;
+			if (s.stop) continue;
+			if (w->ci > 0 && s.image1 && w->ci <= 2) {
+				int ws = im->comp[0].h_samp, hs = im->comp[0].v_samp;
+				int w1 = (im->image_width + ws - 1) / ws, h1 = (im->image_height + hs - 1) / hs;
+				int W0 = im->comp[0].wblk, H0 = im->comp[0].hblk;
+				uint8_t *mem = s.mem_buf[w->ci - 1];
+				CK(qs_launch_upsample(w->plane, s.image2, QS_PLANE_STRIDE(w->W), s.image1, QS_PLANE_STRIDE(W0),
+						mem, W0 * 8, w1, h1, ws, hs, W0 * 8, H0 * 8, st));
+				CK(qs_launch_fdct_plane(mem, W0 * 8, s.coef_up_dev[w->ci - 1], W0, H0, st));
+				ctx->launches += 2;
+			} else if (w->ci == 0 && s.need_downsample) {
+				int ws = w->c->h_samp, hs = w->c->v_samp;
+				if (ws == 1 && hs == 1) s.image2 = w->plane;
+				else {
+					if (flags & QS_UPSAMPLE_UV) s.image1 = w->plane;
+					int w2 = im->comp[1].wblk * 8, h2 = im->comp[1].hblk * 8;
+					int h1 = (w->H * 8 + hs - 1) / hs;
+					CK(qs_launch_downsample(w->plane, QS_PLANE_STRIDE(w->W), w->W * 8, w->H * 8,
+							s.image2_buf, QS_PLANE_STRIDE(im->comp[1].wblk), w2, h2, ws, hs, 0, -1, h2 + 2, h1, st));
+					ctx->launches++;
+					s.image2 = s.image2_buf;
+				}
+			}
+		}
+	}
+	CK(cudaEventRecord(ctx->ev1, st));
+
+	/* ---- results ---- */
+	for (int n = 0; n < nimg; n++) {
+		ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
+		if (s.skip) continue;
+		bool ups = s.image1 && !s.stop;                                 /* 2834-2849 */
+		for (int ci = 0; ci < im->ncomp; ci++) {
+			CompWork &w = W[n][ci];
+			size_t cb = (size_t)w.W * w.H * 128;
+			if (!on_device && cb) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, st));
+			if (ups && ci >= 1 && ci <= 2 && !on_device) {
+				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk * 128;
+				CK(cudaMemcpyAsync(w.c->coef_up, s.coef_up_dev[ci - 1], yb, cudaMemcpyDeviceToHost, st));
+			}
+			if (w.c->has_qtbl) for (int k = 0; k < 64; k++) w.c->quant[k] = 1;      /* 2851-2859 */
+		}
+		im->upsampled = ups ? 1 : 0;
+		if (ret) ret[n] = s.stop;
+	}
+	CK(cudaStreamSynchronize(st));
+	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	return 0;
+}
+
+extern "C" int jpegqs_cuda_run_host(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *img, int flags, int niter,
+		int progprec, jpegqs_cuda_progress_fn progress, void *userdata) {
+	int ret = 0;
+	if (!ctx) return JPEGQS_ERR_ARG;
+	int rc = run_images(ctx, 1, img, flags, niter, progprec, progress, userdata, false, &ret, ctx->stream);
+	return rc < 0 ? rc : ret;
+}
+
+extern "C" int jpegqs_cuda_run_device(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *img, int flags, int niter,
+		int progprec, jpegqs_cuda_progress_fn progress, void *userdata, void *stream) {
+	int ret = 0;
+	if (!ctx) return JPEGQS_ERR_ARG;
+	int rc = run_images(ctx, 1, img, flags, niter, progprec, progress, userdata, true, &ret,
+			stream ? (cudaStream_t)stream : ctx->stream);
+	return rc < 0 ? rc : ret;
+}
+
+extern "C" int jpegqs_cuda_run_batch(jpegqs_cuda_ctx *ctx, int nimages, jpegqs_cuda_image *imgs, int flags,
+		int niter, int on_device, int *ret, void *stream) {
+	if (!ctx) return JPEGQS_ERR_ARG;
+	return run_images(ctx, nimages, imgs, flags, niter, 0, NULL, NULL, on_device != 0, ret,
+			stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * pass-level entry points
+ * ------------------------------------------------------------------------------------------ */
+static int stage_jobs(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int slot, cudaStream_t st,
+		const QsJob **jd, int *tiles) {
+	if (njobs < 0 || njobs > QS_MAX_JOBS || (njobs && !jobs)) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	if (quant_reserve(ctx, QS_MAX_JOBS)) return JPEGQS_ERR_CUDA;
+	std::vector<QsQuantDev> q(njobs); std::vector<QsJob> v(njobs);
+	for (int i = 0; i < njobs; i++) {
+		int val; quant_prepare(jobs[i].quant, &q[i], &val);
+		QsJob &j = v[i]; memset(&j, 0, sizeof(j));
+		j.coef = jobs[i].coef; j.plane = jobs[i].plane; j.plane2 = jobs[i].plane2;
+		j.quant = ctx->quant_dev + i;
+		j.wblk = jobs[i].wblk; j.hblk = jobs[i].hblk; j.stride = QS_PLANE_STRIDE(j.wblk);
+		j.nblocks = j.wblk * j.hblk; j.luma = jobs[i].luma;
+		j.top_edge = jobs[i].top_edge; j.bottom_edge = jobs[i].bottom_edge;
+	}
+	if (njobs) CK(cudaMemcpyAsync(ctx->quant_dev, q.data(), njobs * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
+	ctx->jobs_cache[slot].clear();
+	return upload_jobs(ctx, slot, v, st, jd, tiles);
+}
+
+extern "C" int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int mode,
+		int *bad, void *stream) {
+	if (!ctx) return JPEGQS_ERR_ARG;
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	const QsJob *jd; int tiles;
+	int rc = stage_jobs(ctx, njobs, jobs, 0, st, &jd, &tiles);
+	if (rc) return rc;
+	int m = ((mode & JPEGQS_PASS_DEQUANT) ? QS_IDCT_DEQUANT : 0) | ((mode & JPEGQS_PASS_CLAMP) ? QS_IDCT_CLAMP : 0);
+	CK(cudaMemsetAsync(ctx->flags_dev, 0, (njobs ? njobs : 1) * sizeof(int), st));
+	CK(qs_launch_idct_pass(jd, njobs, tiles, m, ctx->flags_dev, st));
+	if (bad) {
+		*bad = 0;
+		if (njobs) {
+			CK(cudaMemcpyAsync(ctx->flags_host, ctx->flags_dev, njobs * sizeof(int), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			for (int i = 0; i < njobs; i++) *bad |= ctx->flags_host[i];
+		}
+	}
+	return 0;
+}
+
+extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int flags,
+		int clamp_out, void *stream) {
+	if (!ctx) return JPEGQS_ERR_ARG;
+	if (flags & QS_LOW_QUALITY) return JPEGQS_ERR_UNSUPPORTED;
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	const QsJob *jd; int tiles;
+	int rc = stage_jobs(ctx, njobs, jobs, 1, st, &jd, &tiles);
+	if (rc) return rc;
+	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
+	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, st));
+	return 0;
+}

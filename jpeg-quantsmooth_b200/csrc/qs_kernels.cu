@@ -1,0 +1,832 @@
+/*
+ * qs_kernels.cu - hand-written sm_100a kernels for the jpeg-quantsmooth coefficient
+ * smoothing path.  Compile with -gencode arch=compute_100a,code=sm_100a -fmad=false.
+ *
+ * Mapping: ONE THREAD PER 8x8 BLOCK.  The reference's per-coefficient
+ * sums a2/a3 (reference quantsmooth.h:1517-1545) must be accumulated sequentially in the
+ * scalar loop order with separately rounded mul/add to be bit-exact, so a block is never
+ * split across lanes; a warp runs 32 blocks through the same (coefficient, term) sequence,
+ * which makes every weight-table read warp-uniform (shared-memory broadcast) and keeps all
+ * 32 FP32 lanes busy.  The path is FP32-issue bound, not HBM bound.
+ *
+ * Kernels:
+ *   qs_idct_pass_kernel   dequantize (iteration 0) + islow IDCT -> sample plane + borders
+ *                         (reference quantsmooth.h:2589-2620, idct.h:57-548)
+ *   qs_smooth_kernel      quantsmooth_block for every block of every job
+ *                         (reference quantsmooth.h:564-1849 scalar branches)
+ *   qs_downsample_kernel  box-downsampled luma plane (quantsmooth.h:2753-2815)
+ *   qs_upsample_kernel    upsample_row (quantsmooth.h:1851-2394 scalar branches)
+ *   qs_fdct_plane_kernel  float FDCT of the up-sampled chroma plane (quantsmooth.h:2735-2750)
+ *   qs_scale_clamp_kernel dequantize-only / clamp-only fallbacks (quantsmooth.h:2551-2566, 2670-2689)
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+#include "qs_common.h"
+#include "qs_kernels.h"
+
+__constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
+__constant__ int c_nchunks;
+
+/* ------------------------------------------------------------------------------------------
+ * small helpers
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ int qs_find_job(const QsJob *__restrict__ jobs, int njobs, int tile) {
+	int lo = 0, hi = njobs - 1;
+	while (lo < hi) {                       /* last job with tile_begin <= tile */
+		int mid = (lo + hi + 1) >> 1;
+		if (__ldg(&jobs[mid].tile_begin) <= tile) lo = mid; else hi = mid - 1;
+	}
+	return lo;
+}
+
+/* a0 = round_half_away(c / q) * q  (reference quantsmooth.h:338-341 plain form; the
+ * reference's reciprocal form 324-337 is equal on the valid range).
+ * m31 = ceil(2^31 / q) makes floor((|c| + q/2) / q) one IMAD.HI; exact while
+ * |c| + q/2 < 2^31 / q, i.e. for all q < 2^11 and |c| < 2^16. */
+__host__ __device__ __forceinline__ int qs_orig_coef(int c, int q, uint32_t m31) {
+	uint32_t mag = (uint32_t)(c < 0 ? -c : c) + (uint32_t)(q >> 1);
+#ifdef __CUDA_ARCH__
+	int k = (int)__umulhi(mag << 1, m31);
+#else
+	int k = (int)(((uint64_t)(mag << 1) * m31) >> 32);
+#endif
+	int a0 = k * q;
+	return c < 0 ? -a0 : a0;
+}
+
+extern "C" int qs_host_orig_coef(int c, int q) {
+	uint32_t m31 = (uint32_t)(((1ull << 31) + (uint32_t)q - 1) / (uint32_t)q);
+	return qs_orig_coef(c, q, m31);
+}
+
+/* x86 cvttss2si semantics: NaN / out of range -> INT_MIN */
+__device__ __forceinline__ int qs_cvtt_x86(float x) {
+	return fabsf(x) < 2147483648.0f ? __float2int_rz(x) : INT_MIN;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * integer islow IDCT (reference idct.h:39-89 butterfly, 469-538 passes)
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
+	int z1, z2, z3, z4, z5, e0, e1, e2, e3, t0, t1, t2, t3, a, b;
+	z2 = in[2]; z3 = in[6];
+	z1 = (z2 + z3) * 4433;
+	a = z1 - z3 * 15137; b = z1 + z2 * 6270;
+	t0 = (in[0] + in[4]) << 13; t1 = (in[0] - in[4]) << 13;
+	e0 = t0 + b; e3 = t0 - b; e1 = t1 + a; e2 = t1 - a;
+	t0 = in[7]; t1 = in[5]; t2 = in[3]; t3 = in[1];
+	z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;
+	z5 = (z3 + z4) * 9633;
+	t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
+	z1 *= 7373; z2 *= 20995; z3 *= 16069; z4 *= 3196;
+	z3 = z5 - z3; z4 = z5 - z4;
+	t0 += z3 - z1; t1 += z4 - z2; t2 += z3 - z2; t3 += z4 - z1;
+	out[0] = e0 + t3; out[7] = e0 - t3; out[1] = e1 + t2; out[6] = e1 - t2;
+	out[2] = e2 + t1; out[5] = e2 - t1; out[3] = e3 + t0; out[4] = e3 - t0;
+}
+
+/* second pass over a 64-int workspace (already column-transformed and descaled):
+ * rows -> packed pixels lo[y] = px[y][0..3], hi[y] = px[y][4..7] */
+__device__ __forceinline__ void qs_islow_rows(const int *ws, uint32_t *lo, uint32_t *hi) {
+#pragma unroll
+	for (int y = 0; y < 8; y++) {
+		int o[8];
+		qs_islow_1d(ws + y * 8, o);
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			int v = (o[k] + (257 << 17)) >> 18;
+			o[k] = min(max(v, 0), 255);
+		}
+		lo[y] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+		hi[y] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+	}
+}
+
+/* column x of the block: bytes px[0..3][x], px[4..7][x] */
+__device__ __forceinline__ uint2 qs_gather_col(const uint32_t *w, int byte) {
+	uint32_t s = 0x4440u | (uint32_t)byte | ((uint32_t)(4 + byte) << 4);   /* [w0.b, w1.b, -, -] */
+	uint32_t t01 = __byte_perm(w[0], w[1], s), t23 = __byte_perm(w[2], w[3], s);
+	uint32_t t45 = __byte_perm(w[4], w[5], s), t67 = __byte_perm(w[6], w[7], s);
+	return make_uint2(__byte_perm(t01, t23, 0x5410), __byte_perm(t45, t67, 0x5410));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * float FDCT, order-exact (reference idct.h:608-628 op list, 896-915 passes)
+ * ------------------------------------------------------------------------------------------ */
+#define FA(a, b) __fadd_rn(a, b)
+#define FS(a, b) __fsub_rn(a, b)
+#define FM(a, b) __fmul_rn(a, b)
+
+__device__ __forceinline__ void qs_fdct_1d(const float *in, float *r) {
+	float t0, t1, t2, t3, t4, t5, t6, t7, z1, z2, z3, z4, z5;
+	t0 = FA(in[0], in[7]); t7 = FS(in[0], in[7]);
+	t1 = FA(in[1], in[6]); t6 = FS(in[1], in[6]);
+	t2 = FA(in[2], in[5]); t5 = FS(in[2], in[5]);
+	t3 = FA(in[3], in[4]); t4 = FS(in[3], in[4]);
+	z1 = FA(t0, t3); z4 = FS(t0, t3); z2 = FA(t1, t2); z3 = FS(t1, t2);
+	r[0] = FA(z1, z2); r[4] = FS(z1, z2);
+	z1 = FM(FA(z3, z4), 0.541196100f);
+	r[2] = FA(z1, FM(z4, 0.765366865f));
+	r[6] = FS(z1, FM(z3, 1.847759065f));
+	z1 = FA(t4, t7); z2 = FA(t5, t6); z3 = FA(t4, t6); z4 = FA(t5, t7);
+	z5 = FM(FA(z3, z4), 1.175875602f);
+	t4 = FM(t4, 0.298631336f); t5 = FM(t5, 2.053119869f);
+	t6 = FM(t6, 3.072711026f); t7 = FM(t7, 1.501321110f);
+	z1 = FM(z1, 0.899976223f); z2 = FM(z2, 2.562915447f);
+	z3 = FS(FM(z3, 1.961570560f), z5);
+	z4 = FS(FM(z4, 0.390180644f), z5);
+	r[7] = FS(t4, FA(z1, z3)); r[5] = FS(t5, FA(z2, z4));
+	r[3] = FS(t6, FA(z2, z3)); r[1] = FS(t7, FA(z1, z4));
+}
+
+/* in-place 8x8: columns unscaled, then rows x0.125 */
+__device__ __forceinline__ void qs_fdct_8x8(float *f) {
+#pragma unroll
+	for (int x = 0; x < 8; x++) {
+		float in[8], r[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) in[k] = f[k * 8 + x];
+		qs_fdct_1d(in, r);
+#pragma unroll
+		for (int k = 0; k < 8; k++) f[k * 8 + x] = r[k];
+	}
+#pragma unroll
+	for (int y = 0; y < 8; y++) {
+		float r[8];
+		qs_fdct_1d(f + y * 8, r);
+#pragma unroll
+		for (int k = 0; k < 8; k++) f[y * 8 + k] = FM(r[k], 0.125f);
+	}
+}
+
+/* 3x3 luma/chroma regression, weights 4/2/1 (reference quantsmooth.h:894-913, 2134-2155).
+ * A = down-sampled luma, B = chroma, both pointing at the centre pixel. */
+__device__ __forceinline__ float qs_regress(const uint8_t *__restrict__ A, const uint8_t *__restrict__ B,
+		int stride, int &sA, int &sB) {
+	int a, b, sAA, sAB;
+#define TAP(dx, dy) a = A[(dy) * stride + (dx)]; b = B[(dy) * stride + (dx)]; \
+	sA += a; sAA += a * a; sB += b; sAB += a * b;
+	sA = sB = sAA = sAB = 0;
+	TAP(0, 0) sA *= 2; sB *= 2; sAA *= 2; sAB *= 2;
+	TAP(0, -1) TAP(-1, 0) TAP(1, 0) TAP(0, 1) sA *= 2; sB *= 2; sAA *= 2; sAB *= 2;
+	TAP(-1, -1) TAP(1, -1) TAP(-1, 1) TAP(1, 1)
+#undef TAP
+	sAA = sAA * 16 - sA * sA;
+	sAB = sAB * 16 - sA * sB;
+	float scale = (float)sAA;
+	if (sAA) scale = __fdiv_rn((float)sAB, scale);
+	scale = scale < -16.0f ? -16.0f : scale;
+	scale = scale > 16.0f ? 16.0f : scale;
+	return scale;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K1: IDCT pass.  One thread per block; lanes of a warp own 32 consecutive blocks, so the
+ * eight 8-byte row stores of a warp cover 256 contiguous bytes per pixel row.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) qs_idct_pass_kernel(const QsJob *__restrict__ jobs, int njobs,
+		int total_tiles, int mode, int *__restrict__ bad_flags) {
+	int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (tile >= total_tiles) return;
+	int lane = threadIdx.x & 31;
+	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
+	int b = (tile - job->tile_begin) * 32 + lane;
+	if (b >= job->nblocks) return;
+	int W = job->wblk, H = job->hblk, stride = job->stride;
+	int by = b / W, bx = b - by * W;
+	int16_t *cptr = job->coef + (size_t)b * 64;
+	const QsQuantDev *qd = job->quant;
+
+	int c[64];
+	{
+		const int4 *p = (const int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int4 v = p[j];
+			c[j * 8 + 0] = (short)(v.x & 0xffff); c[j * 8 + 1] = v.x >> 16;
+			c[j * 8 + 2] = (short)(v.y & 0xffff); c[j * 8 + 3] = v.y >> 16;
+			c[j * 8 + 4] = (short)(v.z & 0xffff); c[j * 8 + 5] = v.z >> 16;
+			c[j * 8 + 6] = (short)(v.w & 0xffff); c[j * 8 + 7] = v.w >> 16;
+		}
+	}
+	if (mode & QS_IDCT_DEQUANT) {                       /* quantsmooth.h:2596-2603 */
+		int val = 0;
+#pragma unroll
+		for (int k = 0; k < 64; k++) {
+			int t = c[k] * (int)__ldg(&qd->qraw[k]);
+			val |= t + 0x800;
+			c[k] = (short)t;
+		}
+		if (val >> 12) atomicOr(&bad_flags[job->bad_slot], 1);
+	}
+
+	if (!(mode & QS_IDCT_NOPLANE)) {
+		int ws[64];
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			int in[8], o[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) in[k] = c[k * 8 + x];
+			qs_islow_1d(in, o);
+#pragma unroll
+			for (int k = 0; k < 8; k++) ws[k * 8 + x] = (o[k] + 1024) >> 11;
+		}
+		uint32_t lo[8], hi[8];
+		qs_islow_rows(ws, lo, hi);
+
+		uint8_t *p = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+#pragma unroll
+		for (int y = 0; y < 8; y++) *(uint2 *)(p + (size_t)y * stride) = make_uint2(lo[y], hi[y]);
+		/* replicated borders, quantsmooth.h:2612-2620 */
+		bool left = bx == 0, right = bx == W - 1;
+		if (left) {
+#pragma unroll
+			for (int y = 0; y < 8; y++) p[(size_t)y * stride - 1] = (uint8_t)(lo[y] & 0xff);
+		}
+		if (right) {
+#pragma unroll
+			for (int y = 0; y < 8; y++) p[(size_t)y * stride + 8] = (uint8_t)(hi[y] >> 24);
+		}
+		if (by == 0 && job->top_edge) {
+			uint8_t *r = p - stride;
+			*(uint2 *)r = make_uint2(lo[0], hi[0]);
+			if (left) r[-1] = (uint8_t)(lo[0] & 0xff);
+			if (right) r[8] = (uint8_t)(hi[0] >> 24);
+		}
+		if (by == H - 1 && job->bottom_edge) {
+			uint8_t *r = p + (size_t)8 * stride;
+			*(uint2 *)r = make_uint2(lo[7], hi[7]);
+			if (left) r[-1] = (uint8_t)(lo[7] & 0xff);
+			if (right) r[8] = (uint8_t)(hi[7] >> 24);
+		}
+	}
+
+	if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {
+		if (mode & QS_IDCT_CLAMP) {                     /* quantsmooth.h:2670-2689 */
+#pragma unroll
+			for (int k = 0; k < 64; k++) c[k] = min(max(c[k], -1023), 1023);
+		}
+		int4 *p = (int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int4 v;
+			v.x = (c[j * 8 + 0] & 0xffff) | (c[j * 8 + 1] << 16);
+			v.y = (c[j * 8 + 2] & 0xffff) | (c[j * 8 + 3] << 16);
+			v.z = (c[j * 8 + 4] & 0xffff) | (c[j * 8 + 5] << 16);
+			v.w = (c[j * 8 + 6] & 0xffff) | (c[j * 8 + 7] << 16);
+			p[j] = v;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2: the smoothing pass.
+ *
+ * Persistent CTAs (one per SM, 16 warps), dynamic tile scheduler (one atomic per 32-block
+ * tile).  Shared memory: the weight tables (40 KB, or 68 KB with DIAGONALS; read with
+ * warp-uniform LDS.128 = broadcast) + per warp a private 7.5 KB region holding, for each of
+ * the 32 lanes' blocks, the 64 coefficients (packed int16 pairs) and 14 packed 8-pixel words:
+ *   words 0-7  rows of the block's current pixels ("buf", quantsmooth.h:1408)
+ *   word  8/9  column 0 / column 7 of the block
+ *   word 10-13 the 8 neighbour pixels above / below / left / right ("border", 1396-1401)
+ * All per-lane arrays are [item][lane] so lanes hit consecutive banks.
+ *
+ * Exact rescaling: a pixel byte p is turned into the float 1 + p*2^-15 by one PRMT, so a
+ * difference of two of them is d*2^-15 exactly; with R' = 2q*2^-15 the clamp max(R-|d|,0)
+ * becomes ONE add.sat (result < 1, so only the lower clamp acts).  Squares and products
+ * carry pure power-of-two factors which commute with IEEE rounding (no overflow/underflow
+ * in range); the weight table is pre-multiplied by 2^30 so a1 and a3 are
+ * bit-identical to the reference's, a2 comes out scaled by 2^-45 and is rescaled (exactly)
+ * after the division.  Per (term, coefficient): 1 FADD.SAT + 5 FMUL + 2 FADD, no FMA.
+ * ------------------------------------------------------------------------------------------ */
+#define QS_SMOOTH_THREADS 512
+#define QS_WARP_WORDS (32 * 32 + 14 * 32 * 2)     /* uint32 words per warp region */
+
+__device__ __forceinline__ float qs_px(uint32_t w, int j) {
+	return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(j << 4)));
+}
+__device__ __forceinline__ void qs_unpack8(uint2 w, float *f) {
+	f[0] = qs_px(w.x, 0); f[1] = qs_px(w.x, 1); f[2] = qs_px(w.x, 2); f[3] = qs_px(w.x, 3);
+	f[4] = qs_px(w.y, 0); f[5] = qs_px(w.y, 1); f[6] = qs_px(w.y, 2); f[7] = qs_px(w.y, 3);
+}
+
+/* CORE of reference quantsmooth.h:1519-1520 on scaled operands; nad = -|ds| */
+__device__ __forceinline__ void qs_term(float ds, float nad, float w, float Rs, float &a2, float &a3) {
+	float t;
+	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(t) : "f"(Rs), "f"(nad));
+	t = FM(t, t);
+	float a0 = FM(ds, t);
+	float a1 = FM(w, t);
+	a2 = FA(a2, FM(a0, a1));
+	a3 = FA(a3, FM(a1, a1));
+}
+
+template <int N, int NT>
+__device__ __forceinline__ void qs_terms_row(const float *d, const float *const *tab, int off,
+		const float *Rs, float *a2, float *a3) {
+	float nad[8];
+#pragma unroll
+	for (int x = 0; x < NT; x++) nad[x] = -fabsf(d[x]);
+#pragma unroll
+	for (int c = 0; c < N; c++) {
+		float4 wa = *(const float4 *)(tab[c] + off), wb = *(const float4 *)(tab[c] + off + 4);
+		float w[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
+#pragma unroll
+		for (int x = 0; x < NT; x++) qs_term(d[x], nad[x], w[x], Rs[c], a2[c], a3[c]);
+	}
+}
+
+/* horizontal pairs, quantsmooth.h:1527 */
+template <int N>
+__device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *tab, const float *Rs,
+		float *a2, float *a3) {
+#pragma unroll 1
+	for (int y = 0; y < 8; y++) {
+		float f[8], d[8];
+		qs_unpack8(pw[y * 32], f);
+#pragma unroll
+		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
+		qs_terms_row<N, 7>(d, tab, y * 8, Rs, a2, a3);
+	}
+}
+
+/* top, bottom, left, right border pairs, quantsmooth.h:1529-1530 */
+template <int N>
+__device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *const *tab, const float *Rs,
+		float *a2, float *a3) {
+#pragma unroll 1
+	for (int s = 0; s < 4; s++) {
+		int wa = s == 0 ? 0 : s == 1 ? 7 : 6 + s;       /* row 0, row 7, col 0 (8), col 7 (9) */
+		float fa[8], fb[8], d[8];
+		qs_unpack8(pw[wa * 32], fa);
+		qs_unpack8(pw[(10 + s) * 32], fb);
+#pragma unroll
+		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
+		qs_terms_row<N, 8>(d, tab, 64 + s * 8, Rs, a2, a3);
+	}
+}
+
+/* vertical pairs, quantsmooth.h:1531 */
+template <int N>
+__device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *tab, const float *Rs,
+		float *a2, float *a3) {
+	float fp[8];
+	qs_unpack8(pw[0], fp);
+#pragma unroll 1
+	for (int y = 0; y < 7; y++) {
+		float fn[8], d[8];
+		qs_unpack8(pw[(y + 1) * 32], fn);
+#pragma unroll
+		for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
+		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3);
+	}
+}
+
+/* diagonal pairs, quantsmooth.h:1533-1540: per (y,x) first "\" then "/" */
+template <int N>
+__device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const *tab, const float *Rs,
+		float *a2, float *a3) {
+	float fp[8];
+	qs_unpack8(pw[0], fp);
+#pragma unroll 1
+	for (int y = 0; y < 7; y++) {
+		float fn[8], d1[8], d2[8], n1[8], n2[8];
+		qs_unpack8(pw[(y + 1) * 32], fn);
+#pragma unroll
+		for (int x = 0; x < 7; x++) {
+			d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]);
+			n1[x] = -fabsf(d1[x]); n2[x] = -fabsf(d2[x]);
+		}
+#pragma unroll
+		for (int x = 0; x < 8; x++) fp[x] = fn[x];
+#pragma unroll
+		for (int c = 0; c < N; c++) {
+			const float *t = tab[c] + 160 + y * 16;
+			float4 wa = *(const float4 *)t, wb = *(const float4 *)(t + 4);
+			float4 wc = *(const float4 *)(t + 8), wd = *(const float4 *)(t + 12);
+			float w1[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
+			float w2[8] = { wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w };
+#pragma unroll
+			for (int x = 0; x < 7; x++) {
+				qs_term(d1[x], n1[x], w1[x], Rs[c], a2[c], a3[c]);
+				qs_term(d2[x], n2[x], w2[x], Rs[c], a2[c], a3[c]);
+			}
+		}
+	}
+}
+
+/* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
+__device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const QsQuantDev *__restrict__ qd,
+		uint16_t *cs) {
+	float qv = FM(__fdiv_rn(a2s, a3), 35184372088832.0f);      /* * 2^45, exact */
+	int r = qs_cvtt_x86(roundf(qv));
+	if (r) {
+		uint16_t *slot = cs + (i >> 1) * 64 + (i & 1);
+		int c = (short)*slot;
+		int q = __ldg(&qd->q[i]);
+		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[i]));
+		int d0 = (q - 1) >> 1, d1 = q >> 1;
+		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
+		int add = (int)((unsigned)c - (unsigned)r);
+		add = min(add, dh); add = max(add, dl);
+		*slot = (uint16_t)add;
+	}
+}
+
+template <int N, bool DIAG>
+__device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
+		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	const float *tab[N]; float Rs[N], a2[N], a3[N];
+	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+#pragma unroll
+	for (int c = 0; c < N; c++) {
+		int i = ch.idx[c];
+		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
+	}
+	qs_sec_h<N>(pw, tab, Rs, a2, a3);
+	qs_sec_border<N>(pw, tab, Rs, a2, a3);
+	qs_sec_v<N>(pw, tab, Rs, a2, a3);
+	if (DIAG) qs_sec_diag<N>(pw, tab, Rs, a2, a3);
+#pragma unroll
+	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+}
+
+/* the two edge coefficients of an anti-diagonal: idx[0] lies in row 0 (i <= 7: no vertical
+ * terms), idx[1] in column 0 (i & 7 == 0: no horizontal terms) */
+template <bool DIAG>
+__device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *tabs, const uint2 *pw,
+		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	const float *tab[2]; float Rs[2], a2[2], a3[2];
+	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+#pragma unroll
+	for (int c = 0; c < 2; c++) {
+		int i = ch.idx[c];
+		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
+	}
+	qs_sec_h<1>(pw, tab, Rs, a2, a3);
+	qs_sec_border<2>(pw, tab, Rs, a2, a3);
+	qs_sec_v<1>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
+	if (DIAG) qs_sec_diag<2>(pw, tab, Rs, a2, a3);
+#pragma unroll
+	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+}
+
+/* IDCT of the lane's block from shared coefficients into the shared pixel words */
+__device__ __forceinline__ void qs_refresh(const uint32_t *cw, uint2 *pw) {
+	int ws[64];
+#pragma unroll
+	for (int xp = 0; xp < 4; xp++) {
+		int a[8], b[8], oa[8], ob[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			uint32_t w = cw[(k * 4 + xp) * 32];
+			a[k] = (short)(w & 0xffff); b[k] = (int)w >> 16;
+		}
+		qs_islow_1d(a, oa); qs_islow_1d(b, ob);
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			ws[k * 8 + 2 * xp] = (oa[k] + 1024) >> 11;
+			ws[k * 8 + 2 * xp + 1] = (ob[k] + 1024) >> 11;
+		}
+	}
+	uint32_t lo[8], hi[8];
+	qs_islow_rows(ws, lo, hi);
+#pragma unroll
+	for (int y = 0; y < 8; y++) pw[y * 32] = make_uint2(lo[y], hi[y]);
+	pw[8 * 32] = qs_gather_col(lo, 0);
+	pw[9 * 32] = qs_gather_col(hi, 3);
+}
+
+/* JOINT_YUV chroma predictor + fdct_clamp, quantsmooth.h:577-579, 894-921, 551-561 */
+__device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, const uint8_t *__restrict__ img2,
+		int stride, const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	float f[64];
+#pragma unroll
+	for (int y = 0; y < 8; y++) {
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			int sA, sB;
+			const uint8_t *A = img2 + y * stride + x, *B = img + y * stride + x;
+			float scale = qs_regress(A, B, stride, sA, sB);
+			float a = FM(FA(FM((float)((int)A[0] * 16 - sA), scale), (float)sB), 1.0f / 16);
+			a = FS(a < 0 ? 0.0f : a, 128.0f);
+			f[y * 8 + x] = a > 128.0f ? 128.0f : a;
+		}
+	}
+	qs_fdct_8x8(f);
+#pragma unroll
+	for (int x = 0; x < 64; x++) {
+		uint16_t *slot = cs + (x >> 1) * 64 + (x & 1);
+		int c = (short)*slot;
+		int q = __ldg(&qd->q[x]);
+		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[x]));
+		int d0 = (q - 1) >> 1, d1 = q >> 1;
+		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
+		int add = qs_cvtt_x86(roundf(f[x]));
+		add = min(add, dh); add = max(add, dl);
+		*slot = (uint16_t)add;
+	}
+}
+
+/* rebalance, quantsmooth.h:1566-1568, 1823-1848 */
+__device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	long long m0 = 0, m1 = 0;
+#pragma unroll 1
+	for (int k = 1; k < 64; k++) {
+		int c = (short)cs[(k >> 1) * 64 + (k & 1)];
+		int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
+		m0 += c * a0; m1 += a0 * a0;
+	}
+	if (m1 > m0 && m0 != 0) {
+		int mul = (int)(((m1 << 13) + (m0 >> 1)) / m0);
+#pragma unroll 1
+		for (int k = 1; k < 64; k++) {
+			uint16_t *slot = cs + (k >> 1) * 64 + (k & 1);
+			int c = (short)*slot;
+			int q = __ldg(&qd->q[k]);
+			int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[k]));
+			int d0 = (q - 1) >> 1, d1 = q >> 1;
+			int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
+			int add = (int)((unsigned)c * (unsigned)mul + 0x1000u) >> 13;
+			add = min(add, dh); add = max(add, dl);
+			*slot = (uint16_t)add;
+		}
+	}
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
+		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
+		int flags, int clamp_out) {
+	extern __shared__ __align__(16) uint32_t smem[];
+	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+	float *tabs = (float *)smem;
+	{
+		const float4 *src = (const float4 *)tables_g; float4 *dst = (float4 *)tabs;
+		for (int i = threadIdx.x; i < 64 * TS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+	}
+	__syncthreads();
+	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
+	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
+	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
+	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
+
+	for (;;) {
+		int tile = 0;
+		if (lane == 0) tile = atomicAdd(tile_counter, 1);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if (tile >= total_tiles) break;
+		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
+		int nblocks = job->nblocks;
+		int b = (tile - job->tile_begin) * 32 + lane;
+		bool valid = b < nblocks;
+		if (!valid) b = nblocks - 1;                    /* idle lanes shadow the last block */
+		int W = job->wblk, stride = job->stride;
+		int by = b / W, bx = b - by * W;
+		int16_t *cptr = job->coef + (size_t)b * 64;
+		const QsQuantDev *qd = job->quant;
+		const uint8_t *img = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+
+		{
+			const int4 *p = (const int4 *)cptr;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int4 v = p[j];
+				cw[(j * 4 + 0) * 32] = v.x; cw[(j * 4 + 1) * 32] = v.y;
+				cw[(j * 4 + 2) * 32] = v.z; cw[(j * 4 + 3) * 32] = v.w;
+			}
+		}
+		if (job->plane2) {
+			const uint8_t *img2 = job->plane2 + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+			qs_joint_predict(img, img2, stride, qd, cs);
+		}
+		{                                               /* border, quantsmooth.h:1396-1401 */
+			pw[10 * 32] = *(const uint2 *)(img - stride);
+			pw[11 * 32] = *(const uint2 *)(img + (size_t)8 * stride);
+			uint32_t l0 = 0, l1 = 0, r0 = 0, r1 = 0;
+#pragma unroll
+			for (int y = 0; y < 4; y++) {
+				l0 |= (uint32_t)img[(size_t)y * stride - 1] << (8 * y);
+				l1 |= (uint32_t)img[(size_t)(y + 4) * stride - 1] << (8 * y);
+				r0 |= (uint32_t)img[(size_t)y * stride + 8] << (8 * y);
+				r1 |= (uint32_t)img[(size_t)(y + 4) * stride + 8] << (8 * y);
+			}
+			pw[12 * 32] = make_uint2(l0, l1);
+			pw[13 * 32] = make_uint2(r0, r1);
+		}
+
+		int nch = c_nchunks;
+#pragma unroll 1
+		for (int ci = 0; ci < nch; ci++) {
+			QsChunk ch = c_chunks[ci];
+			/* the reference re-renders only if a coefficient changed (need_refresh); an
+			 * unconditional refresh at each anti-diagonal start is value-identical */
+			if (ch.first) qs_refresh(cw, pw);
+			if (ch.type) qs_chunk_edge<DIAG>(ch, tabs, pw, qd, cs);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG>(ch, tabs, pw, qd, cs);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG>(ch, tabs, pw, qd, cs);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG>(ch, tabs, pw, qd, cs);
+			else qs_chunk_full<1, DIAG>(ch, tabs, pw, qd, cs);
+		}
+
+		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
+			qs_rebalance(qd, cs);
+
+		if (valid) {
+			int4 *p = (int4 *)cptr;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				uint32_t w[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					w[k] = cw[(j * 4 + k) * 32];
+					if (clamp_out) {                    /* quantsmooth.h:2670-2689 */
+						int a = (short)(w[k] & 0xffff), c2 = (int)w[k] >> 16;
+						a = min(max(a, -1023), 1023); c2 = min(max(c2, -1023), 1023);
+						w[k] = (uint32_t)(a & 0xffff) | ((uint32_t)c2 << 16);
+					}
+				}
+				p[j] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+			}
+		}
+		__syncwarp();
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * dequantize-only / clamp-only fallbacks (quantsmooth.h:2551-2566, 2670-2689)
+ * ------------------------------------------------------------------------------------------ */
+__global__ void qs_scale_clamp_kernel(int16_t *__restrict__ coef, size_t n, const QsQuantDev *__restrict__ qd,
+		int dequant, int clamp) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	size_t step = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += step) {
+		int c = coef[i];
+		if (dequant) c = (short)(c * (int)__ldg(&qd->qraw[i & 63]));
+		if (clamp) c = min(max(c, -1023), 1023);
+		coef[i] = (int16_t)c;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * down-sampled luma plane with replicated borders, quantsmooth.h:2753-2815.
+ * One thread per output pixel of the PADDED destination plane (incl. borders), so border
+ * replication needs no second pass: every thread clamps its source coordinates.
+ * src: Y plane (w = W*8, h = H*8 valid pixels).  dst: (w2+2) x (h2+2) with w2/h2 = chroma
+ * plane size; valid area w1 x h1 = ceil(w/ws) x ceil(h/hs).
+ * ------------------------------------------------------------------------------------------ */
+__global__ void qs_downsample_kernel(const uint8_t *__restrict__ src, int sstride, int w, int h,
+		uint8_t *__restrict__ dst, int dstride, int w2, int h2, int ws, int hs,
+		int src_row0, int dst_row_first, int dst_rows, int h1_total) {
+	/* rows are expressed in destination-plane coordinates (-1 .. h2) of the whole component;
+	 * this launch renders rows [dst_row_first, dst_row_first + dst_rows) from a source slab
+	 * whose first pixel row is src_row0 (multi-GPU slabs); single GPU: src_row0 = 0. */
+	int x = blockIdx.x * blockDim.x + threadIdx.x - 1;
+	int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x > w2 || yy >= dst_rows) return;
+	int y = dst_row_first + yy;
+	int w1 = (w + ws - 1) / ws;
+	int cx = min(max(x, 0), w1 - 1), cy = min(max(y, 0), h1_total - 1);
+	int hh2 = min(hs, h - cy * hs), ww2 = min(ws, w - cx * ws);
+	const uint8_t *p = src + (size_t)(cy * hs - src_row0 + 1) * sstride + QS_PLANE_PAD + cx * ws;
+	int sum = 0;
+	for (int j = 0; j < hh2; j++) for (int i = 0; i < ww2; i++) sum += p[(size_t)j * sstride + i];
+	int div = ww2 * hh2;
+	dst[(size_t)(yy) * dstride + QS_PLANE_PAD + x] = (uint8_t)((sum + div / 2) / div);
+	(void)h2;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * upsample_row, quantsmooth.h:2134-2158 (scale) + 2364-2389 (emit); one thread per chroma
+ * pixel, writes ws x hs output pixels.  Edge replication of 2390-2393 / 2729-2730 is done
+ * by clamping coordinates: one thread per OUTPUT-plane "cell" (x < wcells, y < hcells)
+ * where cells beyond (w1, h1) replicate the last column / row.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void qs_upsample_kernel(const uint8_t *__restrict__ C, const uint8_t *__restrict__ Yd, int cstride,
+		const uint8_t *__restrict__ Yf, int ystride, uint8_t *__restrict__ out, int ostride,
+		int w1, int h1, int ws, int hs, int ww, int hh) {
+	int ox = blockIdx.x * blockDim.x + threadIdx.x;     /* output pixel */
+	int oy = blockIdx.y * blockDim.y + threadIdx.y;
+	if (ox >= ww || oy >= hh) return;
+	int sx = min(ox, w1 * ws - 1), sy = min(oy, h1 * hs - 1);
+	int x = sx / ws, y = sy / hs;
+	const uint8_t *pc = C + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
+	const uint8_t *pd = Yd + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
+	int sA, sB;
+	float scale = qs_regress(pd, pc, cstride, sA, sB);
+	float offset = FA(FS((float)pc[0], FM((float)pd[0], scale)), 0.5f);
+	float yv = (float)Yf[(size_t)(sy + 1) * ystride + QS_PLANE_PAD + sx];
+	int a = qs_cvtt_x86(FA(FM(yv, scale), offset));
+	out[(size_t)oy * ostride + ox] = (uint8_t)min(max(a, 0), 255);
+}
+
+/* FDCT of the up-sampled plane into new coefficient arrays, quantsmooth.h:2735-2750 */
+__global__ void qs_fdct_plane_kernel(const uint8_t *__restrict__ px, int pstride, int16_t *__restrict__ coef,
+		int W, int nblocks) {
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= nblocks) return;
+	int by = b / W, bx = b - by * W;
+	const uint8_t *p = px + (size_t)by * 8 * pstride + bx * 8;
+	float f[64];
+#pragma unroll
+	for (int y = 0; y < 8; y++) {
+		uint2 w = *(const uint2 *)(p + (size_t)y * pstride);
+#pragma unroll
+		for (int x = 0; x < 4; x++) {
+			f[y * 8 + x] = (float)((int)((w.x >> (8 * x)) & 0xff) - 128);
+			f[y * 8 + 4 + x] = (float)((int)((w.y >> (8 * x)) & 0xff) - 128);
+		}
+	}
+	qs_fdct_8x8(f);
+	int4 *o = (int4 *)(coef + (size_t)b * 64);
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		int c[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) c[k] = (short)qs_cvtt_x86(roundf(f[j * 8 + k]));
+		o[j] = make_int4((c[0] & 0xffff) | (c[1] << 16), (c[2] & 0xffff) | (c[3] << 16),
+				(c[4] & 0xffff) | (c[5] << 16), (c[6] & 0xffff) | (c[7] << 16));
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * launch wrappers
+ * ------------------------------------------------------------------------------------------ */
+cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
+	cudaError_t e = cudaMemcpyToSymbol(c_chunks, chunks, sizeof(QsChunk) * n);
+	if (e != cudaSuccess) return e;
+	return cudaMemcpyToSymbol(c_nchunks, &n, sizeof(int));
+}
+
+size_t qs_smooth_smem_bytes(int diag) {
+	return (size_t)64 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 +
+			(size_t)(QS_SMOOTH_THREADS / 32) * QS_WARP_WORDS * 4;
+}
+
+cudaError_t qs_smooth_configure(void) {
+	cudaError_t e = cudaFuncSetAttribute(qs_smooth_kernel<false>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(0));
+	if (e != cudaSuccess) return e;
+	return cudaFuncSetAttribute(qs_smooth_kernel<true>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(1));
+}
+
+cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
+		int *bad_flags, cudaStream_t st) {
+	if (total_tiles <= 0) return cudaSuccess;
+	int wpb = 256 / 32;
+	qs_idct_pass_kernel<<<(total_tiles + wpb - 1) / wpb, 256, 0, st>>>(jobs_dev, njobs, total_tiles, mode, bad_flags);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
+		int *tile_counter, int flags, int clamp_out, int num_sms, cudaStream_t st) {
+	if (total_tiles <= 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
+	if (e != cudaSuccess) return e;
+	int warps = QS_SMOOTH_THREADS / 32;
+	int grid = (total_tiles + warps - 1) / warps;
+	if (grid > num_sms) grid = num_sms;
+	if (flags & QS_DIAGONALS)
+		qs_smooth_kernel<true><<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(1), st>>>(
+				jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+	else
+		qs_smooth_kernel<false><<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(0), st>>>(
+				jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_scale_clamp(int16_t *coef, size_t n, const QsQuantDev *qd, int dequant, int clamp,
+		cudaStream_t st) {
+	if (!n) return cudaSuccess;
+	size_t blocks = (n + 255) / 256;
+	if (blocks > 148 * 16) blocks = 148 * 16;
+	qs_scale_clamp_kernel<<<(unsigned)blocks, 256, 0, st>>>(coef, n, qd, dequant, clamp);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride,
+		int w2, int h2, int ws, int hs, int src_row0, int dst_row_first, int dst_rows, int h1_total,
+		cudaStream_t st) {
+	dim3 blk(64, 4), grd((w2 + 2 + 63) / 64, (dst_rows + 3) / 4);
+	/* dst points at the plane row that holds destination row dst_row_first */
+	qs_downsample_kernel<<<grd, blk, 0, st>>>(src, sstride, w, h, dst, dstride, w2, h2, ws, hs,
+			src_row0, dst_row_first, dst_rows, h1_total);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_upsample(const uint8_t *C, const uint8_t *Yd, int cstride, const uint8_t *Yf, int ystride,
+		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, cudaStream_t st) {
+	dim3 blk(64, 4), grd((ww + 63) / 64, (hh + 3) / 4);
+	qs_upsample_kernel<<<grd, blk, 0, st>>>(C, Yd, cstride, Yf, ystride, out, ostride, w1, h1, ws, hs, ww, hh);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_fdct_plane(const uint8_t *px, int pstride, int16_t *coef, int W, int H, cudaStream_t st) {
+	int n = W * H;
+	if (!n) return cudaSuccess;
+	qs_fdct_plane_kernel<<<(n + 127) / 128, 128, 0, st>>>(px, pstride, coef, W, n);
+	return cudaGetLastError();
+}

@@ -1,0 +1,23 @@
+/* launch wrappers implemented in qs_kernels.cu (internal, C++ linkage) */
+#ifndef QS_KERNELS_H
+#define QS_KERNELS_H
+#include <cuda_runtime.h>
+#include "qs_common.h"
+
+cudaError_t qs_set_chunks(const QsChunk *chunks, int n);
+size_t qs_smooth_smem_bytes(int diag);
+cudaError_t qs_smooth_configure(void);
+cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
+		int *bad_flags, cudaStream_t st);
+cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
+		int *tile_counter, int flags, int clamp_out, int num_sms, cudaStream_t st);
+cudaError_t qs_launch_scale_clamp(int16_t *coef, size_t n, const QsQuantDev *qd, int dequant, int clamp,
+		cudaStream_t st);
+cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride,
+		int w2, int h2, int ws, int hs, int src_row0, int dst_row_first, int dst_rows, int h1_total,
+		cudaStream_t st);
+cudaError_t qs_launch_upsample(const uint8_t *C, const uint8_t *Yd, int cstride, const uint8_t *Yf, int ystride,
+		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, cudaStream_t st);
+cudaError_t qs_launch_fdct_plane(const uint8_t *px, int pstride, int16_t *coef, int W, int H, cudaStream_t st);
+extern "C" int qs_host_orig_coef(int c, int q);
+#endif

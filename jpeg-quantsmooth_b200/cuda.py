@@ -1,0 +1,320 @@
+"""ctypes binding of the C ABI in include/jpegqs_cuda.h (csrc/libjpegqs_b200.so) and the
+Python mirror of the reference's public call for this path:
+
+    ret, out = do_quantsmooth(image, flags, niter)      # reference libjpegqs.h:47-48
+
+`image` is the flat equivalent of (j_decompress_ptr, coef_arrays) - see image.py.
+There is no CPU fallback: a missing library or device raises QsError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .image import CoefImage, JCS_YCbCr
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_COMP = 10
+
+
+class QsError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "csrc", "libjpegqs_b200.so")
+
+
+class _Comp(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("wblk", C.c_uint32), ("hblk", C.c_uint32),
+                ("h_samp", C.c_int32), ("v_samp", C.c_int32), ("has_qtbl", C.c_int32),
+                ("quant", C.c_uint16 * 64), ("coef_up", C.c_void_p)]
+
+
+class _Image(C.Structure):
+    _fields_ = [("ncomp", C.c_int32), ("is_ycbcr", C.c_int32),
+                ("image_width", C.c_uint32), ("image_height", C.c_uint32),
+                ("comp", _Comp * MAX_COMP), ("upsampled", C.c_int32)]
+
+
+class _Job(C.Structure):
+    _fields_ = [("coef", C.c_void_p), ("plane", C.c_void_p), ("plane2", C.c_void_p),
+                ("wblk", C.c_uint32), ("hblk", C.c_uint32), ("quant", C.c_uint16 * 64),
+                ("luma", C.c_int32), ("top_edge", C.c_int32), ("bottom_edge", C.c_int32)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
+PASS_DEQUANT, PASS_CLAMP = 1, 2
+
+_lib = None
+
+
+def load():
+    """Load the CUDA extension; raises QsError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise QsError(f"{p} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU fallback)")
+    lib = C.CDLL(p)
+    lib.jpegqs_cuda_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.jpegqs_cuda_destroy.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_last_error.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_last_error.restype = C.c_char_p
+    lib.jpegqs_cuda_device_name.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_device_name.restype = C.c_char_p
+    lib.jpegqs_cuda_last_device_ms.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_last_device_ms.restype = C.c_float
+    lib.jpegqs_cuda_last_launches.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_host_alloc.argtypes = [C.c_size_t]
+    lib.jpegqs_cuda_host_alloc.restype = C.c_void_p
+    lib.jpegqs_cuda_host_free.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_run_host.argtypes = [C.c_void_p, C.POINTER(_Image), C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p]
+    lib.jpegqs_cuda_run_device.argtypes = [C.c_void_p, C.POINTER(_Image), C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.jpegqs_cuda_run_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Image), C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(C.c_int), C.c_void_p]
+    lib.jpegqs_cuda_plane_bytes.argtypes = [C.c_uint32, C.c_uint32]
+    lib.jpegqs_cuda_plane_bytes.restype = C.c_size_t
+    lib.jpegqs_cuda_plane_stride.argtypes = [C.c_uint32]
+    lib.jpegqs_cuda_pass_idct.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Job), C.c_int,
+                                          C.POINTER(C.c_int), C.c_void_p]
+    lib.jpegqs_cuda_pass_smooth.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Job), C.c_int, C.c_int,
+                                            C.c_void_p]
+    lib.jpegqs_cuda_tables.argtypes = [C.c_int, C.c_void_p]
+    lib.jpegqs_cuda_orig_coef.argtypes = [C.c_int, C.c_int]
+    _lib = lib
+    return lib
+
+
+def tables(flags: int) -> np.ndarray:
+    """The weight tables the device uses (un-scaled), [64, 160|272] float32.  Host-only."""
+    size = 272 if flags & 1 else 160
+    out = np.zeros((64, size), dtype=np.float32)
+    load().jpegqs_cuda_tables(flags, out.ctypes.data)
+    return out
+
+
+def orig_coef(coef: int, q: int) -> int:
+    return load().jpegqs_cuda_orig_coef(coef, q)
+
+
+class PinnedArray:
+    """int16 numpy view over pinned host memory from jpegqs_cuda_host_alloc."""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape)) * 2
+        self._lib = load()
+        self._p = self._lib.jpegqs_cuda_host_alloc(max(n, 1))
+        if not self._p:
+            raise QsError("cudaMallocHost failed")
+        buf = (C.c_int16 * (n // 2)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=np.int16).reshape(shape)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            self._lib.jpegqs_cuda_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _fill_image(ci: _Image, image: CoefImage, coef_ptrs: Sequence[int], up_ptrs: Sequence[Optional[int]]):
+    ci.ncomp = len(image.comps)
+    ci.is_ycbcr = int(image.colorspace == JCS_YCbCr)
+    ci.image_width, ci.image_height = image.width, image.height
+    for i, c in enumerate(image.comps):
+        cc = ci.comp[i]
+        cc.coef = coef_ptrs[i]
+        cc.wblk, cc.hblk, cc.h_samp, cc.v_samp = c.wblk, c.hblk, c.h_samp, c.v_samp
+        cc.has_qtbl = int(c.quant is not None)
+        if c.quant is not None:
+            for k in range(64):
+                cc.quant[k] = int(c.quant[k])
+        cc.coef_up = up_ptrs[i] if i < len(up_ptrs) and up_ptrs[i] else None
+
+
+class QsContext:
+    """One device context (stream, tables, scratch arena).  Mirrors the process-wide state
+    the reference keeps implicitly (its tables are rebuilt per call, quantsmooth.h:2460-2464)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.jpegqs_cuda_create(device, C.byref(h))
+        if rc:
+            raise QsError(f"jpegqs_cuda_create failed ({rc}): "
+                          f"{self.lib.jpegqs_cuda_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jpegqs_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise QsError(f"CUDA back end error {rc}: {self.lib.jpegqs_cuda_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def device_name(self) -> str:
+        return self.lib.jpegqs_cuda_device_name(self.h).decode()
+
+    @property
+    def last_device_ms(self) -> float:
+        return float(self.lib.jpegqs_cuda_last_device_ms(self.h))
+
+    @property
+    def last_launches(self) -> int:
+        return int(self.lib.jpegqs_cuda_last_launches(self.h))
+
+    # ---- whole image, host buffers (the call a user of the reference makes) ----
+    def do_quantsmooth(self, image: CoefImage, flags: int, niter: int, progprec: int = 0,
+                       progress=None, inplace: bool = False):
+        out = image if inplace else image.clone()
+        keep = []
+        ptrs, ups = [], []
+        for c in out.comps:
+            c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+            ptrs.append(c.coef.ctypes.data)
+        up_arrays = []
+        if len(out.comps) >= 3:
+            y = out.comps[0]
+            ups.append(None)
+            for _ in range(2):
+                a = np.zeros((y.hblk, y.wblk, 64), dtype=np.int16)
+                up_arrays.append(a)
+                ups.append(a.ctypes.data)
+        ci = _Image()
+        _fill_image(ci, out, ptrs, ups)
+        cb = None
+        if progress is not None:
+            cb = PROGRESS_FN(lambda d, cur, mx: int(progress(cur, mx)))
+            keep.append(cb)
+        ret = self._check(self.lib.jpegqs_cuda_run_host(
+            self.h, C.byref(ci), flags & 0x7f, niter, progprec,
+            C.cast(cb, C.c_void_p) if cb else None, None))
+        self._collect(out, ci, up_arrays)
+        return ret, out
+
+    @staticmethod
+    def _collect(out: CoefImage, ci: _Image, up_arrays):
+        for i, c in enumerate(out.comps):
+            if ci.upsampled and i in (1, 2):
+                c.coef = up_arrays[i - 1]
+            if ci.upsampled:
+                c.h_samp = c.v_samp = 1
+            if c.quant is not None:
+                c.quant = np.array(list(ci.comp[i].quant), dtype=np.uint16)
+
+    def run_batch_host(self, images: List[CoefImage], flags: int, niter: int):
+        outs = [im.clone() for im in images]
+        arr = (_Image * len(outs))()
+        ups_all = []
+        for n, out in enumerate(outs):
+            ptrs, ups, up_arrays = [], [], []
+            for c in out.comps:
+                c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+                ptrs.append(c.coef.ctypes.data)
+            if len(out.comps) >= 3:
+                y = out.comps[0]
+                ups.append(None)
+                for _ in range(2):
+                    a = np.zeros((y.hblk, y.wblk, 64), dtype=np.int16)
+                    up_arrays.append(a)
+                    ups.append(a.ctypes.data)
+            _fill_image(arr[n], out, ptrs, ups)
+            ups_all.append(up_arrays)
+        rets = (C.c_int * len(outs))()
+        self._check(self.lib.jpegqs_cuda_run_batch(self.h, len(outs), arr, flags & 0x7f, niter, 0, rets, None))
+        for n, out in enumerate(outs):
+            self._collect(out, arr[n], ups_all[n])
+        return list(rets), outs
+
+    # ---- device-resident buffers (torch tensors or raw pointers) ----
+    def run_device(self, image: CoefImage, coef_ptrs: Sequence[int], up_ptrs: Sequence[Optional[int]],
+                   flags: int, niter: int, stream: int = 0):
+        """image carries geometry + quant tables; coef_ptrs/up_ptrs are device pointers.
+        Returns (ret, upsampled)."""
+        ci = _Image()
+        _fill_image(ci, image, coef_ptrs, up_ptrs)
+        ret = self._check(self.lib.jpegqs_cuda_run_device(self.h, C.byref(ci), flags & 0x7f, niter, 0,
+                                                         None, None, C.c_void_p(stream or None)))
+        return ret, bool(ci.upsampled)
+
+    def run_batch_device(self, images: List[CoefImage], coef_ptrs: List[Sequence[int]],
+                         up_ptrs: List[Sequence[Optional[int]]], flags: int, niter: int, stream: int = 0):
+        arr = (_Image * len(images))()
+        for n, im in enumerate(images):
+            _fill_image(arr[n], im, coef_ptrs[n], up_ptrs[n] if up_ptrs else [])
+        rets = (C.c_int * len(images))()
+        self._check(self.lib.jpegqs_cuda_run_batch(self.h, len(images), arr, flags & 0x7f, niter, 1, rets,
+                                                   C.c_void_p(stream or None)))
+        return list(rets), [bool(a.upsampled) for a in arr]
+
+    # ---- pass level (multi-GPU slabs) ----
+    @staticmethod
+    def make_job(coef_ptr, plane_ptr, plane2_ptr, wblk, hblk, quant, luma, top_edge, bottom_edge) -> _Job:
+        j = _Job()
+        j.coef, j.plane, j.plane2 = coef_ptr, plane_ptr, plane2_ptr or None
+        j.wblk, j.hblk = wblk, hblk
+        for k in range(64):
+            j.quant[k] = int(quant[k])
+        j.luma, j.top_edge, j.bottom_edge = int(luma), int(top_edge), int(bottom_edge)
+        return j
+
+    def pass_idct(self, jobs: List[_Job], mode: int, want_bad: bool = False, stream: int = 0) -> int:
+        arr = (_Job * len(jobs))(*jobs)
+        bad = C.c_int(0)
+        self._check(self.lib.jpegqs_cuda_pass_idct(self.h, len(jobs), arr, mode,
+                                                   C.byref(bad) if want_bad else None,
+                                                   C.c_void_p(stream or None)))
+        return bad.value
+
+    def pass_smooth(self, jobs: List[_Job], flags: int, clamp_out: bool, stream: int = 0):
+        arr = (_Job * len(jobs))(*jobs)
+        self._check(self.lib.jpegqs_cuda_pass_smooth(self.h, len(jobs), arr, flags & 0x7f, int(clamp_out),
+                                                     C.c_void_p(stream or None)))
+
+    def plane_bytes(self, wblk, hblk) -> int:
+        return int(self.lib.jpegqs_cuda_plane_bytes(wblk, hblk))
+
+    def plane_stride(self, wblk) -> int:
+        return int(self.lib.jpegqs_cuda_plane_stride(wblk))
+
+    def plane_pad(self) -> int:
+        return int(self.lib.jpegqs_cuda_plane_pad())
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = -1) -> QsContext:
+    if device not in _default_ctx:
+        _default_ctx[device] = QsContext(device)
+    return _default_ctx[device]
+
+
+def do_quantsmooth(image: CoefImage, flags: int, niter: int, progprec: int = 0, progress=None,
+                   device: int = -1):
+    """Python mirror of `int do_quantsmooth(srcinfo, coef_arrays, opts)` (reference
+    libjpegqs.h:47-48): returns (stop, smoothed image)."""
+    return default_context(device).do_quantsmooth(image, flags, niter, progprec, progress)
