@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py - the hot path's benchmark (contract in the task prompt, section 4).
+
+    python bench.py --gpus 1 --steps K --warmup W            # B200 arm
+    python bench.py --impl reference --steps K --warmup W    # reference CPU arm
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # MCU-row sharded, weak scaling
+
+A "step" is one complete do_quantsmooth pass (all components, all iterations) over one
+synthetic image.  N=1 workload: BASELINE.json's metric configuration, 7680x4320 YCbCr
+4:2:0, q=3 (flags 0), niter=3.  N>1: the same image stacked N times vertically
+(7680 x 4320*N), sharded by MCU rows with one halo pixel row per component exchanged over
+NCCL between the IDCT and smoothing passes of every iteration (weak scaling).
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpixels/sec at q=3 niter=3 (8K 4:2:0); achieved HBM GB/s vs peak"
+WIDTH, HEIGHT, SUBSAMPLING, FLAGS, NITER, QUALITY, SEED = 7680, 4320, "420", 0, 3, 50, 12345
+ALGO_BYTES_PER_BLOCK_ITER = 256          # 128 B coefficient read + 128 B write
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(world, rank):
+    import jpegqs_b200 as qs
+    mcu_total = (HEIGHT * world + 15) // 16
+    from jpegqs_b200.multigpu import split_mcu_rows
+    rng = split_mcu_rows(mcu_total, world)[rank]
+    im = qs.synth.make_image(WIDTH, HEIGHT * world, SUBSAMPLING, quality=QUALITY, seed=SEED,
+                             mcu_rows=None if world == 1 else rng)
+    return im, rng, mcu_total
+
+
+def cpu_reference_time(im, threads=0, runs=5):
+    """The reference's own AVX-512+OpenMP do_quantsmooth (oracle/_ref, built from the
+    unmodified sources) - or, if that object is absent, the scalar C port with OpenMP -
+    timed on this box's host cores.  Returns (seconds_median, kind, cores, how)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    ol.ensure_built()
+    if ol.have_ref("avx512"):
+        lib = ol.reflib("avx512")
+        cores = lib.qsref_num_procs()
+        times = []
+        for i in range(runs + 1):
+            lib.qsref_take_log()
+            ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=threads)
+            log = lib.qsref_take_log().decode()
+            ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
+            if i and ms:
+                times.append(ms[-1] / 1e3)
+        return statistics.median(times), "reference", cores, "reference's own timer ('quantsmooth: ..ms'), AVX-512 + OpenMP"
+    lib = ol.oraclelib()
+    cores = lib.qso_num_procs()
+    times = []
+    for i in range(runs + 1):
+        t = time.perf_counter()
+        ol.run_oracle(im, FLAGS, NITER, threads=threads)
+        if i:
+            times.append(time.perf_counter() - t)
+    return statistics.median(times), "port", cores, "scalar C port with OpenMP, wall clock"
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import jpegqs_b200 as qs
+    im = qs.synth.make_image(WIDTH, HEIGHT, SUBSAMPLING, quality=QUALITY, seed=SEED)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    ol.ensure_built()
+    kind = "reference" if ol.have_ref("avx512") else "port"
+    times = []
+    cores = None
+    for i in range(args.warmup + args.steps):
+        if kind == "reference":
+            lib = ol.reflib("avx512")
+            cores = lib.qsref_num_procs()
+            lib.qsref_take_log()
+            ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=0)
+            log = lib.qsref_take_log().decode()
+            ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
+            dt = ms[-1] / 1e3
+        else:
+            cores = ol.oraclelib().qso_num_procs()
+            t = time.perf_counter()
+            ol.run_oracle(im, FLAGS, NITER, threads=0)
+            dt = time.perf_counter() - t
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    mpix = WIDTH * HEIGHT / 1e6
+    value = mpix * len(times) / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mpixels/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(total / len(times) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WIDTH}x{HEIGHT} YCbCr 4:2:0, q=3 (flags 0), niter=3, whole image per step",
+                   "timer": "reference's own 'quantsmooth: ms' line" if kind == "reference" else "wall clock"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mpixels/s", "cores": cores, "kind": kind,
+                         "sample": "the full 8K image, every step"},
+        "e2e": {"value": round(value, 3), "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import jpegqs_b200 as qs
+    from jpegqs_b200 import multigpu as mg
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    ctx = qs.cuda.QsContext(local_rank)
+    ctx.set_profiling(True)
+
+    im, mcu_rng, mcu_total = make_workload(world, rank)
+    nblocks_rank = im.num_blocks
+    total_blocks = nblocks_rank
+    K, Wm = args.steps, args.warmup
+    nbuf = K + Wm
+    stream = torch.cuda.current_stream().cuda_stream
+    mpix_job = WIDTH * HEIGHT * world / 1e6
+
+    # ---- device-resident arm: a distinct pristine input buffer per step -----------------
+    host_coefs = [torch.from_numpy(np.ascontiguousarray(c.coef)) for c in im.comps]
+    dev_bufs = [[h.to(dev) for h in host_coefs] for _ in range(nbuf)]
+    torch.cuda.synchronize()
+
+    if world == 1:
+        def step(i):
+            ret, _ = ctx.run_device(im, [t.data_ptr() for t in dev_bufs[i]], [], FLAGS, NITER, stream)
+            return ret
+    else:
+        passes = mg.CudaPasses(ctx, stream)
+        planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev)
+                  for c in im.comps]
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def allreduce_flag(v):
+            flag.fill_(int(v))
+            dist.all_reduce(flag, op=dist.ReduceOp.BOR)
+            return int(flag.item())
+
+        def step(i):
+            comps = [mg.SlabComp(dev_bufs[i][k], planes[k], c.wblk, c.hblk, c.quant, k == 0)
+                     for k, c in enumerate(im.comps)]
+            return mg.run_slab(passes, comps, FLAGS, NITER, rank, world, dist, allreduce_flag)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    smooth_ms, smooth_n, idct_ms, idct_n = 0.0, 0, 0.0, 0
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(Wm + i)
+        if world == 1:
+            launches += ctx.last_launches
+            a, b, c, d = ctx.kernel_stats()
+            idct_ms += a; idct_n += b; smooth_ms += c; smooth_n += d
+        else:
+            launches += 2 * NITER
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        nb = torch.tensor([nblocks_rank], dtype=torch.int64, device=dev)
+        dist.all_reduce(nb)
+        total_blocks = int(nb.item())
+    ms_per_step = ms_total / K
+    value = mpix_job / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (smoothing pass) -------------------------------
+    peak, peak_src = peaks()
+    roofline = None
+    if world == 1 and smooth_n:
+        bytes_per_launch = ALGO_BYTES_PER_BLOCK_ITER * nblocks_rank
+        avg_ms = smooth_ms / smooth_n
+        achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "smooth_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "qs_smooth_kernel", "achieved": round(achieved, 2),
+                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
+                    "peak_source": peak_src, "avg_launch_ms": round(avg_ms, 4),
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "share_of_step": round(smooth_ms / (ms_total if ms_total else 1), 4),
+                    "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md 8d, DESIGN.md 4); "
+                            "see roofline_fp32"}
+        # FP32-issue roofline: 8 FP32 pipe instructions per (term, coefficient), 8288 terms per block
+        fp_inst = 8288 * 8 * nblocks_rank / 32.0                       # warp instructions per launch
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6                            # warp-instr/s at 1 per SMSP per clock
+        roofline_fp32 = {"bound": "fp32-issue", "achieved": round(fp_inst / (avg_ms / 1e3) / 1e12, 4),
+                         "peak": round(issue_peak / 1e12, 4), "unit": "T warp-instr/s",
+                         "frac": round(fp_inst / (avg_ms / 1e3) / issue_peak, 4),
+                         "note": "minimum FP32-pipe instructions of the order-exact arithmetic / (148 SM x 4 "
+                                 "sub-partitions x measured SM clock)"}
+    else:
+        roofline_fp32 = None
+
+    # ---- e2e: the public host-buffer call (pinned host in, pinned host out) -------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = []
+        for _ in range(nbuf):
+            row = []
+            for c in im.comps:
+                p = qs.cuda.PinnedArray(c.coef.shape)
+                p.array[...] = c.coef
+                row.append(p)
+            pinned.append(row)
+        h2d = sum(c.coef.nbytes for c in im.comps)
+        d2h = h2d
+
+        def e2e_step(i):
+            work = im.clone()
+            for k, c in enumerate(work.comps):
+                c.coef = pinned[i][k].array
+            if world == 1:
+                ctx.do_quantsmooth(work, FLAGS, NITER, inplace=True)
+            else:
+                for k in range(len(work.comps)):
+                    dev_bufs[i][k].copy_(torch.from_numpy(pinned[i][k].array), non_blocking=True)
+                step(i)
+                for k in range(len(work.comps)):
+                    torch.from_numpy(pinned[i][k].array).copy_(dev_bufs[i][k], non_blocking=True)
+                torch.cuda.synchronize()
+
+        for i in range(Wm):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(Wm + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": round(mpix_job * K / dt, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": round(dt / K * 1e3, 3),
+               "api": "jpegqs_cuda_run_host (C ABI, pinned host buffers)" if world == 1 else
+                      "pinned host -> slab tensors -> pass-level C ABI -> pinned host"}
+        for row in pinned:
+            for p in row:
+                p.close()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, kind, cores, how = cpu_reference_time(im, threads=0, runs=5)
+        cpu = {"value": round(WIDTH * HEIGHT / 1e6 / sec, 3), "unit": "Mpixels/s", "cores": cores, "kind": kind,
+               "sample": f"the full 8K image, 1 warm-up + median of 5 runs ({how})"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mpixels/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WIDTH}x{HEIGHT * world} YCbCr 4:2:0 (8K x{world} stacked), q=3 (flags 0), "
+                                   f"niter=3, quality-50 Annex-K tables, seed {SEED}",
+                       "blocks": total_blocks,
+                       "cache": "a distinct pristine input buffer per step (100 MB each, "
+                                f"{nbuf} buffers > 126 MB L2)",
+                       "sharding": "none" if world == 1 else f"MCU rows over {world} GPUs, NCCL halo rows"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
+            "kernel_ms_per_step": {"idct_pass": round(idct_ms / K, 4), "smooth_pass": round(smooth_ms / K, 4)}
+            if world == 1 else None,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

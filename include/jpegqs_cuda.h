@@ -68,6 +68,13 @@ float jpegqs_cuda_last_device_ms(const jpegqs_cuda_ctx *ctx);
 /* number of kernel launches issued by the last run_* call */
 int jpegqs_cuda_last_launches(const jpegqs_cuda_ctx *ctx);
 
+/* optional per-kernel timing of the following run_* calls (CUDA event pairs around every
+ * IDCT-pass and smoothing-pass launch, on the stream they are launched on); the sums are
+ * read back with jpegqs_cuda_kernel_stats after the call.  Measurement aid for bench.py. */
+void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on);
+void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
+		float *smooth_ms, int *smooth_launches);
+
 /* pinned host memory for coefficient arrays (fast H2D/D2H); plain malloc'd memory works too */
 void *jpegqs_cuda_host_alloc(size_t bytes);
 void jpegqs_cuda_host_free(void *p);
@@ -107,8 +114,9 @@ int jpegqs_cuda_plane_pad(void);   /* byte offset of pixel column 0 inside a pla
 
 #define JPEGQS_PASS_DEQUANT 1      /* iteration 0: coef *= quantval, range check (2596-2603) */
 #define JPEGQS_PASS_CLAMP   2      /* write coefficients back clamped to +-1023 (2670-2689)  */
-/* IDCT pass (2589-2620): renders each job's plane (+ replicated borders).  *bad receives
- * non-zero if a de-quantized coefficient left [-2048, 2047] (host sync).  bad may be NULL. */
+/* IDCT pass (2589-2620): renders each job's plane (+ replicated borders).  *bad receives a
+ * bit mask (bit i = job i, jobs >= 31 share bit 31) of the jobs in which a de-quantized
+ * coefficient left [-2048, 2047] (host sync).  bad may be NULL. */
 int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int mode,
 		int *bad, void *stream);
 /* smoothing pass (2627-2640): quantsmooth_block on every block of every job */

@@ -119,6 +119,11 @@ struct jpegqs_cuda_ctx {
 	char *arena; size_t arena_cap, arena_pos;
 	cudaEvent_t ev0, ev1;
 	float last_ms; int launches;
+	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
+	int profiling;
+	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
+	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
+	float kernel_ms[2]; int kernel_launches[2];
 	char err[512];
 };
 
@@ -154,6 +159,7 @@ extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
 	if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
 	delete ctx;
 }
 
@@ -181,6 +187,8 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
+	ctx->profiling = 0; ctx->ev_used = 0;
+	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 		CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
@@ -268,6 +276,42 @@ static int upload_jobs(jpegqs_cuda_ctx *ctx, int slot, std::vector<QsJob> &jobs,
 	return 0;
 }
 
+/* per-kernel timing helpers: prof_begin/prof_end bracket one launch with an event pair */
+static int prof_begin(jpegqs_cuda_ctx *ctx, int kind, cudaStream_t st) {
+	if (!ctx->profiling) return 0;
+	while (ctx->ev_pool.size() < ctx->ev_used + 2) {
+		cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->ev_pool.push_back(e);
+	}
+	ctx->ev_kind.push_back(kind);
+	CK(cudaEventRecord(ctx->ev_pool[ctx->ev_used], st));
+	return 0;
+}
+static int prof_end(jpegqs_cuda_ctx *ctx, cudaStream_t st) {
+	if (!ctx->profiling) return 0;
+	CK(cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], st));
+	ctx->ev_used += 2;
+	return 0;
+}
+static int prof_collect(jpegqs_cuda_ctx *ctx) {
+	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
+	for (size_t i = 0; i < ctx->ev_kind.size(); i++) {
+		float ms = 0; int k = ctx->ev_kind[i];
+		CK(cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]));
+		ctx->kernel_ms[k] += ms; ctx->kernel_launches[k]++;
+	}
+	ctx->ev_kind.clear(); ctx->ev_used = 0;
+	return 0;
+}
+
+extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->profiling = on; }
+extern "C" void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
+		float *smooth_ms, int *smooth_launches) {
+	if (idct_ms) *idct_ms = ctx->kernel_ms[0];
+	if (idct_launches) *idct_launches = ctx->kernel_launches[0];
+	if (smooth_ms) *smooth_ms = ctx->kernel_ms[1];
+	if (smooth_launches) *smooth_launches = ctx->kernel_launches[1];
+}
+
 /* ------------------------------------------------------------------------------------------
  * whole-image driver
  * ------------------------------------------------------------------------------------------ */
@@ -303,6 +347,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	if (progress && nimg != 1) return JPEGQS_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
 	ctx->launches = 0; ctx->last_ms = 0;
+	ctx->ev_kind.clear(); ctx->ev_used = 0;
 	if (niter < 0) niter = 0;
 	if (niter > 100) niter = 100;                       /* quantsmooth.h:2455-2456 */
 
@@ -453,7 +498,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
 				int mode = (iter == 0 ? QS_IDCT_DEQUANT : 0) | (clampv ? QS_IDCT_CLAMP : 0);
 				if (iter == 0) CK(cudaMemsetAsync(bad_dev, 0, jobs.size() * sizeof(int), st));
+				if (prof_begin(ctx, 0, st)) return JPEGQS_ERR_CUDA;
 				CK(qs_launch_idct_pass(jd, (int)jobs.size(), tiles, mode, bad_dev, st));
+				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
 				if (iter == 0) {                                           /* bad_coef, 2602-2610 */
@@ -485,7 +532,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				if (jobs.empty()) continue;
 				const QsJob *jd; int tiles;
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
 				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, st));
+				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
 			}
@@ -556,6 +605,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	}
 	CK(cudaStreamSynchronize(st));
 	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	if (prof_collect(ctx)) return JPEGQS_ERR_CUDA;
 	return 0;
 }
 
@@ -621,7 +671,7 @@ extern "C" int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpeg
 		if (njobs) {
 			CK(cudaMemcpyAsync(ctx->flags_host, ctx->flags_dev, njobs * sizeof(int), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
-			for (int i = 0; i < njobs; i++) *bad |= ctx->flags_host[i];
+			for (int i = 0; i < njobs; i++) if (ctx->flags_host[i]) *bad |= (int)(1u << (i < 31 ? i : 31));
 		}
 	}
 	return 0;

@@ -87,6 +87,9 @@ def load():
                                           C.POINTER(C.c_int), C.c_void_p]
     lib.jpegqs_cuda_pass_smooth.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Job), C.c_int, C.c_int,
                                             C.c_void_p]
+    lib.jpegqs_cuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.jpegqs_cuda_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                             C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.jpegqs_cuda_tables.argtypes = [C.c_int, C.c_void_p]
     lib.jpegqs_cuda_orig_coef.argtypes = [C.c_int, C.c_int]
     _lib = lib
@@ -185,6 +188,15 @@ class QsContext:
     @property
     def last_launches(self) -> int:
         return int(self.lib.jpegqs_cuda_last_launches(self.h))
+
+    def set_profiling(self, on: bool):
+        self.lib.jpegqs_cuda_set_profiling(self.h, int(on))
+
+    def kernel_stats(self):
+        """(idct_ms, idct_launches, smooth_ms, smooth_launches) of the last run_* call."""
+        a, b, c, d = C.c_float(), C.c_int(), C.c_float(), C.c_int()
+        self.lib.jpegqs_cuda_kernel_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return a.value, b.value, c.value, d.value
 
     # ---- whole image, host buffers (the call a user of the reference makes) ----
     def do_quantsmooth(self, image: CoefImage, flags: int, niter: int, progprec: int = 0,

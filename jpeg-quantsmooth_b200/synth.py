@@ -83,8 +83,11 @@ def quantize_blocks(px: np.ndarray, q: np.ndarray) -> np.ndarray:
 
 
 def make_image(width: int, height: int, subsampling: str = "420", quality: int = 50,
-               seed: int = 12345, noise: int = 4, chunk_rows: int = 64) -> CoefImage:
-    """subsampling: 'gray', '444', '422', '420', '440'."""
+               seed: int = 12345, noise: int = 4, chunk_rows: int = 64, mcu_rows=None) -> CoefImage:
+    """subsampling: 'gray', '444', '422', '420', '440'.
+    mcu_rows=(m0, m1): generate only the slab of MCU rows [m0, m1) of the image (each
+    component then holds block rows [m0*v_samp, min(m1*v_samp, hblk))); the values are
+    identical to the corresponding rows of the full image."""
     if subsampling == "gray":
         samp = [(1, 1)]
         cs = JCS_GRAYSCALE
@@ -100,11 +103,14 @@ def make_image(width: int, height: int, subsampling: str = "420", quality: int =
         wb = blocks_for(width, hs, max_h)
         hb = blocks_for(height, vs, max_v)
         q = tables[0 if c == 0 else 1]
-        coef = np.empty((hb, wb, 64), dtype=np.int16)
-        for r0 in range(0, hb, chunk_rows):
-            r1 = min(hb, r0 + chunk_rows)
+        b0, b1 = 0, hb
+        if mcu_rows is not None:
+            b0, b1 = min(mcu_rows[0] * vs, hb), min(mcu_rows[1] * vs, hb)
+        coef = np.empty((b1 - b0, wb, 64), dtype=np.int16)
+        for r0 in range(b0, b1, chunk_rows):
+            r1 = min(b1, r0 + chunk_rows)
             px = pixels(c, r0 * 8, r1 * 8, wb * 8, max_h // hs, max_v // vs, seed, noise)
-            coef[r0:r1] = quantize_blocks(px, q)
+            coef[r0 - b0:r1 - b0] = quantize_blocks(px, q)
         comps.append(Component(coef=coef, quant=q.copy(), h_samp=hs, v_samp=vs,
                                quant_tbl_no=0 if c == 0 else 1))
     return CoefImage(width=width, height=height, colorspace=cs, comps=comps)
