@@ -76,7 +76,7 @@ static int build_tables(int flags, float *out, float prescale) {
 
 /* chunk schedule: anti-diagonals s = 14..1 of the 8x8 coefficient grid in the reference's
  * visiting order (reverse zig-zag, quantsmooth.h:1403 + zigzag_refresh 313-322) */
-static int build_chunks(QsChunk *ch) {
+static int build_chunks(QsChunk *ch, int maxn) {
 	int n = 0;
 	for (int s = 14; s >= 1; s--) {
 		int full[8], nf = 0; bool first = true;
@@ -92,7 +92,7 @@ static int build_chunks(QsChunk *ch) {
 			c.idx[1] = (uint8_t)(s * 8);    /* column 0: border + vertical   (+diag) */
 			ch[n++] = c;
 		}
-		int parts = (nf + 3) / 4, pos = 0;
+		int parts = (nf + maxn - 1) / maxn, pos = 0;
 		for (int p = 0; p < parts; p++) {
 			int len = (nf - pos + (parts - p) - 1) / (parts - p);
 			QsChunk c; memset(&c, 0, sizeof(c));
@@ -121,6 +121,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
+	int tune_sync, tune_maxn;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -187,7 +188,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0;
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 1; ctx->tune_maxn = 4;
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -201,7 +202,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 		CK(cudaMalloc(&ctx->tab_diag, 64 * QS_TAB_DIAG * sizeof(float)));
 		CK(cudaMemcpy(ctx->tab_diag, t.data(), 64 * QS_TAB_DIAG * sizeof(float), cudaMemcpyHostToDevice));
 		QsChunk ch[QS_MAX_CHUNKS];
-		int n = build_chunks(ch);
+		int n = build_chunks(ch, 4);
 		CK(qs_set_chunks(ch, n));
 		CK(qs_smooth_configure());
 		CK(cudaMalloc(&ctx->jobs_dev, 2 * QS_MAX_JOBS * sizeof(QsJob)));
@@ -304,6 +305,26 @@ static int prof_collect(jpegqs_cuda_ctx *ctx) {
 }
 
 extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->profiling = on; }
+
+/* kernel-variant knobs for tuning runs (tools/tune.py); results are identical for every
+ * setting.  key 0: lock-step sub-partition groups (0/1); key 1: max coefficients per chunk (1..4) */
+extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) {
+	if (!ctx) return JPEGQS_ERR_ARG;
+	if (key == 0) { ctx->tune_sync = value ? 1 : 0; return 0; }
+	if (key == 1) {
+		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
+		CK(cudaSetDevice(ctx->device));
+		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaDeviceSynchronize());
+		QsChunk ch[QS_MAX_CHUNKS * 2];
+		int n = build_chunks(ch, value);
+		if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
+		CK(qs_set_chunks(ch, n));
+		ctx->tune_maxn = value;
+		return 0;
+	}
+	return JPEGQS_ERR_ARG;
+}
 extern "C" void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
 		float *smooth_ms, int *smooth_launches) {
 	if (idct_ms) *idct_ms = ctx->kernel_ms[0];
@@ -533,7 +554,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				const QsJob *jd; int tiles;
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
 				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
-				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, st));
+				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, st));
 				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
@@ -686,6 +707,6 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	int rc = stage_jobs(ctx, njobs, jobs, 1, st, &jd, &tiles);
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
-	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, st));
+	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, st));
 	return 0;
 }

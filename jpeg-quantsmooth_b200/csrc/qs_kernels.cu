@@ -416,6 +416,15 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 	}
 }
 
+/* Lock-step execution: the 4 warps that share an SM sub-partition (warp id % 4) run the same
+ * code region at the same time, separated by a named barrier, so that the sub-partition's
+ * L0 instruction cache holds ONE unrolled loop body instead of four (the first ncu capture
+ * showed stall_no_instruction = 4.3 per issue with free-running warps, profiles/). */
+template <int SYNC>
+__device__ __forceinline__ void qs_group_sync(int grp) {
+	if (SYNC) asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");
+}
+
 /* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
 __device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const QsQuantDev *__restrict__ qd,
 		uint16_t *cs) {
@@ -434,9 +443,9 @@ __device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const
 	}
 }
 
-template <int N, bool DIAG>
+template <int N, bool DIAG, int SYNC>
 __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp) {
 	const float *tab[N]; float Rs[N], a2[N], a3[N];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -445,18 +454,21 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
 	qs_sec_h<N>(pw, tab, Rs, a2, a3);
+	qs_group_sync<SYNC>(grp);
 	qs_sec_border<N>(pw, tab, Rs, a2, a3);
+	qs_group_sync<SYNC>(grp);
 	qs_sec_v<N>(pw, tab, Rs, a2, a3);
-	if (DIAG) qs_sec_diag<N>(pw, tab, Rs, a2, a3);
+	if (DIAG) { qs_group_sync<SYNC>(grp); qs_sec_diag<N>(pw, tab, Rs, a2, a3); }
+	qs_group_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
 }
 
 /* the two edge coefficients of an anti-diagonal: idx[0] lies in row 0 (i <= 7: no vertical
  * terms), idx[1] in column 0 (i & 7 == 0: no horizontal terms) */
-template <bool DIAG>
+template <bool DIAG, int SYNC>
 __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp) {
 	const float *tab[2]; float Rs[2], a2[2], a3[2];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -465,9 +477,12 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
 	qs_sec_h<1>(pw, tab, Rs, a2, a3);
+	qs_group_sync<SYNC>(grp);
 	qs_sec_border<2>(pw, tab, Rs, a2, a3);
+	qs_group_sync<SYNC>(grp);
 	qs_sec_v<1>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
-	if (DIAG) qs_sec_diag<2>(pw, tab, Rs, a2, a3);
+	if (DIAG) { qs_group_sync<SYNC>(grp); qs_sec_diag<2>(pw, tab, Rs, a2, a3); }
+	qs_group_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
 }
@@ -555,11 +570,12 @@ __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, 
 	}
 }
 
-template <bool DIAG>
+template <bool DIAG, int SYNC>
 __global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
 		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
 		int flags, int clamp_out) {
 	extern __shared__ __align__(16) uint32_t smem[];
+	__shared__ int s_tile[4];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 	float *tabs = (float *)smem;
 	{
@@ -568,21 +584,33 @@ __global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const Q
 	}
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int grp = warp & 3, wig = warp >> 2;                /* sub-partition, warp within it */
 	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
 	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
 
 	for (;;) {
-		int tile = 0;
-		if (lane == 0) tile = atomicAdd(tile_counter, 1);
-		tile = __shfl_sync(0xffffffffu, tile, 0);
-		if (tile >= total_tiles) break;
+		int tile = 0; bool active = true;
+		if (SYNC) {
+			/* one atomic per group of 4 tiles; the group's warps then stay in lock step */
+			if (wig == 0 && lane == 0) s_tile[grp] = atomicAdd(tile_counter, 1);
+			qs_group_sync<SYNC>(grp);
+			int gt = *(volatile int *)&s_tile[grp];
+			if (gt * 4 >= total_tiles) break;
+			tile = gt * 4 + wig;
+			active = tile < total_tiles;
+			if (!active) tile = total_tiles - 1;        /* shadow work keeps the barriers aligned */
+		} else {
+			if (lane == 0) tile = atomicAdd(tile_counter, 1);
+			tile = __shfl_sync(0xffffffffu, tile, 0);
+			if (tile >= total_tiles) break;
+		}
 		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 		int nblocks = job->nblocks;
 		int b = (tile - job->tile_begin) * 32 + lane;
-		bool valid = b < nblocks;
-		if (!valid) b = nblocks - 1;                    /* idle lanes shadow the last block */
+		bool valid = active && b < nblocks;
+		if (b >= nblocks) b = nblocks - 1;              /* idle lanes shadow the last block */
 		int W = job->wblk, stride = job->stride;
 		int by = b / W, bx = b - by * W;
 		int16_t *cptr = job->coef + (size_t)b * 64;
@@ -621,14 +649,15 @@ __global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const Q
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
 			QsChunk ch = c_chunks[ci];
+			qs_group_sync<SYNC>(grp);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
-			if (ch.first) qs_refresh(cw, pw);
-			if (ch.type) qs_chunk_edge<DIAG>(ch, tabs, pw, qd, cs);
-			else if (ch.n == 4) qs_chunk_full<4, DIAG>(ch, tabs, pw, qd, cs);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG>(ch, tabs, pw, qd, cs);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG>(ch, tabs, pw, qd, cs);
-			else qs_chunk_full<1, DIAG>(ch, tabs, pw, qd, cs);
+			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(grp); }
+			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else qs_chunk_full<1, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 		}
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
@@ -765,12 +794,19 @@ size_t qs_smooth_smem_bytes(int diag) {
 			(size_t)(QS_SMOOTH_THREADS / 32) * QS_WARP_WORDS * 4;
 }
 
+typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
+static qs_smooth_fn qs_smooth_variant(int diag, int sync) {
+	if (diag) return sync ? qs_smooth_kernel<true, 1> : qs_smooth_kernel<true, 0>;
+	return sync ? qs_smooth_kernel<false, 1> : qs_smooth_kernel<false, 0>;
+}
+
 cudaError_t qs_smooth_configure(void) {
-	cudaError_t e = cudaFuncSetAttribute(qs_smooth_kernel<false>,
-			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(0));
-	if (e != cudaSuccess) return e;
-	return cudaFuncSetAttribute(qs_smooth_kernel<true>,
-			cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(1));
+	for (int d = 0; d < 2; d++) for (int sy = 0; sy < 2; sy++) {
+		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy),
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d));
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
 }
 
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
@@ -782,19 +818,16 @@ cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tile
 }
 
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, cudaStream_t st) {
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
 	int warps = QS_SMOOTH_THREADS / 32;
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
-	if (flags & QS_DIAGONALS)
-		qs_smooth_kernel<true><<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(1), st>>>(
-				jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
-	else
-		qs_smooth_kernel<false><<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(0), st>>>(
-				jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
+	qs_smooth_variant(diag, sync)<<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(diag), st>>>(
+			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
 	return cudaGetLastError();
 }
 

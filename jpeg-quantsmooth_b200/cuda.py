@@ -90,6 +90,7 @@ def load():
     lib.jpegqs_cuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.jpegqs_cuda_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                              C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.jpegqs_cuda_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.jpegqs_cuda_tables.argtypes = [C.c_int, C.c_void_p]
     lib.jpegqs_cuda_orig_coef.argtypes = [C.c_int, C.c_int]
     _lib = lib
@@ -191,6 +192,9 @@ class QsContext:
 
     def set_profiling(self, on: bool):
         self.lib.jpegqs_cuda_set_profiling(self.h, int(on))
+
+    def set_tuning(self, key: int, value: int):
+        self._check(self.lib.jpegqs_cuda_set_tuning(self.h, key, value))
 
     def kernel_stats(self):
         """(idct_ms, idct_launches, smooth_ms, smooth_launches) of the last run_* call."""

@@ -1,0 +1,52 @@
+"""Kernel-variant sweep on the 8K q3 workload (device-resident).  Usage on the GPU box:
+    python tools/tune.py [--flags 0] [--variants sync:maxn,...]
+Prints per-variant average smoothing-pass launch time and checks that every variant
+produces byte-identical output."""
+import argparse
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import jpegqs_b200 as qs
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--niter", type=int, default=3)
+ap.add_argument("--width", type=int, default=7680)
+ap.add_argument("--height", type=int, default=4320)
+ap.add_argument("--variants", default="0:4,1:4,1:3,1:2")
+ap.add_argument("--steps", type=int, default=3)
+args = ap.parse_args()
+
+ctx = qs.cuda.QsContext(0)
+ctx.set_profiling(True)
+im = qs.synth.make_image(args.width, args.height, "420")
+dev = torch.device("cuda", 0)
+host = [torch.from_numpy(np.ascontiguousarray(c.coef)) for c in im.comps]
+stream = torch.cuda.current_stream().cuda_stream
+ref_hash = None
+for v in args.variants.split(","):
+    sync, maxn = (int(x) for x in v.split(":"))
+    ctx.set_tuning(0, sync)
+    ctx.set_tuning(1, maxn)
+    sm, n, tot = 0.0, 0, 0.0
+    for i in range(args.steps + 1):
+        bufs = [h.to(dev) for h in host]
+        ups = []
+        if args.flags & 4:
+            y = im.comps[0]
+            ups = [None] + [torch.empty((y.hblk, y.wblk, 64), dtype=torch.int16, device=dev).data_ptr() for _ in range(2)]
+        torch.cuda.synchronize()
+        ctx.run_device(im, [t.data_ptr() for t in bufs], ups, args.flags, args.niter, stream)
+        if i:
+            a, b, c, d = ctx.kernel_stats()
+            sm += c; n += d; tot += ctx.last_device_ms
+    h = hashlib.sha1(b"".join(t.cpu().numpy().tobytes() for t in bufs)).hexdigest()
+    if ref_hash is None:
+        ref_hash = h
+    print(f"sync={sync} maxn={maxn}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
+          f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
