@@ -69,6 +69,6 @@ typedef struct {
 	uint8_t type, n, first, pad;
 	uint8_t idx[4];
 } QsChunk;
-#define QS_MAX_CHUNKS 32
+#define QS_MAX_CHUNKS 64
 
 #endif
