@@ -108,15 +108,23 @@ def cpu_reference_time(im, threads=0, runs=5):
     if ol.have_ref("avx512"):
         lib = ol.reflib("avx512")
         cores = lib.qsref_num_procs()
-        times = []
-        for i in range(runs + 1):
-            lib.qsref_take_log()
-            ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=threads)
-            log = lib.qsref_take_log().decode()
-            ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
-            if i and ms:
-                times.append(ms[-1] / 1e3)
-        return statistics.median(times), "reference", cores, "reference's own timer ('quantsmooth: ..ms'), AVX-512 + OpenMP"
+        best = None
+        # the reference's default is all processors (opts.threads = 0); on many-core hosts
+        # fewer threads can be faster, so the best of {all, 1/2, 1/4} is reported (fair to it)
+        for thr in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+            times = []
+            for i in range(runs + 1):
+                lib.qsref_take_log()
+                ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=thr)
+                log = lib.qsref_take_log().decode()
+                ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
+                if i and ms:
+                    times.append(ms[-1] / 1e3)
+            med = statistics.median(times)
+            if best is None or med < best[0]:
+                best = (med, thr)
+        return best[0], "reference", best[1], ("reference's own timer ('quantsmooth: ..ms'), AVX-512 + OpenMP, "
+                                              f"best of thread counts all/half/quarter of {cores} processors")
     lib = ol.oraclelib()
     cores = lib.qso_num_procs()
     times = []
@@ -139,12 +147,28 @@ def run_reference_arm(args, rank, world):
     kind = "reference" if ol.have_ref("avx512") else "port"
     times = []
     cores = None
+    nthreads = 0
+    if kind == "reference":
+        # untimed calibration: the reference defaults to all processors; on many-core hosts
+        # fewer threads can be faster, so it gets the best of {all, 1/2, 1/4} (fair to it)
+        lib = ol.reflib("avx512")
+        allp = lib.qsref_num_procs()
+        best = None
+        for thr in sorted({allp, max(1, allp // 2), max(1, allp // 4)}, reverse=True):
+            for rep in range(2):
+                lib.qsref_take_log()
+                ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=thr)
+                log = lib.qsref_take_log().decode()
+                ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
+            if best is None or ms[-1] < best[0]:
+                best = (ms[-1], thr)
+        nthreads = best[1]
     for i in range(args.warmup + args.steps):
         if kind == "reference":
             lib = ol.reflib("avx512")
-            cores = lib.qsref_num_procs()
+            cores = nthreads
             lib.qsref_take_log()
-            ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=0)
+            ol.run_reference(im, FLAGS | (8 << 16), NITER, variant="avx512", threads=nthreads)
             log = lib.qsref_take_log().decode()
             ms = [float(l.split(":")[1].replace("ms", "")) for l in log.splitlines() if l.startswith("quantsmooth:")]
             dt = ms[-1] / 1e3
@@ -321,17 +345,21 @@ def main():
         h2d = sum(c.coef.nbytes for c in im.comps)
         d2h = h2d
 
+        from jpegqs_b200.image import CoefImage, Component
+        works = []
+        for i in range(nbuf):                      # views over the pinned buffers, built up front
+            works.append(CoefImage(im.width, im.height, im.colorspace,
+                                   [Component(pinned[i][k].array, c.quant.copy(), c.h_samp, c.v_samp, c.quant_tbl_no)
+                                    for k, c in enumerate(im.comps)]))
+
         def e2e_step(i):
-            work = im.clone()
-            for k, c in enumerate(work.comps):
-                c.coef = pinned[i][k].array
             if world == 1:
-                ctx.do_quantsmooth(work, FLAGS, NITER, inplace=True)
+                ctx.do_quantsmooth(works[i], FLAGS, NITER, inplace=True)
             else:
-                for k in range(len(work.comps)):
+                for k in range(len(im.comps)):
                     dev_bufs[i][k].copy_(torch.from_numpy(pinned[i][k].array), non_blocking=True)
                 step(i)
-                for k in range(len(work.comps)):
+                for k in range(len(im.comps)):
                     torch.from_numpy(pinned[i][k].array).copy_(dev_bufs[i][k], non_blocking=True)
                 torch.cuda.synchronize()
 

@@ -1,0 +1,206 @@
+"""GPU edge cases, the libjpeg-facing C entry point, the batch and pass-level entry points,
+and size-independent properties at BASELINE.json's full sizes."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import jpegqs_b200 as qs
+import oracle_lib as ol
+from golden_io import adversarial_image
+from jpegqs_b200 import multigpu as mg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = qs.cuda.QsContext(0)
+    yield c
+    c.close()
+
+
+def _same(ctx, im, flags, niter, **kw):
+    ret, out = ctx.do_quantsmooth(im, flags, niter, **kw)
+    oret, oout = ol.run_oracle(im, flags, niter)
+    assert ret == oret
+    assert ol.images_equal(out, oout), f"{ol.diff_count(out, oout)} coefficients differ"
+    return out
+
+
+@pytest.mark.parametrize("kind,flags,niter", [("nan", 0, 1), ("nan", 1, 2), ("badcoef", 0, 2), ("bigquant", 0, 2),
+                                              ("zeroquant", 0, 2), ("flat", 1, 2), ("q1", 0, 3),
+                                              ("badcoef", 7, 2), ("bigquant", 7, 1), ("zeroquant", 7, 2)])
+def test_adversarial(ctx, kind, flags, niter):
+    _same(ctx, adversarial_image(kind), flags, niter)
+
+
+def test_niter_zero_and_clamping_of_niter(ctx):
+    im = qs.synth.make_image(64, 48, "420")
+    ret, out = ctx.do_quantsmooth(im, 0, 0)          # early return: nothing touched (2458)
+    assert ret == 0 and ol.images_equal(out, im)
+    _same(ctx, im, 4, 0)                             # UPSAMPLE_UV alone still runs (2458, 2495)
+    _same(ctx, im, 0, -5)
+    ret, out = ctx.do_quantsmooth(im, 0, 1000)       # clamped to JPEGQS_ITER_MAX
+    ret2, out2 = ctx.do_quantsmooth(im, 0, 100)
+    assert ol.images_equal(out, out2)
+
+
+def test_low_quality_is_refused_not_faked(ctx):
+    im = qs.synth.make_image(32, 32, "gray")
+    with pytest.raises(qs.cuda.QsError):
+        ctx.do_quantsmooth(im, 8, 3)
+
+
+def test_component_without_table_and_four_components(ctx):
+    im = qs.synth.make_image(64, 48, "420")
+    im.comps[1].quant = None
+    _same(ctx, im, 1, 2)
+    im = qs.synth.make_image(64, 48, "444")
+    im.colorspace = qs.JCS_RGB                        # not YCbCr: all components are "luma"
+    _same(ctx, im, 7 | 32, 2)
+
+
+def test_progress_sequence_and_cancel(ctx):
+    im = qs.synth.make_image(96, 80, "420")
+    seq_o, seq_g = [], []
+    ol.run_oracle(im, 3, 3, progprec=7, progress=lambda d, cur, mx: seq_o.append((cur, mx)) or 0)
+    ret, out = ctx.do_quantsmooth(im, 3, 3, progprec=7, progress=lambda cur, mx: seq_g.append((cur, mx)) or 0)
+    assert seq_g == seq_o and len(seq_g) > 2
+    _, want = ol.run_oracle(im, 3, 3)
+    assert ol.images_equal(out, want)
+    s1, s2 = [], []
+    r1, o1 = ol.run_oracle(im, 0, 3, progprec=7, progress=lambda d, cur, mx: (s1.append(cur), 5 if len(s1) >= 2 else 0)[1])
+    r2, o2 = ctx.do_quantsmooth(im, 0, 3, progprec=7, progress=lambda cur, mx: (s2.append(cur), 5 if len(s2) >= 2 else 0)[1])
+    assert r1 == r2 == 5 and s1 == s2
+    assert ol.images_equal(o1, o2)
+
+
+@pytest.mark.parametrize("flags,niter,ss", [(0, 3, "420"), (7, 2, "420"), (3, 2, "444"), (1, 1, "gray")])
+def test_libjpeg_facing_entry_point(flags, niter, ss):
+    """do_quantsmooth(j_decompress_ptr, jvirt_barray_ptr*, jpegqs_control_t*) through the
+    fake libjpeg front end, rows scattered in memory like libjpeg's virtual arrays."""
+    lib = qs.cuda.load()
+    im = qs.synth.make_image(120, 72, ss)
+    ret, out = ol.run_libjpeg_boundary(lib.do_quantsmooth, im, flags | 64, niter, scatter_rows=True)
+    oret, oout = ol.run_oracle(im, flags, niter)
+    assert ret == oret and ol.images_equal(out, oout)
+    if ol.have_ref("scalar"):
+        rret, rout = ol.run_reference(im, flags, niter, scatter_rows=True)
+        assert ret == rret and ol.images_equal(out, rout)
+
+
+def test_batch_entry_point(ctx):
+    ims = [qs.synth.make_image(1920 // 4, 1080 // 4, "420", seed=s) for s in range(5)]
+    ims.append(adversarial_image("badcoef"))
+    ims.append(qs.synth.make_image(64, 64, "gray", quality=80))
+    for flags in (0, 7):
+        rets, outs = ctx.run_batch_host(ims, flags, 2)
+        for im, r, o in zip(ims, rets, outs):
+            wr, want = ol.run_oracle(im, flags, 2)
+            assert r == wr and ol.images_equal(o, want)
+
+
+def _run_slabs_one_gpu(ctx, im, flags, niter, nshards):
+    """Emulates the multi-GPU schedule on one device: slabs are separate job sets, halo rows
+    are copied by hand between the IDCT and smoothing passes."""
+    import torch
+    dev = torch.device("cuda", 0)
+    vmax = max(c.v_samp for c in im.comps)
+    total = -(-im.height // (8 * vmax))
+    ranges = mg.split_mcu_rows(total, nshards)
+    slabs = []
+    for rng in ranges:
+        comps = []
+        for k, c in enumerate(im.comps):
+            r0, r1 = mg.comp_block_rows(rng, c.v_samp, c.hblk)
+            coef = torch.from_numpy(np.ascontiguousarray(c.coef[r0:r1])).to(dev)
+            plane = torch.zeros(((r1 - r0) * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev)
+            comps.append(mg.SlabComp(coef, plane, c.wblk, r1 - r0, c.quant, k == 0))
+        slabs.append(comps)
+    passes = mg.CudaPasses(ctx, torch.cuda.current_stream().cuda_stream)
+    for it in range(niter):
+        for r, comps in enumerate(slabs):
+            passes.idct(comps, mg.PASS_DEQUANT if it == 0 else 0, r == 0, r == nshards - 1, False)
+        for r in range(nshards - 1):
+            for a, b in zip(slabs[r], slabs[r + 1]):
+                if a.rows and b.rows:
+                    b.plane[0].copy_(a.plane[a.rows * 8])
+                    a.plane[a.rows * 8 + 1].copy_(b.plane[1])
+        for r, comps in enumerate(slabs):
+            passes.smooth(comps, flags, it == niter - 1, r == 0, r == nshards - 1)
+    torch.cuda.synchronize()
+    return [np.concatenate([s[k].coef.cpu().numpy() for s in slabs], axis=0) for k in range(len(im.comps))]
+
+
+@pytest.mark.parametrize("nshards,flags", [(2, 0), (3, 1), (5, 0)])
+def test_pass_level_slabs_are_shard_invariant(ctx, nshards, flags):
+    im = qs.synth.make_image(256, 208, "420")
+    got = _run_slabs_one_gpu(ctx, im, flags, 2, nshards)
+    _, want = ol.run_oracle(im, flags, 2)
+    for g, c in zip(got, want.comps):
+        assert np.array_equal(g, c.coef)
+
+
+def test_tuning_variants_are_bit_identical(ctx):
+    im = qs.synth.make_image(320, 240, "420")
+    _, want = ol.run_oracle(im, 1, 2)
+    try:
+        for sync in (0, 1):
+            for maxn in (1, 2, 3, 4):
+                ctx.set_tuning(0, sync); ctx.set_tuning(1, maxn)
+                _, out = ctx.do_quantsmooth(im, 1, 2)
+                assert ol.images_equal(out, want), (sync, maxn)
+    finally:
+        ctx.set_tuning(0, 1); ctx.set_tuning(1, 4)
+
+
+# ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----
+def _interval_property(im, out):
+    """Every output coefficient stays inside the quantization interval of its input:
+    |out - in*q| <= q/2 (quantsmooth.h:1551-1564), clamped to +-1023 (2670-2689)."""
+    for a, b in zip(im.comps, out.comps):
+        q = a.quant.astype(np.int32)
+        a0 = a.coef.astype(np.int32) * q
+        lo = np.clip(a0 - (q >> 1), -1023, 1023)
+        hi = np.clip(a0 + (q >> 1), -1023, 1023)
+        assert np.all((b.coef >= lo) & (b.coef <= hi))
+        assert np.array_equal(b.quant, np.ones(64, dtype=np.uint16))
+
+
+def test_8k_q3_properties_and_row_band_parity(ctx):
+    im = qs.synth.make_image(7680, 4320, "420")                     # BASELINE headline shape
+    ret, out = ctx.do_quantsmooth(im, 0, 3)
+    assert ret == 0
+    _interval_property(im, out)
+    # a horizontal band of the image smoothed on its own differs from the full run only next
+    # to the cut (Jacobi dependence reaches 1 block row per iteration): compare the interior
+    band = qs.synth.make_image(7680, 4320, "420", mcu_rows=(100, 112))
+    band.height = 12 * 16
+    _, bo = ol.run_oracle(band, 0, 3, threads=0)
+    for k, (c, b) in enumerate(zip(out.comps, bo.comps)):
+        v = c.v_samp if k == 0 else 1
+        r0 = 100 * (2 if k == 0 else 1)
+        m = 3                                                        # niter block rows of margin
+        assert np.array_equal(c.coef[r0 + m:r0 + b.hblk - m], b.coef[m:b.hblk - m])
+    # shard-count invariance at full size
+    got = _run_slabs_one_gpu(ctx, im, 0, 3, 4)
+    for g, c in zip(got, out.comps):
+        assert np.array_equal(g, c.coef)
+
+
+def test_8k_q6_properties(ctx):
+    im = qs.synth.make_image(7680, 4320, "420")                     # BASELINE config 3
+    ret, out = ctx.do_quantsmooth(im, 7, 3)
+    assert ret == 0
+    assert [c.coef.shape for c in out.comps] == [(540, 960, 64)] * 3
+    assert all(c.h_samp == 1 and c.v_samp == 1 for c in out.comps)
+    _interval_property(qs.CoefImage(im.width, im.height, im.colorspace, im.comps[:1]),
+                       qs.CoefImage(im.width, im.height, im.colorspace, out.comps[:1]))
+    band = qs.synth.make_image(7680, 4320, "420", mcu_rows=(40, 50))
+    band.height = 10 * 16
+    _, bo = ol.run_oracle(band, 7, 3, threads=0)
+    for c, b in zip(out.comps, bo.comps):
+        m = 8                                                        # Y margin 3 -> chroma uses Y: be generous
+        assert np.array_equal(c.coef[80 + m:100 - m], b.coef[m:20 - m])
