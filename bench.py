@@ -233,7 +233,11 @@ def main():
     total_blocks = nblocks_rank
     K, Wm = args.steps, args.warmup
     nbuf = K + Wm
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated stream: the C ABI launches on it, the CUDA events below are recorded on it
+    # and NCCL orders its halo exchange against it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     mpix_job = WIDTH * HEIGHT * world / 1e6
 
     # ---- device-resident arm: a distinct pristine input buffer per step -----------------

@@ -351,6 +351,7 @@ struct ImgState {
 	jpegqs_cuda_image *im;
 	bool skip;             /* early return of quantsmooth.h:2458: image untouched */
 	int need_downsample, stop;
+	int stop_ci;           /* component at which `stop` was raised (components run in order) */
 	uint8_t *image1, *image2;    /* full-res luma plane / down-sampled luma plane */
 	uint8_t *image2_buf, *mem_buf[2];
 	int16_t *coef_up_dev[2];
@@ -377,7 +378,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	size_t bytes = 0; int nquant = 0, max_groups = 0;
 	for (int n = 0; n < nimg; n++) {
 		jpegqs_cuda_image *im = &imgs[n]; ImgState &s = S[n];
-		memset(&s, 0, sizeof(s)); s.im = im; im->upsampled = 0;
+		memset(&s, 0, sizeof(s)); s.im = im; im->upsampled = 0; s.stop_ci = 1 << 30;
 		if (im->ncomp < 1 || im->ncomp > JPEGQS_CUDA_MAX_COMP) return JPEGQS_ERR_ARG;
 		s.need_downsample = (flags & (QS_JOINT_YUV | QS_UPSAMPLE_UV)) && im->is_ycbcr && im->ncomp >= 3 &&
 				im->comp[1].h_samp == 1 && im->comp[1].v_samp == 1 &&
@@ -488,7 +489,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				if (!w.c->has_qtbl) continue;                              /* 2494 */
 				w.extra = (s.image1 || (!ci && s.need_downsample)) ? 1 : 0;      /* 2495 */
 				w.niter2 = qval[n][ci] <= 1 ? 0 : niter;                   /* 2501 */
-				if (qval[n][ci] >= 0x800) s.stop = 1;                      /* 2504 */
+				if (qval[n][ci] >= 0x800 && !s.stop) { s.stop = 1; s.stop_ci = ci; }   /* 2504 */
 				if (w.niter2 + w.extra == 0) continue;                     /* 2542 */
 				if (s.stop) {                                              /* 2551-2566 */
 					CK(qs_launch_scale_clamp(w.coef_dev, (size_t)w.W * w.H * 64, ctx->quant_dev + w.qslot, 1, 0, st));
@@ -529,12 +530,14 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 					CK(cudaStreamSynchronize(st));
 					for (size_t k = 0; k < who.size(); k++) {
 						CompWork *w = who[k]; ImgState &s = S[w->img];
-						if (s.stop) {
+						if (s.stop && w->ci > s.stop_ci) {
 							/* an earlier component of this image already failed: the reference
 							 * would only have de-quantized this one - which the pass just did */
 							w->iterate = false; w->done_clamp = true;
 						} else if (ctx->flags_host[k]) {
-							s.stop = 1; w->iterate = false;               /* falls to the clamp below */
+							/* components run in order in the reference: this one stops here (it
+							 * falls to the clamp below), earlier ones are unaffected */
+							s.stop = 1; s.stop_ci = w->ci; w->iterate = false;
 						}
 					}
 				}
@@ -567,6 +570,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 					cur = (int)((int64_t)progprec * cur / prog_max);
 					prog_thr = (int)(((int64_t)(cur + 1) * prog_max + progprec - 1) / progprec);
 					s.stop = progress(userdata, cur, progprec);
+					if (s.stop) s.stop_ci = w->ci;
 				}
 				if (s.stop) w->iterate = false;
 			}

@@ -59,7 +59,10 @@ class CudaPasses:
     """Pass backend over the C ABI (jpegqs_cuda_pass_idct / jpegqs_cuda_pass_smooth)."""
 
     def __init__(self, ctx, stream: int = 0):
-        self.ctx, self.stream = ctx, stream
+        # stream: a cudaStream_t handle.  0 is mapped to cudaStreamLegacy (0x1) so that the
+        # passes are ordered with torch work on the default stream; the C ABI reserves NULL
+        # for "the context's own stream".
+        self.ctx, self.stream = ctx, (stream or 1)
 
     def _jobs(self, comps: Sequence[SlabComp], top_edge: bool, bottom_edge: bool):
         return [self.ctx.make_job(c.coef.data_ptr(), c.plane.data_ptr(), None, c.wblk, c.rows,

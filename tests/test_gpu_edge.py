@@ -180,11 +180,14 @@ def test_8k_q3_properties_and_row_band_parity(ctx):
     band.height = 12 * 16
     _, bo = ol.run_oracle(band, 0, 3, threads=0)
     for k, (c, b) in enumerate(zip(out.comps, bo.comps)):
-        v = c.v_samp if k == 0 else 1
         r0 = 100 * (2 if k == 0 else 1)
         m = 3                                                        # niter block rows of margin
-        assert np.array_equal(c.coef[r0 + m:r0 + b.hblk - m], b.coef[m:b.hblk - m])
-    # shard-count invariance at full size
+        assert np.array_equal(c.coef[r0 + m:r0 + b.hblk - m], b.coef[m:b.hblk - m]), k
+
+
+def test_8k_q3_shard_invariance(ctx):
+    im = qs.synth.make_image(7680, 4320, "420")
+    _, out = ctx.do_quantsmooth(im, 0, 3)
     got = _run_slabs_one_gpu(ctx, im, 0, 3, 4)
     for g, c in zip(got, out.comps):
         assert np.array_equal(g, c.coef)
@@ -198,9 +201,11 @@ def test_8k_q6_properties(ctx):
     assert all(c.h_samp == 1 and c.v_samp == 1 for c in out.comps)
     _interval_property(qs.CoefImage(im.width, im.height, im.colorspace, im.comps[:1]),
                        qs.CoefImage(im.width, im.height, im.colorspace, out.comps[:1]))
-    band = qs.synth.make_image(7680, 4320, "420", mcu_rows=(40, 50))
-    band.height = 10 * 16
+    # band parity: luma differs within 3 block rows of the cut; chroma is predicted from the
+    # luma plane and then re-sampled to luma resolution, so its disturbed zone is wider
+    band = qs.synth.make_image(7680, 4320, "420", mcu_rows=(40, 64))
+    band.height = 24 * 16
     _, bo = ol.run_oracle(band, 7, 3, threads=0)
-    for c, b in zip(out.comps, bo.comps):
-        m = 8                                                        # Y margin 3 -> chroma uses Y: be generous
-        assert np.array_equal(c.coef[80 + m:100 - m], b.coef[m:20 - m])
+    for k, (c, b) in enumerate(zip(out.comps, bo.comps)):
+        m = 3 if k == 0 else 16
+        assert np.array_equal(c.coef[80 + m:128 - m], b.coef[m:48 - m]), k

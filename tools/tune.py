@@ -27,7 +27,7 @@ ctx.set_profiling(True)
 im = qs.synth.make_image(args.width, args.height, "420")
 dev = torch.device("cuda", 0)
 host = [torch.from_numpy(np.ascontiguousarray(c.coef)) for c in im.comps]
-stream = torch.cuda.current_stream().cuda_stream
+stream = torch.cuda.current_stream().cuda_stream or 1   # 1 = cudaStreamLegacy
 ref_hash = None
 for v in args.variants.split(","):
     sync, maxn = (int(x) for x in v.split(":"))
