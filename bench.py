@@ -48,11 +48,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None        # perf_counter window of the timed region
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -61,7 +62,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -73,7 +74,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
+        scope = "timed region"
+        if len(inside) < 2:                 # region shorter than the sampling period: use the
+            inside = [ln for (t, ln) in self.lines]     # whole loaded phase (warm-up .. end)
+            scope = "warm-up + timed region"
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -85,7 +91,7 @@ class ClockSampler:
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 def make_workload(world, rank):
@@ -200,7 +206,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -271,16 +277,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(Wm):
-        step(i)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(Wm):
+        step(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     smooth_ms, smooth_n, idct_ms, idct_n = 0.0, 0, 0.0, 0
     barrier()
+    sampler.t0 = time.perf_counter()
     e0.record()
     for i in range(K):
         step(Wm + i)
@@ -292,6 +299,7 @@ def main():
             launches += 2 * NITER
     e1.record()
     barrier()
+    sampler.t1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
