@@ -114,3 +114,71 @@ def make_image(width: int, height: int, subsampling: str = "420", quality: int =
         comps.append(Component(coef=coef, quant=q.copy(), h_samp=hs, v_samp=vs,
                                quant_tbl_no=0 if c == 0 else 1))
     return CoefImage(width=width, height=height, colorspace=cs, comps=comps)
+
+
+# ---- the same generator on a torch device (big configurations are generated on the GPU) ----
+def _tri_t(t, period, amp):
+    return ((2 * (t % period) - period).abs() * (2 * amp)) // period - amp
+
+
+def pixels_torch(c, y0, y1, width, sx, sy, seed, noise, device):
+    import torch
+    Y = (torch.arange(y0, y1, dtype=torch.int64, device=device) * sy)[:, None]
+    X = (torch.arange(width, dtype=torch.int64, device=device) * sx)[None, :]
+    amp = 1 if c == 0 else 2
+    v = _tri_t(X + 61 * c, 483, 30) + _tri_t(Y + 50 * c, 369, 30) + _tri_t(X + 2 * Y, 23, 8)
+    v = v + (((X // 37) + (Y // 53)) & 1) * 50 - 25
+    v = torch.div(v, amp, rounding_mode="floor")
+    if noise:
+        M = 0xFFFFFFFF
+        h = ((X * 0x9E3779B1) & M) ^ ((Y * 0x85EBCA77) & M)
+        h = h ^ ((c * 0xC2B2AE3D + seed * 0x27D4EB2F) & M)
+        h = h ^ (h >> 15)
+        h = (h * 0x2C1B3C6D) & M
+        h = h ^ (h >> 12)
+        h = (h * 0x297A2D39) & M
+        h = h ^ (h >> 15)
+        v = v + (h % (2 * noise + 1)) - noise
+    return (128 + v).clamp_(0, 255)
+
+
+def quantize_blocks_torch(px, q):
+    import torch
+    hb, wb = px.shape[0] // 8, px.shape[1] // 8
+    M = torch.from_numpy(_M).to(px.device)
+    b = (px - 128).to(torch.float64).reshape(hb, 8, wb, 8).permute(0, 2, 1, 3)
+    f = (M @ b @ M.T).to(torch.int64).reshape(hb, wb, 64)        # exact: |values| < 2^39
+    qs = torch.from_numpy(q.astype(np.int64)).to(px.device)[None, None, :] << _MBITS
+    mag = (f.abs() + (qs >> 1)) // qs
+    return (torch.sign(f) * mag).to(torch.int16)
+
+
+def make_image_torch(width, height, subsampling="420", quality=50, seed=12345, noise=4,
+                     chunk_rows=32, mcu_rows=None, device="cuda"):
+    """Same values as make_image, but the coefficient arrays are torch int16 tensors on
+    `device` (Component.coef holds the tensor)."""
+    import torch
+    if subsampling == "gray":
+        samp, cs = [(1, 1)], JCS_GRAYSCALE
+    else:
+        hv = {"444": (1, 1), "422": (2, 1), "420": (2, 2), "440": (1, 2)}[subsampling]
+        samp, cs = [hv, (1, 1), (1, 1)], JCS_YCbCr
+    max_h = max(s[0] for s in samp)
+    max_v = max(s[1] for s in samp)
+    tables = [quality_table(ANNEX_K_LUMA, quality), quality_table(ANNEX_K_CHROMA, quality)]
+    comps = []
+    for c, (hs, vs) in enumerate(samp):
+        wb = blocks_for(width, hs, max_h)
+        hb = blocks_for(height, vs, max_v)
+        q = tables[0 if c == 0 else 1]
+        b0, b1 = 0, hb
+        if mcu_rows is not None:
+            b0, b1 = min(mcu_rows[0] * vs, hb), min(mcu_rows[1] * vs, hb)
+        coef = torch.empty((b1 - b0, wb, 64), dtype=torch.int16, device=device)
+        for r0 in range(b0, b1, chunk_rows):
+            r1 = min(b1, r0 + chunk_rows)
+            px = pixels_torch(c, r0 * 8, r1 * 8, wb * 8, max_h // hs, max_v // vs, seed, noise, device)
+            coef[r0 - b0:r1 - b0] = quantize_blocks_torch(px, q)
+        comps.append(Component(coef=coef, quant=q.copy(), h_samp=hs, v_samp=vs,
+                               quant_tbl_no=0 if c == 0 else 1))
+    return CoefImage(width=width, height=height, colorspace=cs, comps=comps)

@@ -47,3 +47,13 @@ def test_slabs_are_rows_of_the_full_image():
 def test_split_handles_more_ranks_than_rows():
     parts = mg.split_mcu_rows(3, 8)
     assert sum(b - a for a, b in parts) == 3 and all(b >= a for a, b in parts)
+
+
+def test_torch_generator_matches_numpy():
+    import torch
+    for (w, h, ss, qual, rng) in [(200, 120, "420", 50, None), (96, 200, "444", 90, (2, 9)), (64, 64, "gray", 30, None)]:
+        a = qs.synth.make_image(w, h, ss, quality=qual, mcu_rows=rng)
+        b = qs.synth.make_image_torch(w, h, ss, quality=qual, mcu_rows=rng, device="cpu", chunk_rows=5)
+        for ca, cb in zip(a.comps, b.comps):
+            assert np.array_equal(ca.coef, cb.coef.numpy())
+            assert np.array_equal(ca.quant, cb.quant)
