@@ -129,6 +129,8 @@ def sharded(cfg, size, flags, niter, check):
            "ms": round(ms, 3), "mpix_s": round(size * size / 1e6 / (ms / 1e3), 1)}
     if check:
         # the sharded result of every rank's slab must equal the same rows of a single-GPU run
+        fn()                                  # `work` now holds the sharded result again
+        torch.cuda.synchronize()
         full = qs.synth.make_image_torch(size, size, "420", device=dev)
         fw = [c.coef.clone() for c in full.comps]
         ctx.run_device(full, [t.data_ptr() for t in fw], [], flags, niter, stream)
