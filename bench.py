@@ -259,12 +259,7 @@ def main():
         passes = mg.CudaPasses(ctx, stream)
         planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev)
                   for c in im.comps]
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
-
-        def allreduce_flag(v):
-            flag.fill_(int(v))
-            dist.all_reduce(flag, op=dist.ReduceOp.BOR)
-            return int(flag.item())
+        allreduce_flag = mg.make_flag_allreduce(dist, dev)
 
         def step(i):
             comps = [mg.SlabComp(dev_bufs[i][k], planes[k], c.wblk, c.hblk, c.quant, k == 0)

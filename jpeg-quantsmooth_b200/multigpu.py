@@ -79,6 +79,22 @@ class CudaPasses:
             c.coef.clamp_(-1023, 1023)
 
 
+def make_flag_allreduce(dist, device):
+    """Returns f(bitmask) -> bitwise OR of the 32-bit mask over all ranks.  NCCL has no BOR,
+    so the mask travels as 32 0/1 lanes reduced with MAX."""
+    import torch
+    lanes = torch.zeros(32, dtype=torch.int32, device=device)
+    weights = [1 << i for i in range(32)]
+
+    def f(mask: int) -> int:
+        mask &= 0xFFFFFFFF
+        lanes.copy_(torch.tensor([(mask >> i) & 1 for i in range(32)], dtype=torch.int32))
+        dist.all_reduce(lanes, op=dist.ReduceOp.MAX)
+        got = lanes.cpu().tolist()
+        return sum(w for w, g in zip(weights, got) if g)
+    return f
+
+
 def exchange_halos(comps: Sequence[SlabComp], rank: int, world: int, dist, group=None):
     """Fill row 0 / row h+1 of every plane with the neighbour slab's adjacent pixel row
     (side border bytes included).  Image top/bottom rows are replicated by the IDCT pass."""

@@ -55,10 +55,7 @@ def _worker(rank, world, port, cfg, outdir):
                                  torch.zeros((rows * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8),
                                  c.wblk, rows, c.quant, k == 0 or ss == "gray"))
 
-    def allreduce_flag(v):
-        t = torch.tensor([int(v)], dtype=torch.int32)
-        dist.all_reduce(t, op=dist.ReduceOp.BOR)
-        return int(t.item())
+    allreduce_flag = mg.make_flag_allreduce(dist, torch.device('cpu'))
 
     stop = mg.run_slab(OraclePasses(flags), comps, flags, niter, rank, world, dist, allreduce_flag)
     np.savez(os.path.join(outdir, f"r{rank}.npz"), stop=stop, **{f"c{k}": c.coef.numpy() for k, c in enumerate(comps)})

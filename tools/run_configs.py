@@ -104,13 +104,7 @@ def sharded(cfg, size, flags, niter, check):
     work = [torch.empty_like(t) for t in src]
     planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev) for c in slab.comps]
     passes = mg.CudaPasses(ctx, stream)
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
-
-    def allreduce_flag(v):
-        if dist is None:
-            return v
-        flag.fill_(int(v)); dist.all_reduce(flag, op=dist.ReduceOp.BOR)
-        return int(flag.item())
+    allreduce_flag = mg.make_flag_allreduce(dist, dev) if dist is not None else None
 
     def copy_only():
         for a, b in zip(work, src):
