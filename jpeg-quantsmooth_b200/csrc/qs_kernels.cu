@@ -86,6 +86,14 @@ __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	out[2] = e2 + t1; out[5] = e2 - t1; out[3] = e3 + t0; out[4] = e3 - t0;
 }
 
+/* four int32 -> four saturated bytes b0 | b1<<8 | b2<<16 | b3<<24 */
+__device__ __forceinline__ uint32_t qs_pack_sat_u8(int b0, int b1, int b2, int b3) {
+	uint32_t t, r;
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(t) : "r"(b3), "r"(b2));
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b1), "r"(b0), "r"(t));
+	return r;
+}
+
 /* second pass over a 64-int workspace (already column-transformed and descaled):
  * rows -> packed pixels lo[y] = px[y][0..3], hi[y] = px[y][4..7] */
 __device__ __forceinline__ void qs_islow_rows(const int *ws, uint32_t *lo, uint32_t *hi) {
@@ -94,12 +102,10 @@ __device__ __forceinline__ void qs_islow_rows(const int *ws, uint32_t *lo, uint3
 		int o[8];
 		qs_islow_1d(ws + y * 8, o);
 #pragma unroll
-		for (int k = 0; k < 8; k++) {
-			int v = (o[k] + (257 << 17)) >> 18;
-			o[k] = min(max(v, 0), 255);
-		}
-		lo[y] = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
-		hi[y] = (uint32_t)o[4] | ((uint32_t)o[5] << 8) | ((uint32_t)o[6] << 16) | ((uint32_t)o[7] << 24);
+		for (int k = 0; k < 8; k++) o[k] = (o[k] + (257 << 17)) >> 18;
+		/* clamp to [0,255] and pack: one saturating I2IP per two pixels (idct.h:509-511) */
+		lo[y] = qs_pack_sat_u8(o[0], o[1], o[2], o[3]);
+		hi[y] = qs_pack_sat_u8(o[4], o[5], o[6], o[7]);
 	}
 }
 
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(256) qs_idct_pass_kernel(const QsJob *__restri
  * bit-identical to the reference's, a2 comes out scaled by 2^-45 and is rescaled (exactly)
  * after the division.  Per (term, coefficient): 1 FADD.SAT + 5 FMUL + 2 FADD, no FMA.
  * ------------------------------------------------------------------------------------------ */
-#define QS_SMOOTH_THREADS 512
+#define QS_SMOOTH_THREADS 512               /* default: 4 warps per sub-partition */
 #define QS_WARP_WORDS (32 * 32 + 14 * 32 * 2)     /* uint32 words per warp region */
 
 __device__ __forceinline__ float qs_px(uint32_t w, int j) {
@@ -420,9 +426,15 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
  * code region at the same time, separated by a named barrier, so that the sub-partition's
  * L0 instruction cache holds ONE unrolled loop body instead of four (the first ncu capture
  * showed stall_no_instruction = 4.3 per issue with free-running warps, profiles/). */
+/* SYNC encodes (level, warps per group): SYNC = level + 16 * WPG; level 0 = free-running,
+ * 1 = barrier per section, 2 = barrier per chunk only */
 template <int SYNC>
 __device__ __forceinline__ void qs_group_sync(int grp) {
-	if (SYNC) asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");
+	if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"((SYNC >> 4) * 32) : "memory");
+}
+template <int SYNC>
+__device__ __forceinline__ void qs_section_sync(int grp) {
+	if ((SYNC & 15) == 1) qs_group_sync<SYNC>(grp);
 }
 
 /* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
@@ -454,12 +466,12 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
 	qs_sec_h<N>(pw, tab, Rs, a2, a3);
-	qs_group_sync<SYNC>(grp);
+	qs_section_sync<SYNC>(grp);
 	qs_sec_border<N>(pw, tab, Rs, a2, a3);
-	qs_group_sync<SYNC>(grp);
+	qs_section_sync<SYNC>(grp);
 	qs_sec_v<N>(pw, tab, Rs, a2, a3);
-	if (DIAG) { qs_group_sync<SYNC>(grp); qs_sec_diag<N>(pw, tab, Rs, a2, a3); }
-	qs_group_sync<SYNC>(grp);
+	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<N>(pw, tab, Rs, a2, a3); }
+	qs_section_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
 }
@@ -477,12 +489,12 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
 	qs_sec_h<1>(pw, tab, Rs, a2, a3);
-	qs_group_sync<SYNC>(grp);
+	qs_section_sync<SYNC>(grp);
 	qs_sec_border<2>(pw, tab, Rs, a2, a3);
-	qs_group_sync<SYNC>(grp);
+	qs_section_sync<SYNC>(grp);
 	qs_sec_v<1>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
-	if (DIAG) { qs_group_sync<SYNC>(grp); qs_sec_diag<2>(pw, tab, Rs, a2, a3); }
-	qs_group_sync<SYNC>(grp);
+	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<2>(pw, tab, Rs, a2, a3); }
+	qs_section_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
 }
@@ -571,7 +583,7 @@ __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, 
 }
 
 template <bool DIAG, int SYNC>
-__global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
+__global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
 		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
 		int flags, int clamp_out) {
 	extern __shared__ __align__(16) uint32_t smem[];
@@ -585,6 +597,7 @@ __global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const Q
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int grp = warp & 3, wig = warp >> 2;                /* sub-partition, warp within it */
+	const int WPG = SYNC >> 4;
 	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
@@ -592,13 +605,13 @@ __global__ void __launch_bounds__(QS_SMOOTH_THREADS, 1) qs_smooth_kernel(const Q
 
 	for (;;) {
 		int tile = 0; bool active = true;
-		if (SYNC) {
-			/* one atomic per group of 4 tiles; the group's warps then stay in lock step */
+		if (SYNC & 15) {
+			/* one atomic per group of WPG tiles; the group's warps then stay in lock step */
 			if (wig == 0 && lane == 0) s_tile[grp] = atomicAdd(tile_counter, 1);
 			qs_group_sync<SYNC>(grp);
 			int gt = *(volatile int *)&s_tile[grp];
-			if (gt * 4 >= total_tiles) break;
-			tile = gt * 4 + wig;
+			if (gt * WPG >= total_tiles) break;
+			tile = gt * WPG + wig;
 			active = tile < total_tiles;
 			if (!active) tile = total_tiles - 1;        /* shadow work keeps the barriers aligned */
 		} else {
@@ -789,21 +802,25 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 	return cudaMemcpyToSymbol(c_nchunks, &n, sizeof(int));
 }
 
-size_t qs_smooth_smem_bytes(int diag) {
-	return (size_t)64 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 +
-			(size_t)(QS_SMOOTH_THREADS / 32) * QS_WARP_WORDS * 4;
+typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
+#define QS_V(d, lvl, wpg) qs_smooth_kernel<d, (lvl) + 16 * (wpg)>
+static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wpg) {
+	if (wpg == 5) return diag ? QS_V(true, 1, 5) : QS_V(false, 1, 5);
+	if (wpg == 6) return diag ? QS_V(true, 1, 6) : QS_V(false, 1, 6);
+	if (diag) return sync == 2 ? QS_V(true, 2, 4) : sync ? QS_V(true, 1, 4) : QS_V(true, 0, 4);
+	return sync == 2 ? QS_V(false, 2, 4) : sync ? QS_V(false, 1, 4) : QS_V(false, 0, 4);
 }
 
-typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
-static qs_smooth_fn qs_smooth_variant(int diag, int sync) {
-	if (diag) return sync ? qs_smooth_kernel<true, 1> : qs_smooth_kernel<true, 0>;
-	return sync ? qs_smooth_kernel<false, 1> : qs_smooth_kernel<false, 0>;
+size_t qs_smooth_smem_bytes(int diag, int wpg) {
+	return (size_t)64 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 + (size_t)(wpg * 4) * QS_WARP_WORDS * 4;
 }
 
 cudaError_t qs_smooth_configure(void) {
-	for (int d = 0; d < 2; d++) for (int sy = 0; sy < 2; sy++) {
-		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy),
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d));
+	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg++) for (int sy = 0; sy < 3; sy++) {
+		if (wpg > 4 && sy != 1) continue;
+		if (qs_smooth_smem_bytes(d, wpg) > 227 * 1024) continue;
+		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wpg),
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wpg));
 		if (e != cudaSuccess) return e;
 	}
 	return cudaSuccess;
@@ -818,15 +835,17 @@ cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tile
 }
 
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, cudaStream_t st) {
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
-	int warps = QS_SMOOTH_THREADS / 32;
+	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
+	if (wpg < 4 || wpg > 6 || qs_smooth_smem_bytes(diag, wpg) > 227 * 1024) wpg = 4;
+	if (wpg > 4) sync = 1;
+	int warps = wpg * 4;
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
-	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
-	qs_smooth_variant(diag, sync)<<<grid, QS_SMOOTH_THREADS, qs_smooth_smem_bytes(diag), st>>>(
+	qs_smooth_variant(diag, sync, wpg)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
 			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
 	return cudaGetLastError();
 }

@@ -30,9 +30,11 @@ host = [torch.from_numpy(np.ascontiguousarray(c.coef)) for c in im.comps]
 stream = torch.cuda.current_stream().cuda_stream or 1   # 1 = cudaStreamLegacy
 ref_hash = None
 for v in args.variants.split(","):
-    sync, maxn = (int(x) for x in v.split(":"))
+    f = [int(x) for x in v.split(":")]
+    sync, maxn, wpg = f[0], f[1], (f[2] if len(f) > 2 else 4)
     ctx.set_tuning(0, sync)
     ctx.set_tuning(1, maxn)
+    ctx.set_tuning(2, wpg)
     sm, n, tot = 0.0, 0, 0.0
     for i in range(args.steps + 1):
         bufs = [h.to(dev) for h in host]
@@ -48,5 +50,5 @@ for v in args.variants.split(","):
     h = hashlib.sha1(b"".join(t.cpu().numpy().tobytes() for t in bufs)).hexdigest()
     if ref_hash is None:
         ref_hash = h
-    print(f"sync={sync} maxn={maxn}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
+    print(f"sync={sync} maxn={maxn} wpg={wpg}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
           f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
