@@ -78,7 +78,7 @@ void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *i
 /* kernel-variant knobs for tuning runs; results are bit-identical for every setting.
  * key 0: lock-step execution of the warps sharing an SM sub-partition (0 = off, 1 = barrier
  *        per section (default), 2 = barrier per chunk)
- * key 1: maximum coefficients per accumulation chunk (1..4, default 4)
+ * key 1: maximum coefficients per accumulation chunk (1..7, default 4)
  * key 2: warps per SM sub-partition (4..6, default 4; larger = fewer registers per thread) */
 int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value);
 

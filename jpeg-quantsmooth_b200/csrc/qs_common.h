@@ -62,12 +62,12 @@ typedef struct {
 #define QS_IDCT_NOPLANE 4     /* do not render pixels (dequantize/clamp only) */
 
 /* chunk schedule of the 63 AC coefficients: 14 anti-diagonal groups (reverse zig-zag,
- * quantsmooth.h:313-322, 1403-1409) split into chunks of <= 4 coefficients that share the
+ * quantsmooth.h:313-322, 1403-1409) split into chunks of <= 7 coefficients that share the
  * pixel-difference work.  type 1 = the group's two edge coefficients (row 0: no vertical
  * terms; column 0: no horizontal terms; quantsmooth.h:1527, 1531). */
 typedef struct {
 	uint8_t type, n, first, pad;
-	uint8_t idx[4];
+	uint8_t idx[8];
 } QsChunk;
 #define QS_MAX_CHUNKS 64
 

@@ -313,7 +313,7 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 1 : value; return 0; }
 	if (key == 2) { ctx->tune_wpg = value < 4 || value > 6 ? 4 : value; return 0; }
 	if (key == 1) {
-		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
+		if (value < 1 || value > 7) return JPEGQS_ERR_ARG;
 		CK(cudaSetDevice(ctx->device));
 		CK(cudaStreamSynchronize(ctx->stream));
 		CK(cudaDeviceSynchronize());

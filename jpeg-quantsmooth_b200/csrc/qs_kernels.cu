@@ -667,6 +667,9 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(grp); }
 			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 7) qs_chunk_full<7, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 6) qs_chunk_full<6, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			else if (ch.n == 5) qs_chunk_full<5, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
