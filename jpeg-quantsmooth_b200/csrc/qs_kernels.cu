@@ -426,15 +426,17 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
  * code region at the same time, separated by a named barrier, so that the sub-partition's
  * L0 instruction cache holds ONE unrolled loop body instead of four (the first ncu capture
  * showed stall_no_instruction = 4.3 per issue with free-running warps, profiles/). */
-/* SYNC encodes (level, warps per group): SYNC = level + 16 * WPG; level 0 = free-running,
- * 1 = barrier per section, 2 = barrier per chunk only */
+/* SYNC encodes (level, warps per sub-partition): SYNC = level + 16 * WPG; level 0 =
+ * free-running, 1 = sub-partition groups with a barrier per section, 2 = per chunk only,
+ * 3 / 4 = the same with the whole CTA as one group (all 4 sub-partitions in one phase) */
 template <int SYNC>
 __device__ __forceinline__ void qs_group_sync(int grp) {
-	if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"((SYNC >> 4) * 32) : "memory");
+	if ((SYNC & 15) >= 3) asm volatile("bar.sync 1, %0;" :: "n"((SYNC >> 4) * 128) : "memory");
+	else if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"((SYNC >> 4) * 32) : "memory");
 }
 template <int SYNC>
 __device__ __forceinline__ void qs_section_sync(int grp) {
-	if ((SYNC & 15) == 1) qs_group_sync<SYNC>(grp);
+	if ((SYNC & 15) == 1 || (SYNC & 15) == 3) qs_group_sync<SYNC>(grp);
 }
 
 /* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
@@ -596,8 +598,9 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 	}
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int grp = warp & 3, wig = warp >> 2;                /* sub-partition, warp within it */
-	const int WPG = SYNC >> 4;
+	const bool CTAG = (SYNC & 15) >= 3;                 /* whole CTA = one lock-step group */
+	int grp = CTAG ? 0 : (warp & 3), wig = CTAG ? warp : (warp >> 2);   /* group, warp within it */
+	const int WPG = CTAG ? (SYNC >> 4) * 4 : (SYNC >> 4);
 	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
@@ -667,9 +670,6 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(grp); }
 			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 7) qs_chunk_full<7, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 6) qs_chunk_full<6, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 5) qs_chunk_full<5, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
 			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
@@ -810,6 +810,8 @@ typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int,
 static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wpg) {
 	if (wpg == 5) return diag ? QS_V(true, 1, 5) : QS_V(false, 1, 5);
 	if (wpg == 6) return diag ? QS_V(true, 1, 6) : QS_V(false, 1, 6);
+	if (sync == 3) return diag ? QS_V(true, 3, 4) : QS_V(false, 3, 4);
+	if (sync == 4) return diag ? QS_V(true, 4, 4) : QS_V(false, 4, 4);
 	if (diag) return sync == 2 ? QS_V(true, 2, 4) : sync ? QS_V(true, 1, 4) : QS_V(true, 0, 4);
 	return sync == 2 ? QS_V(false, 2, 4) : sync ? QS_V(false, 1, 4) : QS_V(false, 0, 4);
 }
@@ -819,7 +821,7 @@ size_t qs_smooth_smem_bytes(int diag, int wpg) {
 }
 
 cudaError_t qs_smooth_configure(void) {
-	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg++) for (int sy = 0; sy < 3; sy++) {
+	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg++) for (int sy = 0; sy < 5; sy++) {
 		if (wpg > 4 && sy != 1) continue;
 		if (qs_smooth_smem_bytes(d, wpg) > 227 * 1024) continue;
 		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wpg),
