@@ -343,33 +343,56 @@ __device__ __forceinline__ void qs_terms_row(const float *d, const float *const 
 	}
 }
 
+/* The four sections below are software pipelined by hand: the packed pixel words of the
+ * NEXT row are loaded before the current row's ~28*N FP instructions and expanded / differenced
+ * after them, so neither the LDS latency nor the PRMT->FADD chain sits in front of the FP work
+ * (in lock step all warps of a sub-partition would otherwise wait for their LDS at the same
+ * time; the first lock-step capture had 34 % of the stall samples on these lines). */
+
 /* horizontal pairs, quantsmooth.h:1527 */
 template <int N>
 __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
-#pragma unroll 1
-	for (int y = 0; y < 8; y++) {
-		float f[8], d[8];
-		qs_unpack8(pw[y * 32], f);
+	float d[8];
+	{
+		float f[8];
+		qs_unpack8(pw[0], f);
 #pragma unroll
 		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
+	}
+#pragma unroll 1
+	for (int y = 0; y < 8; y++) {
+		uint2 wn = pw[((y + 1) & 7) * 32];              /* next row (wraps on the last pass) */
 		qs_terms_row<N, 7>(d, tab, y * 8, Rs, a2, a3);
+		float f[8];
+		qs_unpack8(wn, f);
+#pragma unroll
+		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
 	}
 }
 
-/* top, bottom, left, right border pairs, quantsmooth.h:1529-1530 */
+/* top, bottom, left, right border pairs, quantsmooth.h:1529-1530:
+ * (row 0, above), (row 7, below), (column 0, left), (column 7, right) */
 template <int N>
 __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
-#pragma unroll 1
-	for (int s = 0; s < 4; s++) {
-		int wa = s == 0 ? 0 : s == 1 ? 7 : 6 + s;       /* row 0, row 7, col 0 (8), col 7 (9) */
-		float fa[8], fb[8], d[8];
-		qs_unpack8(pw[wa * 32], fa);
-		qs_unpack8(pw[(10 + s) * 32], fb);
+	float d[8];
+	{
+		float fa[8], fb[8];
+		qs_unpack8(pw[0], fa); qs_unpack8(pw[10 * 32], fb);
 #pragma unroll
 		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
+	}
+#pragma unroll 1
+	for (int s = 0; s < 4; s++) {
+		int sn = (s + 1) & 3;
+		int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;     /* word of the block edge for step sn */
+		uint2 wa = pw[wi * 32], wb = pw[(10 + sn) * 32];
 		qs_terms_row<N, 8>(d, tab, 64 + s * 8, Rs, a2, a3);
+		float fa[8], fb[8];
+		qs_unpack8(wa, fa); qs_unpack8(wb, fb);
+#pragma unroll
+		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
 	}
 }
 
@@ -377,15 +400,21 @@ __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *cons
 template <int N>
 __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
-	float fp[8];
-	qs_unpack8(pw[0], fp);
+	float fp[8], d[8];
+	{
+		float f0[8];
+		qs_unpack8(pw[0], f0); qs_unpack8(pw[32], fp);
+#pragma unroll
+		for (int x = 0; x < 8; x++) d[x] = FS(f0[x], fp[x]);
+	}
 #pragma unroll 1
 	for (int y = 0; y < 7; y++) {
-		float fn[8], d[8];
-		qs_unpack8(pw[(y + 1) * 32], fn);
+		uint2 wn = pw[min(y + 2, 7) * 32];
+		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3);
+		float fn[8];
+		qs_unpack8(wn, fn);
 #pragma unroll
 		for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
-		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3);
 	}
 }
 
@@ -393,19 +422,16 @@ __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *ta
 template <int N>
 __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
-	float fp[8];
-	qs_unpack8(pw[0], fp);
+	float fp[8], d1[8], d2[8];
+	{
+		float f0[8];
+		qs_unpack8(pw[0], f0); qs_unpack8(pw[32], fp);
+#pragma unroll
+		for (int x = 0; x < 7; x++) { d1[x] = FS(f0[x], fp[x + 1]); d2[x] = FS(f0[x + 1], fp[x]); }
+	}
 #pragma unroll 1
 	for (int y = 0; y < 7; y++) {
-		float fn[8], d1[8], d2[8], n1[8], n2[8];
-		qs_unpack8(pw[(y + 1) * 32], fn);
-#pragma unroll
-		for (int x = 0; x < 7; x++) {
-			d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]);
-			n1[x] = -fabsf(d1[x]); n2[x] = -fabsf(d2[x]);
-		}
-#pragma unroll
-		for (int x = 0; x < 8; x++) fp[x] = fn[x];
+		uint2 wn = pw[min(y + 2, 7) * 32];
 #pragma unroll
 		for (int c = 0; c < N; c++) {
 			const float *t = tab[c] + 160 + y * 16;
@@ -415,10 +441,16 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 			float w2[8] = { wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w };
 #pragma unroll
 			for (int x = 0; x < 7; x++) {
-				qs_term(d1[x], n1[x], w1[x], Rs[c], a2[c], a3[c]);
-				qs_term(d2[x], n2[x], w2[x], Rs[c], a2[c], a3[c]);
+				qs_term(d1[x], -fabsf(d1[x]), w1[x], Rs[c], a2[c], a3[c]);
+				qs_term(d2[x], -fabsf(d2[x]), w2[x], Rs[c], a2[c], a3[c]);
 			}
 		}
+		float fn[8];
+		qs_unpack8(wn, fn);
+#pragma unroll
+		for (int x = 0; x < 7; x++) { d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]); }
+#pragma unroll
+		for (int x = 0; x < 8; x++) fp[x] = fn[x];
 	}
 }
 
