@@ -310,8 +310,8 @@ extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->p
  * setting.  key 0: lock-step sub-partition groups (0/1); key 1: max coefficients per chunk (1..4) */
 extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) {
 	if (!ctx) return JPEGQS_ERR_ARG;
-	if (key == 0) { ctx->tune_sync = value < 0 || value > 4 ? 1 : value; return 0; }
-	if (key == 2) { ctx->tune_wpg = value < 4 || value > 6 ? 4 : value; return 0; }
+	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 1 : value; return 0; }
+	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
 	if (key == 1) {
 		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
 		CK(cudaSetDevice(ctx->device));

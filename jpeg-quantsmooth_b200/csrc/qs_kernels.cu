@@ -459,16 +459,15 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
  * L0 instruction cache holds ONE unrolled loop body instead of four (the first ncu capture
  * showed stall_no_instruction = 4.3 per issue with free-running warps, profiles/). */
 /* SYNC encodes (level, warps per sub-partition): SYNC = level + 16 * WPG; level 0 =
- * free-running, 1 = sub-partition groups with a barrier per section, 2 = per chunk only,
- * 3 / 4 = the same with the whole CTA as one group (all 4 sub-partitions in one phase) */
+ * free-running, 1 = sub-partition groups with a barrier per section, 2 = per chunk only */
 template <int SYNC>
 __device__ __forceinline__ void qs_group_sync(int grp) {
-	if ((SYNC & 15) >= 3) asm volatile("bar.sync 1, %0;" :: "n"((SYNC >> 4) * 128) : "memory");
-	else if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"((SYNC >> 4) * 32) : "memory");
+	/* grp = barrier id | (participating threads << 8), see qs_smooth_kernel */
+	if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp & 255), "r"(grp >> 8) : "memory");
 }
 template <int SYNC>
 __device__ __forceinline__ void qs_section_sync(int grp) {
-	if ((SYNC & 15) == 1 || (SYNC & 15) == 3) qs_group_sync<SYNC>(grp);
+	if ((SYNC & 15) == 1) qs_group_sync<SYNC>(grp);
 }
 
 /* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
@@ -630,30 +629,46 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 	}
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const bool CTAG = (SYNC & 15) >= 3;                 /* whole CTA = one lock-step group */
-	int grp = CTAG ? 0 : (warp & 3), wig = CTAG ? warp : (warp >> 2);   /* group, warp within it */
-	const int WPG = CTAG ? (SYNC >> 4) * 4 : (SYNC >> 4);
+	const int WPG = SYNC >> 4;
+	int grp = warp & 3, wig = warp >> 2;                /* sub-partition group, warp within it */
 	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
 	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
 
+	/* Tile schedule of the lock-step groups: first `a_tiles` group tiles of WPG warp tiles
+	 * each (dynamic, one atomic per group tile), then the left-over warp tiles spread evenly
+	 * over ALL groups (1..WPG warps active per group) so that the last wave is short instead
+	 * of leaving most sub-partitions idle for a whole tile time. */
+	const int G = gridDim.x * 4;
+	const int a_tiles = (total_tiles / (WPG * G)) * G;
+	const int left = total_tiles - a_tiles * WPG, lbase = left / G, lextra = left - lbase * G;
+	const int sched_bar = (1 + grp) | ((WPG * 32) << 8);
+
 	for (;;) {
-		int tile = 0; bool active = true;
+		int tile = 0, gsync = 0;
 		if (SYNC & 15) {
-			/* one atomic per group of WPG tiles; the group's warps then stay in lock step */
 			if (wig == 0 && lane == 0) s_tile[grp] = atomicAdd(tile_counter, 1);
-			qs_group_sync<SYNC>(grp);
+			qs_group_sync<SYNC>(sched_bar);
 			int gt = *(volatile int *)&s_tile[grp];
-			if (gt * WPG >= total_tiles) break;
-			tile = gt * WPG + wig;
-			active = tile < total_tiles;
-			if (!active) tile = total_tiles - 1;        /* shadow work keeps the barriers aligned */
+			int nw = WPG;
+			if (gt < a_tiles) tile = gt * WPG + wig;
+			else {
+				int j = gt - a_tiles;
+				if (j >= G) break;
+				nw = lbase + (j < lextra ? 1 : 0);
+				if (nw == 0) break;                     /* groups are handed out in order */
+				tile = a_tiles * WPG + j * lbase + min(j, lextra) + wig;
+			}
+			qs_group_sync<SYNC>(sched_bar);             /* s_tile may be rewritten from here on */
+			if (wig >= nw) continue;                    /* idle warp: wait for the next hand-out */
+			gsync = (5 + grp) | ((nw * 32) << 8);       /* work barrier: only the active warps */
 		} else {
 			if (lane == 0) tile = atomicAdd(tile_counter, 1);
 			tile = __shfl_sync(0xffffffffu, tile, 0);
 			if (tile >= total_tiles) break;
 		}
+		const bool active = true;
 		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 		int nblocks = job->nblocks;
 		int b = (tile - job->tile_begin) * 32 + lane;
@@ -697,15 +712,15 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
 			QsChunk ch = c_chunks[ci];
-			qs_group_sync<SYNC>(grp);
+			qs_group_sync<SYNC>(gsync);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
-			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(grp); }
-			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
-			else qs_chunk_full<1, DIAG, SYNC>(ch, tabs, pw, qd, cs, grp);
+			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			else qs_chunk_full<1, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
 		}
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
@@ -840,10 +855,10 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wpg) qs_smooth_kernel<d, (lvl) + 16 * (wpg)>
 static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wpg) {
-	if (wpg == 5) return diag ? QS_V(true, 1, 5) : QS_V(false, 1, 5);
-	if (wpg == 6) return diag ? QS_V(true, 1, 6) : QS_V(false, 1, 6);
-	if (sync == 3) return diag ? QS_V(true, 3, 4) : QS_V(false, 3, 4);
-	if (sync == 4) return diag ? QS_V(true, 4, 4) : QS_V(false, 4, 4);
+	if (wpg == 6) {
+		if (diag) return sync == 2 ? QS_V(true, 2, 6) : sync ? QS_V(true, 1, 6) : QS_V(true, 0, 6);
+		return sync == 2 ? QS_V(false, 2, 6) : sync ? QS_V(false, 1, 6) : QS_V(false, 0, 6);
+	}
 	if (diag) return sync == 2 ? QS_V(true, 2, 4) : sync ? QS_V(true, 1, 4) : QS_V(true, 0, 4);
 	return sync == 2 ? QS_V(false, 2, 4) : sync ? QS_V(false, 1, 4) : QS_V(false, 0, 4);
 }
@@ -853,8 +868,7 @@ size_t qs_smooth_smem_bytes(int diag, int wpg) {
 }
 
 cudaError_t qs_smooth_configure(void) {
-	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg++) for (int sy = 0; sy < 5; sy++) {
-		if (wpg > 4 && sy != 1) continue;
+	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg += 2) for (int sy = 0; sy < 3; sy++) {
 		if (qs_smooth_smem_bytes(d, wpg) > 227 * 1024) continue;
 		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wpg),
 				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wpg));
@@ -877,8 +891,8 @@ cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, 
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
 	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
-	if (wpg < 4 || wpg > 6 || qs_smooth_smem_bytes(diag, wpg) > 227 * 1024) wpg = 4;
-	if (wpg > 4) sync = 1;
+	if ((wpg != 4 && wpg != 6) || qs_smooth_smem_bytes(diag, wpg) > 227 * 1024) wpg = 4;
+	if (sync < 0 || sync > 2) sync = 1;
 	int warps = wpg * 4;
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
