@@ -146,14 +146,17 @@ def test_pass_level_slabs_are_shard_invariant(ctx, nshards, flags):
 def test_tuning_variants_are_bit_identical(ctx):
     im = qs.synth.make_image(320, 240, "420")
     _, want = ol.run_oracle(im, 1, 2)
+    _, want0 = ol.run_oracle(im, 0, 2)
     try:
-        for sync in (0, 1):
-            for maxn in (1, 2, 3, 4):
-                ctx.set_tuning(0, sync); ctx.set_tuning(1, maxn)
-                _, out = ctx.do_quantsmooth(im, 1, 2)
-                assert ol.images_equal(out, want), (sync, maxn)
+        for wpg in (4, 6):
+            for sync in (0, 1, 2):
+                for maxn in (1, 2, 3, 4):
+                    ctx.set_tuning(0, sync); ctx.set_tuning(1, maxn); ctx.set_tuning(2, wpg)
+                    _, out = ctx.do_quantsmooth(im, 1 if wpg == 4 else 0, 2)
+                    ref = want if wpg == 4 else want0
+                    assert ol.images_equal(out, ref), (sync, maxn, wpg)
     finally:
-        ctx.set_tuning(0, 1); ctx.set_tuning(1, 4)
+        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4)
 
 
 # ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----
