@@ -79,7 +79,8 @@ void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *i
  * key 0: lock-step execution of the warps sharing an SM sub-partition (0 = off, 1 = barrier
  *        per section (default), 2 = barrier per chunk)
  * key 1: maximum coefficients per accumulation chunk (1..7, default 4)
- * key 2: warps per SM sub-partition (4..6, default 4; larger = fewer registers per thread) */
+ * key 2: warps per SM sub-partition (4 or 6, default 4; 6 = 80 registers per thread)
+ * key 3: independent lock-step groups per sub-partition (1..3, default 1) */
 int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value);
 
 /* pinned host memory for coefficient arrays (fast H2D/D2H); plain malloc'd memory works too */

@@ -121,7 +121,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
-	int tune_sync, tune_maxn, tune_wpg;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
+	int tune_sync, tune_maxn, tune_wpg, tune_gs;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -188,7 +188,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4;
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1;
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -311,6 +311,7 @@ extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->p
 extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) {
 	if (!ctx) return JPEGQS_ERR_ARG;
 	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 1 : value; return 0; }
+	if (key == 3) { ctx->tune_gs = value < 1 || value > 3 ? 1 : value; return 0; }
 	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
 	if (key == 1) {
 		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
@@ -558,7 +559,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				const QsJob *jd; int tiles;
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
 				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
-				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
+				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
@@ -712,6 +713,6 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	int rc = stage_jobs(ctx, njobs, jobs, 1, st, &jd, &tiles);
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
-	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
+	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 	return 0;
 }

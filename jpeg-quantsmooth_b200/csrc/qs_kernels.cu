@@ -458,16 +458,23 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
  * code region at the same time, separated by a named barrier, so that the sub-partition's
  * L0 instruction cache holds ONE unrolled loop body instead of four (the first ncu capture
  * showed stall_no_instruction = 4.3 per issue with free-running warps, profiles/). */
-/* SYNC encodes (level, warps per sub-partition): SYNC = level + 16 * WPG; level 0 =
- * free-running, 1 = sub-partition groups with a barrier per section, 2 = per chunk only */
+/* SYNC encodes (level, warps per sub-partition, lock-step groups per sub-partition):
+ * SYNC = level + 16 * WPS + 256 * GS; level 0 = free-running, 1 = barrier per section,
+ * 2 = barrier per chunk only.  With GS > 1 a sub-partition hosts GS independent groups that
+ * drift against each other, so the ALU-heavy refresh of one overlaps the FMA-heavy sums of
+ * the other while the L0 instruction cache still only sees GS loop bodies. */
+#define QS_SYNC(level, wps, gs) ((level) + 16 * (wps) + 256 * (gs))
+#define QS_SYNC_LEVEL(s) ((s) & 15)
+#define QS_SYNC_WPS(s) (((s) >> 4) & 15)
+#define QS_SYNC_GS(s) ((s) >> 8)
 template <int SYNC>
 __device__ __forceinline__ void qs_group_sync(int grp) {
 	/* grp = barrier id | (participating threads << 8), see qs_smooth_kernel */
-	if (SYNC & 15) asm volatile("bar.sync %0, %1;" :: "r"(grp & 255), "r"(grp >> 8) : "memory");
+	if (QS_SYNC_LEVEL(SYNC)) asm volatile("bar.sync %0, %1;" :: "r"(grp & 255), "r"(grp >> 8) : "memory");
 }
 template <int SYNC>
 __device__ __forceinline__ void qs_section_sync(int grp) {
-	if ((SYNC & 15) == 1) qs_group_sync<SYNC>(grp);
+	if (QS_SYNC_LEVEL(SYNC) == 1) qs_group_sync<SYNC>(grp);
 }
 
 /* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
@@ -616,11 +623,11 @@ __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, 
 }
 
 template <bool DIAG, int SYNC>
-__global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
+__global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
 		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
 		int flags, int clamp_out) {
 	extern __shared__ __align__(16) uint32_t smem[];
-	__shared__ int s_tile[4];
+	__shared__ int s_tile[16];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 	float *tabs = (float *)smem;
 	{
@@ -629,45 +636,47 @@ __global__ void __launch_bounds__((SYNC >> 4) * 128, 1) qs_smooth_kernel(const Q
 	}
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int WPG = SYNC >> 4;
-	int grp = warp & 3, wig = warp >> 2;                /* sub-partition group, warp within it */
+	const int NG = 4 * QS_SYNC_GS(SYNC);                /* lock-step groups in this CTA */
+	const int WPG = QS_SYNC_WPS(SYNC) / QS_SYNC_GS(SYNC);   /* warps per group, all on one sub-partition */
+	int grp = warp % NG, wig = warp / NG;
 	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
 	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
 
 	/* Tile schedule of the lock-step groups: first `a_tiles` group tiles of WPG warp tiles
-	 * each (dynamic, one atomic per group tile), then the left-over warp tiles spread evenly
-	 * over ALL groups (1..WPG warps active per group) so that the last wave is short instead
-	 * of leaving most sub-partitions idle for a whole tile time. */
-	const int G = gridDim.x * 4;
+	 * each (dynamic, one atomic per group tile); then the left-over warp tiles are spread
+	 * evenly over ALL groups (0..WPG warps active per group, static) so that the last wave is
+	 * short instead of leaving most sub-partitions idle for a whole tile time. */
+	const int G = gridDim.x * NG;
 	const int a_tiles = (total_tiles / (WPG * G)) * G;
 	const int left = total_tiles - a_tiles * WPG, lbase = left / G, lextra = left - lbase * G;
-	const int sched_bar = (1 + grp) | ((WPG * 32) << 8);
+	int gbar = (1 + grp) | ((WPG * 32) << 8);           /* barrier id | participating threads */
+	bool last = false;
 
 	for (;;) {
-		int tile = 0, gsync = 0;
-		if (SYNC & 15) {
+		int tile = 0;
+		if (QS_SYNC_LEVEL(SYNC)) {
+			if (last) break;
 			if (wig == 0 && lane == 0) s_tile[grp] = atomicAdd(tile_counter, 1);
-			qs_group_sync<SYNC>(sched_bar);
+			qs_group_sync<SYNC>(gbar);
 			int gt = *(volatile int *)&s_tile[grp];
-			int nw = WPG;
+			qs_group_sync<SYNC>(gbar);                  /* s_tile may be rewritten from here on */
 			if (gt < a_tiles) tile = gt * WPG + wig;
 			else {
-				int j = gt - a_tiles;
-				if (j >= G) break;
-				nw = lbase + (j < lextra ? 1 : 0);
-				if (nw == 0) break;                     /* groups are handed out in order */
+				int j = blockIdx.x * NG + grp;          /* this group's left-over share */
+				int nw = lbase + (j < lextra ? 1 : 0);
+				if (wig >= nw) break;                   /* idle warps leave; the rest re-size the barrier */
 				tile = a_tiles * WPG + j * lbase + min(j, lextra) + wig;
+				gbar = (1 + grp) | ((nw * 32) << 8);
+				last = true;
 			}
-			qs_group_sync<SYNC>(sched_bar);             /* s_tile may be rewritten from here on */
-			if (wig >= nw) continue;                    /* idle warp: wait for the next hand-out */
-			gsync = (5 + grp) | ((nw * 32) << 8);       /* work barrier: only the active warps */
 		} else {
 			if (lane == 0) tile = atomicAdd(tile_counter, 1);
 			tile = __shfl_sync(0xffffffffu, tile, 0);
 			if (tile >= total_tiles) break;
 		}
+		const int gsync = gbar;
 		const bool active = true;
 		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 		int nblocks = job->nblocks;
@@ -853,14 +862,17 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 }
 
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
-#define QS_V(d, lvl, wpg) qs_smooth_kernel<d, (lvl) + 16 * (wpg)>
-static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wpg) {
-	if (wpg == 6) {
-		if (diag) return sync == 2 ? QS_V(true, 2, 6) : sync ? QS_V(true, 1, 6) : QS_V(true, 0, 6);
-		return sync == 2 ? QS_V(false, 2, 6) : sync ? QS_V(false, 1, 6) : QS_V(false, 0, 6);
+#define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
+static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
+	if (wps == 6) {
+		if (gs == 3) return diag ? QS_V(true, 2, 6, 3) : QS_V(false, 2, 6, 3);
+		if (gs == 2) return diag ? QS_V(true, 2, 6, 2) : QS_V(false, 2, 6, 2);
+		if (diag) return sync == 2 ? QS_V(true, 2, 6, 1) : QS_V(true, 1, 6, 1);
+		return sync == 2 ? QS_V(false, 2, 6, 1) : QS_V(false, 1, 6, 1);
 	}
-	if (diag) return sync == 2 ? QS_V(true, 2, 4) : sync ? QS_V(true, 1, 4) : QS_V(true, 0, 4);
-	return sync == 2 ? QS_V(false, 2, 4) : sync ? QS_V(false, 1, 4) : QS_V(false, 0, 4);
+	if (gs == 2) return diag ? QS_V(true, 2, 4, 2) : QS_V(false, 2, 4, 2);
+	if (diag) return sync == 2 ? QS_V(true, 2, 4, 1) : sync ? QS_V(true, 1, 4, 1) : QS_V(true, 0, 4, 1);
+	return sync == 2 ? QS_V(false, 2, 4, 1) : sync ? QS_V(false, 1, 4, 1) : QS_V(false, 0, 4, 1);
 }
 
 size_t qs_smooth_smem_bytes(int diag, int wpg) {
@@ -868,12 +880,13 @@ size_t qs_smooth_smem_bytes(int diag, int wpg) {
 }
 
 cudaError_t qs_smooth_configure(void) {
-	for (int d = 0; d < 2; d++) for (int wpg = 4; wpg <= 6; wpg += 2) for (int sy = 0; sy < 3; sy++) {
-		if (qs_smooth_smem_bytes(d, wpg) > 227 * 1024) continue;
-		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wpg),
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wpg));
-		if (e != cudaSuccess) return e;
-	}
+	for (int d = 0; d < 2; d++) for (int wps = 4; wps <= 6; wps += 2) for (int gs = 1; gs <= 3; gs++)
+		for (int sy = 0; sy < 3; sy++) {
+			if (qs_smooth_smem_bytes(d, wps) > 227 * 1024) continue;
+			cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wps, gs),
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wps));
+			if (e != cudaSuccess) return e;
+		}
 	return cudaSuccess;
 }
 
@@ -886,7 +899,7 @@ cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tile
 }
 
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st) {
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, int gs, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
@@ -896,7 +909,8 @@ cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, 
 	int warps = wpg * 4;
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
-	qs_smooth_variant(diag, sync, wpg)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
+	if (gs < 1 || gs > 3 || (wpg == 4 && gs == 3)) gs = 1;
+	qs_smooth_variant(diag, sync, wpg, gs)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
 			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
 	return cudaGetLastError();
 }

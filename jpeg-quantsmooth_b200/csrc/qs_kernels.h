@@ -10,7 +10,7 @@ cudaError_t qs_smooth_configure(void);
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
 		int *bad_flags, cudaStream_t st);
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st);
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, int gs, cudaStream_t st);
 cudaError_t qs_launch_scale_clamp(int16_t *coef, size_t n, const QsQuantDev *qd, int dequant, int clamp,
 		cudaStream_t st);
 cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride,

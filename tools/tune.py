@@ -31,10 +31,11 @@ stream = torch.cuda.current_stream().cuda_stream or 1   # 1 = cudaStreamLegacy
 ref_hash = None
 for v in args.variants.split(","):
     f = [int(x) for x in v.split(":")]
-    sync, maxn, wpg = f[0], f[1], (f[2] if len(f) > 2 else 4)
+    sync, maxn, wpg, gs = f[0], f[1], (f[2] if len(f) > 2 else 4), (f[3] if len(f) > 3 else 1)
     ctx.set_tuning(0, sync)
     ctx.set_tuning(1, maxn)
     ctx.set_tuning(2, wpg)
+    ctx.set_tuning(3, gs)
     sm, n, tot = 0.0, 0, 0.0
     for i in range(args.steps + 1):
         bufs = [h.to(dev) for h in host]
@@ -50,5 +51,5 @@ for v in args.variants.split(","):
     h = hashlib.sha1(b"".join(t.cpu().numpy().tobytes() for t in bufs)).hexdigest()
     if ref_hash is None:
         ref_hash = h
-    print(f"sync={sync} maxn={maxn} wpg={wpg}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
+    print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
           f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
