@@ -29,7 +29,7 @@ enum {
 	JPEGQS_DIAGONALS = 1,           /* q>=4: add the 98 diagonal pair terms  */
 	JPEGQS_JOINT_YUV = 2,           /* q>=5: chroma predicted from luma      */
 	JPEGQS_UPSAMPLE_UV = 4,         /* q>=6: chroma re-sampled at luma size  */
-	JPEGQS_LOW_QUALITY = 8,         /* q<=2: one-shot filter (not on device) */
+	JPEGQS_LOW_QUALITY = 8,         /* q<=2: one-shot 8-neighbour filter      */
 	JPEGQS_NO_REBALANCE = 16,
 	JPEGQS_NO_REBALANCE_UV = 32,
 	JPEGQS_TRANSCODE = 64,

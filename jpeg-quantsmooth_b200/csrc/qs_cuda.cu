@@ -364,10 +364,6 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		int progprec, jpegqs_cuda_progress_fn progress, void *userdata, bool on_device, int *ret,
 		cudaStream_t st) {
 	if (!ctx || nimg < 0 || (nimg && !imgs)) return JPEGQS_ERR_ARG;
-	if (flags & QS_LOW_QUALITY) {
-		snprintf(ctx->err, sizeof(ctx->err), "JPEGQS_LOW_QUALITY (quality 0-2) is not implemented on the CUDA back end");
-		return JPEGQS_ERR_UNSUPPORTED;
-	}
 	if (progress && nimg != 1) return JPEGQS_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
 	ctx->launches = 0; ctx->last_ms = 0;
@@ -559,7 +555,8 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				const QsJob *jd; int tiles;
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
 				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
-				CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+				if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, (int)jobs.size(), tiles, flags, clampv, st));
+				else CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
@@ -707,12 +704,12 @@ extern "C" int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpeg
 extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int flags,
 		int clamp_out, void *stream) {
 	if (!ctx) return JPEGQS_ERR_ARG;
-	if (flags & QS_LOW_QUALITY) return JPEGQS_ERR_UNSUPPORTED;
 	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
 	const QsJob *jd; int tiles;
 	int rc = stage_jobs(ctx, njobs, jobs, 1, st, &jd, &tiles);
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
-	CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, st));
+	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 	return 0;
 }

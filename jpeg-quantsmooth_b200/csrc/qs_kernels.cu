@@ -565,6 +565,24 @@ __device__ __forceinline__ void qs_refresh(const uint32_t *cw, uint2 *pw) {
 	pw[9 * 32] = qs_gather_col(hi, 3);
 }
 
+/* fdct_clamp, quantsmooth.h:343-347, 551-561: FDCT, round half away, clamp every
+ * coefficient (DC included) into the quantization interval of its current value */
+__device__ __forceinline__ void qs_fdct_clamp(float *f, const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	qs_fdct_8x8(f);
+#pragma unroll
+	for (int x = 0; x < 64; x++) {
+		uint16_t *slot = cs + (x >> 1) * 64 + (x & 1);
+		int c = (short)*slot;
+		int q = __ldg(&qd->q[x]);
+		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[x]));
+		int d0 = (q - 1) >> 1, d1 = q >> 1;
+		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
+		int add = qs_cvtt_x86(roundf(f[x]));
+		add = min(add, dh); add = max(add, dl);
+		*slot = (uint16_t)add;
+	}
+}
+
 /* JOINT_YUV chroma predictor + fdct_clamp, quantsmooth.h:577-579, 894-921, 551-561 */
 __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, const uint8_t *__restrict__ img2,
 		int stride, const QsQuantDev *__restrict__ qd, uint16_t *cs) {
@@ -581,19 +599,7 @@ __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, c
 			f[y * 8 + x] = a > 128.0f ? 128.0f : a;
 		}
 	}
-	qs_fdct_8x8(f);
-#pragma unroll
-	for (int x = 0; x < 64; x++) {
-		uint16_t *slot = cs + (x >> 1) * 64 + (x & 1);
-		int c = (short)*slot;
-		int q = __ldg(&qd->q[x]);
-		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[x]));
-		int d0 = (q - 1) >> 1, d1 = q >> 1;
-		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
-		int add = qs_cvtt_x86(roundf(f[x]));
-		add = min(add, dh); add = max(add, dl);
-		*slot = (uint16_t)add;
-	}
+	qs_fdct_clamp(f, qd, cs);
 }
 
 /* rebalance, quantsmooth.h:1566-1568, 1823-1848 */
@@ -757,6 +763,104 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 }
 
 /* ------------------------------------------------------------------------------------------
+ * LOW_QUALITY (q0-2) block function, quantsmooth.h:924-938 + 1162-1178 (scalar branch, which
+ * truncates `a -= a0/an` to int - the reference's SIMD branches keep it in float and give
+ * different results; the scalar build is the contract).  One thread per block, no tables:
+ * range from the coefficient magnitudes, 8-neighbour one-shot filter, FDCT + clamp,
+ * rebalance.  ~10 k instructions and ~420 B of traffic per block: the HBM-bound mode.
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, int *r) {
+	/* 10 pixels x = -1..8 of one plane row; p points at x = 0 (8-byte aligned) */
+	uint2 w = *(const uint2 *)p;
+	r[0] = p[-1]; r[9] = p[8];
+#pragma unroll
+	for (int k = 0; k < 4; k++) { r[1 + k] = (w.x >> (8 * k)) & 0xff; r[5 + k] = (w.y >> (8 * k)) & 0xff; }
+}
+
+__global__ void __launch_bounds__(128) qs_lowq_kernel(const QsJob *__restrict__ jobs, int njobs, int total_tiles,
+		int flags, int clamp_out) {
+	__shared__ uint32_t sm[4 * 32 * 32];
+	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int tile = blockIdx.x * 4 + warp;
+	if (tile >= total_tiles) return;
+	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
+	int b = (tile - job->tile_begin) * 32 + lane;
+	if (b >= job->nblocks) return;
+	uint32_t *cw = sm + warp * 1024 + lane;
+	uint16_t *cs = (uint16_t *)(sm + warp * 1024) + lane * 2;
+	int W = job->wblk, stride = job->stride;
+	int by = b / W, bx = b - by * W;
+	int16_t *cptr = job->coef + (size_t)b * 64;
+	const QsQuantDev *qd = job->quant;
+	const uint8_t *img = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+	{
+		const int4 *p = (const int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int4 v = p[j];
+			cw[(j * 4 + 0) * 32] = v.x; cw[(j * 4 + 1) * 32] = v.y;
+			cw[(j * 4 + 2) * 32] = v.z; cw[(j * 4 + 3) * 32] = v.w;
+		}
+	}
+	if (job->plane2) {                                  /* JOINT_YUV predictor, then straight to rebalance (928) */
+		const uint8_t *img2 = job->plane2 + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+		qs_joint_predict(img, img2, stride, qd, cs);
+	} else {
+		float range = 0.0f; int sum = 0;
+#pragma unroll 1
+		for (int x = 1; x < 64; x++) {
+			int a = (short)cs[(x >> 1) * 64 + (x & 1)]; a = a < 0 ? -a : a;
+			range = FA(range, (float)((int)__ldg(&qd->q[x]) * a)); sum += a;
+		}
+		if (sum) range = FM(range, __fdiv_rn(4.0f, (float)sum));
+		if (range > 128.0f) range = 128.0f;
+		range = roundf(range);
+		const float c0 = 2.0f, c1 = FM(2.0f, 0.70710678118654752440f);   /* c0 * sqrtf(0.5f) */
+		float f[64];
+		int r0[10], r1[10], r2[10];
+		qs_lowq_row(img - stride, r0); qs_lowq_row(img, r1);
+#pragma unroll
+		for (int y = 0; y < 8; y++) {
+			qs_lowq_row(img + (size_t)(y + 1) * stride, r2);
+#pragma unroll
+			for (int x = 0; x < 8; x++) {
+				int a = r1[x + 1]; float a0 = 0.0f, an = 0.0f;
+#define NB(c_, v_) { float t0 = (float)(a - (v_)), t = FS(range, fabsf(t0)), aw; \
+	t = t < 0.0f ? 0.0f : t; t = FM(t, t); aw = FM(c_, t); a0 = FA(a0, FM(FM(t0, t), aw)); an = FA(an, FM(aw, aw)); }
+				NB(c1, r0[x]) NB(c0, r0[x + 1]) NB(c1, r0[x + 2])
+				NB(c0, r1[x]) NB(c0, r1[x + 2])
+				NB(c1, r2[x]) NB(c0, r2[x + 1]) NB(c1, r2[x + 2])
+#undef NB
+				if (an > 0.0f) a = qs_cvtt_x86(FS((float)a, __fdiv_rn(a0, an)));
+				f[y * 8 + x] = (float)(a - 128);
+			}
+#pragma unroll
+			for (int k = 0; k < 10; k++) { r0[k] = r1[k]; r1[k] = r2[k]; }
+		}
+		qs_fdct_clamp(f, qd, cs);
+	}
+	if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
+		qs_rebalance(qd, cs);
+	{
+		int4 *p = (int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			uint32_t w[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				w[k] = cw[(j * 4 + k) * 32];
+				if (clamp_out) {
+					int a = (short)(w[k] & 0xffff), c2 = (int)w[k] >> 16;
+					a = min(max(a, -1023), 1023); c2 = min(max(c2, -1023), 1023);
+					w[k] = (uint32_t)(a & 0xffff) | ((uint32_t)c2 << 16);
+				}
+			}
+			p[j] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
  * dequantize-only / clamp-only fallbacks (quantsmooth.h:2551-2566, 2670-2689)
  * ------------------------------------------------------------------------------------------ */
 __global__ void qs_scale_clamp_kernel(int16_t *__restrict__ coef, size_t n, const QsQuantDev *__restrict__ qd,
@@ -912,6 +1016,13 @@ cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, 
 	if (gs < 1 || gs > 3 || (wpg == 4 && gs == 3)) gs = 1;
 	qs_smooth_variant(diag, sync, wpg, gs)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
 			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_launch_lowq(const QsJob *jobs_dev, int njobs, int total_tiles, int flags, int clamp_out,
+		cudaStream_t st) {
+	if (total_tiles <= 0) return cudaSuccess;
+	qs_lowq_kernel<<<(total_tiles + 3) / 4, 128, 0, st>>>(jobs_dev, njobs, total_tiles, flags, clamp_out);
 	return cudaGetLastError();
 }
 

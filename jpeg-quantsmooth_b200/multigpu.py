@@ -121,8 +121,8 @@ def run_slab(passes, comps: Sequence[SlabComp], flags: int, niter: int, rank: in
     """The iteration loop of do_quantsmooth (reference quantsmooth.h:2580-2689) on one slab.
     Returns the reference's `stop`.  Components are independent for flags without
     JOINT_YUV/UPSAMPLE_UV, so they share the passes."""
-    if flags & (2 | 4 | 8):
-        raise NotImplementedError("multi-GPU sharding supports q3/q4 (flags DIAGONALS, NO_REBALANCE*) only")
+    if flags & (2 | 4):
+        raise NotImplementedError("multi-GPU sharding does not cover JOINT_YUV / UPSAMPLE_UV yet (DESIGN.md 5)")
     niter = max(0, min(int(niter), 100))
     if niter == 0:
         return 0

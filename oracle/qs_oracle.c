@@ -246,7 +246,7 @@ static float regress_scale(const uint8_t *A, const uint8_t *B, int stride, int32
  *      JOINT_YUV 894-921, main loop 1396-1409 + 1517-1565, rebalance 1566-1568 + 1823-1848).
  *      image  -> top-left pixel of this block in the component's sample plane
  *      image2 -> same position in the down-sampled luma plane, or NULL
- *      tables -> qso_tables() output.  LOW_QUALITY is not restated (not on the path). */
+ *      tables -> qso_tables() output (unused with LOW_QUALITY, quantsmooth.h:924-938, 1162-1178). */
 void qso_smooth_block(int16_t *coef, const uint16_t *q, const uint8_t *image,
 		const uint8_t *image2, int stride, int flags, const float *tables, int luma) {
 	uint8_t buf[64], border[32]; int k, x, y, need_refresh = 1;
@@ -262,6 +262,32 @@ void qso_smooth_block(int16_t *coef, const uint16_t *q, const uint8_t *image,
 			fbuf[y * 8 + x] = a > 128 ? 128 : a;
 		}
 		qso_fdct_clamp(fbuf, coef, q);
+	}
+
+	if (flags & QSO_LOW_QUALITY) {                            /* 924-938, 1162-1178 (scalar) */
+		if (!image2) {
+			float fbuf[64], range = 0, c0 = 2, c1 = c0 * sqrtf(0.5f); int sum = 0;
+			for (x = 1; x < 64; x++) {
+				int a = coef[x]; a = a < 0 ? -a : a;
+				range = range + (float)(q[x] * a); sum += a;
+			}
+			if (sum) range = range * (4.0f / (float)sum);
+			if (range > 128) range = 128;
+			range = roundf(range);
+			for (y = 0; y < 8; y++) for (x = 0; x < 8; x++) {
+				int a = image[y * stride + x]; float a0 = 0, an = 0;
+#define NB(c_, dx, dy) { float t0 = (float)(a - image[(y + (dy)) * stride + x + (dx)]), t = range - fabsf(t0), aw; \
+	t = t < 0 ? 0 : t; t = t * t; aw = (c_) * t; a0 = a0 + t0 * t * aw; an = an + aw * aw; }
+				NB(c1, -1, -1) NB(c0, 0, -1) NB(c1, 1, -1)
+				NB(c0, -1, 0) NB(c0, 1, 0)
+				NB(c1, -1, 1) NB(c0, 0, 1) NB(c1, 1, 1)
+#undef NB
+				if (an > 0.0f) a = cvtt((float)a - a0 / an);   /* int a -= float: truncates */
+				fbuf[y * 8 + x] = (float)(a - 128);
+			}
+			qso_fdct_clamp(fbuf, coef, q);
+		}
+		goto rebalance;
 	}
 
 	for (x = 0; x < 8; x++) {                                 /* 1396-1401 */
@@ -307,6 +333,7 @@ void qso_smooth_block(int16_t *coef, const uint16_t *q, const uint8_t *image,
 		}
 	}
 
+rebalance:
 	if (flags & QSO_NO_REBALANCE) return;                                     /* 1566-1568 */
 	if (!luma && (flags & QSO_NO_REBALANCE_UV)) return;
 	{                                                                         /* 1823-1848 */

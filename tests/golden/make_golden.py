@@ -33,6 +33,9 @@ CASES = [
     ("422_q6", (64, 32, "422", 50, 8), 7, 1),
     ("420_norebal", (48, 32, "420", 50, 9), 16, 2),
     ("420_norebal_uv", (48, 32, "420", 50, 10), 33, 2),
+    ("420_lowq0", (64, 48, "420", 25, 11), 8 | 1, 3),
+    ("420_lowq2", (64, 48, "420", 30, 12), 8 | 7, 2),
+    ("gray_lowq", (40, 32, "gray", 15, 13), 8, 3),
 ]
 
 

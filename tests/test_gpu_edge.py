@@ -47,10 +47,18 @@ def test_niter_zero_and_clamping_of_niter(ctx):
     assert ol.images_equal(out, out2)
 
 
-def test_low_quality_is_refused_not_faked(ctx):
-    im = qs.synth.make_image(32, 32, "gray")
-    with pytest.raises(qs.cuda.QsError):
-        ctx.do_quantsmooth(im, 8, 3)
+@pytest.mark.parametrize("w,h,ss,flags,niter,quality", [
+    (256, 128, "420", 8 | 1, 3, 30),       # -q 0
+    (250, 130, "420", 8 | 3, 2, 20),       # -q 1 (JOINT_YUV predictor, then rebalance only)
+    (256, 128, "420", 8 | 7, 2, 40),       # -q 2 (+ UPSAMPLE_UV)
+    (128, 64, "gray", 8, 3, 10),
+    (256, 128, "444", 8 | 7, 2, 50),
+    (64, 48, "420", 8 | 16, 2, 30),
+    (1920, 1080, "420", 8 | 1, 3, 25),
+])
+def test_low_quality(ctx, w, h, ss, flags, niter, quality):
+    """LOW_QUALITY (q0-2): the scalar branch's int truncation is the contract."""
+    _same(ctx, qs.synth.make_image(w, h, ss, quality=quality), flags, niter)
 
 
 def test_component_without_table_and_four_components(ctx):
@@ -134,7 +142,7 @@ def _run_slabs_one_gpu(ctx, im, flags, niter, nshards):
     return [np.concatenate([s[k].coef.cpu().numpy() for s in slabs], axis=0) for k in range(len(im.comps))]
 
 
-@pytest.mark.parametrize("nshards,flags", [(2, 0), (3, 1), (5, 0)])
+@pytest.mark.parametrize("nshards,flags", [(2, 0), (3, 1), (5, 0), (3, 8)])
 def test_pass_level_slabs_are_shard_invariant(ctx, nshards, flags):
     im = qs.synth.make_image(256, 208, "420")
     got = _run_slabs_one_gpu(ctx, im, flags, 2, nshards)

@@ -68,6 +68,7 @@ CFGS = [
     (3, (64, 112, "420", 1, 2, None)),         # DIAGONALS, uneven split
     (2, (48, 40, "gray", 16, 3, None)),        # NO_REBALANCE, 8-row MCUs
     (2, (0, 0, "420", 0, 2, "badcoef")),       # stop semantics across ranks
+    (2, (64, 96, "420", 8, 2, None)),          # LOW_QUALITY
 ]
 
 

@@ -84,6 +84,8 @@ CASES = [
     (256, 128, "444", 7, 2, 50), (256, 128, "422", 7, 2, 50), (248, 136, "440", 7, 2, 75),
     (128, 64, "420", 16, 2, 50), (128, 64, "420", 33, 2, 50), (128, 64, "420", 6, 0, 50),
     (128, 64, "420", 0, 0, 50), (8, 8, "gray", 0, 3, 50), (128, 64, "420", 5, 1, 30),
+    (256, 128, "420", 9, 3, 30), (250, 130, "420", 11, 2, 20), (256, 128, "420", 15, 2, 40),
+    (128, 64, "gray", 8, 3, 10), (256, 128, "444", 15, 2, 50), (64, 48, "420", 24, 2, 30),
 ]
 
 
