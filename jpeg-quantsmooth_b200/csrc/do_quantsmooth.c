@@ -81,10 +81,15 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 			JQUANT_TBL *t = srcinfo->quant_tbl_ptrs[i]; int k;
 			if (!t) continue;
 			logfmt("quant[%i]:\n", i);
-			for (k = 0; k < DCTSIZE2; k++) logfmt("%04x%c", t->quantval[k], (k & 7) == 7 ? '\n' : ' ');
+			for (k = 0; k < DCTSIZE2; k++) {
+				logfmt("%04x ", t->quantval[k]);
+				if ((k & 7) == 7) logfmt("\n");
+			}
 		}
 	if (flags & JPEGQS_INFO_TIME) t0 = now_usec();
 #endif
+#define LOG_COMP2 if (flags & JPEGQS_INFO_COMP2) for (ci = 0; ci < ncomp; ci++) if (comp[ci].quant_table) \
+	logfmt("component[%i] : size %ix%i\n", ci, comp[ci].width_in_blocks, comp[ci].height_in_blocks);
 	if (ncomp < 1 || ncomp > JPEGQS_CUDA_MAX_COMP) return 0;
 
 	/* same early exit as the reference (quantsmooth.h:2447-2458): nothing is touched */
@@ -98,6 +103,7 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 	if (!ctx) return JPEGQS_ERR_CUDA;
 #ifdef WITH_LOG
 	if (flags & JPEGQS_INFO_CPU) logfmt("SIMD type: CUDA sm_100a (%s)\n", jpegqs_cuda_device_name(ctx));
+	LOG_COMP2                                          /* quantsmooth.h:2569-2572 */
 #endif
 
 	memset(&img, 0, sizeof(img));

@@ -1,0 +1,616 @@
+/*
+ * jpegcoef.c - JPEG coefficient reader / writer (see jpegcoef.h).  Written from ITU-T T.81:
+ * marker syntax (Annex B), Huffman decoding (F.2.2), progressive procedures (G.1.2 / G.2),
+ * Huffman table generation (C.2, K.2) and the example tables of K.3.  It stands in for the
+ * jpeg_read_coefficients / jpeg_write_coefficients calls of the reference CLI
+ * (reference quantsmooth.c:548-549, 579-596).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include "jpegcoef.h"
+
+/* zig-zag index -> natural (row-major) index, T.81 figure A.6 */
+static const unsigned char zz_nat[64 + 16] = {
+	0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+	28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
+	54, 47, 55, 62, 63,
+	63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63       /* guard for corrupt run lengths */
+};
+
+/* ---------------------------------------------------------------- in-memory "virtual" arrays */
+struct jvirt_barray_control {
+	JDIMENSION w, h;
+	JBLOCKROW *rows;
+	JBLOCK *data;
+	struct jvirt_barray_control *next;
+};
+
+typedef struct {
+	struct jpeg_memory_mgr pub;          /* must be first: cinfo.mem points here */
+	struct jvirt_barray_control *head;
+} jq_mem;
+
+typedef struct {
+	jq_mem mem;
+	jpeg_component_info comps[MAX_COMPONENTS];
+	JQUANT_TBL qt[NUM_QUANT_TBLS];
+} jq_priv;
+
+static jvirt_barray_ptr jq_request(j_common_ptr cinfo, int pool, boolean pre_zero, JDIMENSION w, JDIMENSION h,
+		JDIMENSION maxaccess) {
+	jq_mem *m = (jq_mem*)cinfo->mem; JDIMENSION y;
+	struct jvirt_barray_control *a = (struct jvirt_barray_control*)calloc(1, sizeof(*a));
+	(void)pool; (void)pre_zero; (void)maxaccess;
+	if (!a) return NULL;
+	a->w = w; a->h = h;
+	a->rows = (JBLOCKROW*)malloc(sizeof(JBLOCKROW) * (h ? h : 1));
+	a->data = (JBLOCK*)calloc((size_t)w * h + 1, sizeof(JBLOCK));
+	if (!a->rows || !a->data) { free(a->rows); free(a->data); free(a); return NULL; }
+	for (y = 0; y < h; y++) a->rows[y] = a->data + (size_t)y * w;
+	a->next = m->head; m->head = a;
+	return a;
+}
+static void jq_realize(j_common_ptr cinfo) { (void)cinfo; }
+static JBLOCKARRAY jq_access(j_common_ptr cinfo, jvirt_barray_ptr a, JDIMENSION start, JDIMENSION n, boolean wr) {
+	(void)cinfo; (void)n; (void)wr;
+	return a->rows + start;
+}
+
+void jq_free(jq_image *im) {
+	jq_priv *p = (jq_priv*)im->priv;
+	while (im->markers) { jq_marker *m = im->markers; im->markers = m->next; free(m->data); free(m); }
+	if (p) {
+		while (p->mem.head) {
+			struct jvirt_barray_control *a = p->mem.head; p->mem.head = a->next;
+			free(a->rows); free(a->data); free(a);
+		}
+		free(p);
+	}
+	memset(im, 0, sizeof(*im));
+}
+
+/* ---------------------------------------------------------------- Huffman decoding */
+typedef struct {
+	int present;
+	unsigned char bits[17], val[256];
+	uint16_t look[512];                  /* 9-bit prefix -> (length << 8) | symbol, 0 = longer */
+	int32_t maxcode[18], valptr[17], mincode[17];
+} jq_dhuff;
+
+static int dhuff_build(jq_dhuff *h) {
+	int code = 0, k = 0, l, i;
+	memset(h->look, 0, sizeof(h->look));
+	for (l = 1; l <= 16; l++) {
+		h->valptr[l] = k; h->mincode[l] = code;
+		for (i = 0; i < h->bits[l]; i++, k++, code++) {
+			if (k >= 256) return -1;
+			if (l <= 9) {
+				int base = code << (9 - l), n = 1 << (9 - l), j;
+				if (base + n > 512) return -1;
+				for (j = 0; j < n; j++) h->look[base + j] = (uint16_t)((l << 8) | h->val[k]);
+			}
+		}
+		h->maxcode[l] = h->bits[l] ? code - 1 : -1;
+		if (code > (1 << l)) return -1;
+		code <<= 1;
+	}
+	h->maxcode[17] = 0x7fffffff;
+	h->present = 1;
+	return 0;
+}
+
+typedef struct {
+	const unsigned char *p, *end;
+	uint64_t buf; int nbits;
+	int hit_marker;                      /* a marker (not a stuffed FF00) stopped the feed */
+} jq_bits;
+
+static void bits_fill(jq_bits *b) {
+	while (b->nbits <= 48) {
+		unsigned c = 0;
+		if (!b->hit_marker && b->p < b->end) {
+			c = *b->p;
+			if (c == 0xFF) {
+				if (b->p + 1 < b->end && b->p[1] == 0) b->p += 2;
+				else { b->hit_marker = 1; c = 0; }
+			} else b->p++;
+		}
+		b->buf = (b->buf << 8) | c; b->nbits += 8;
+	}
+}
+static inline unsigned bits_peek(jq_bits *b, int n) {
+	if (b->nbits < n) bits_fill(b);
+	return (unsigned)(b->buf >> (b->nbits - n)) & ((1u << n) - 1);
+}
+static inline unsigned bits_get(jq_bits *b, int n) {
+	unsigned v;
+	if (!n) return 0;
+	v = bits_peek(b, n); b->nbits -= n;
+	return v;
+}
+static inline int huff_decode(jq_bits *b, const jq_dhuff *h) {
+	unsigned look = bits_peek(b, 16), e = h->look[look >> 7];
+	int l, code;
+	if (e) { b->nbits -= e >> 8; return e & 255; }
+	for (l = 10, code = (int)(look >> 6); l <= 16; l++, code = (int)(look >> (16 - l)))
+		if (code <= h->maxcode[l]) { b->nbits -= l; return h->val[h->valptr[l] + code - h->mincode[l]]; }
+	b->nbits -= 16;
+	return 0;                            /* corrupt data: keep going like libjpeg's warning path */
+}
+static inline int extend(unsigned v, int s) { return s && v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v; }
+
+/* ---------------------------------------------------------------- the reader */
+typedef struct {
+	int ncomp, ci[4], td[4], ta[4], Ss, Se, Ah, Al;
+} jq_scan;
+
+typedef struct {
+	jq_image *im; jq_priv *pv;
+	jq_dhuff dc[4], ac[4];
+	int pred[MAX_COMPONENTS];
+	unsigned eobrun;
+	JDIMENSION mcux, mcuy;
+} jq_dec;
+
+static void dec_block_seq(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFPTR blk) {
+	int c = s->ci[k], t, i;
+	t = huff_decode(b, &d->dc[s->td[k]]);
+	d->pred[c] += extend(bits_get(b, t & 15), t & 15);
+	blk[0] = (JCOEF)d->pred[c];
+	for (i = 1; i < 64; ) {
+		int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15;
+		if (!sz) { if (r != 15) break; i += 16; continue; }
+		i += r;
+		blk[zz_nat[i]] = (JCOEF)extend(bits_get(b, sz), sz);
+		i++;
+	}
+}
+
+static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFPTR blk) {
+	int c = s->ci[k], Al = s->Al, i;
+	if (s->Ss == 0) {                                   /* DC scans, G.1.2.1 */
+		if (s->Ah == 0) {
+			int t = huff_decode(b, &d->dc[s->td[k]]);
+			d->pred[c] += extend(bits_get(b, t & 15), t & 15);
+			blk[0] = (JCOEF)(d->pred[c] * (1 << Al));
+		} else if (bits_get(b, 1)) blk[0] |= (JCOEF)(1 << Al);
+		return;
+	}
+	if (s->Ah == 0) {                                   /* AC first scan, G.1.2.2 */
+		if (d->eobrun) { d->eobrun--; return; }
+		for (i = s->Ss; i <= s->Se; ) {
+			int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15;
+			if (sz) {
+				i += r;
+				blk[zz_nat[i]] = (JCOEF)(extend(bits_get(b, sz), sz) * (1 << Al));
+				i++;
+			} else if (r == 15) i += 16;
+			else { d->eobrun = (1u << r) + bits_get(b, r) - 1; break; }
+		}
+		return;
+	}
+	{                                                   /* AC refinement scan, G.1.2.3 */
+		int p1 = 1 << Al, m1 = -(1 << Al);
+		i = s->Ss;
+		if (!d->eobrun) {
+			while (i <= s->Se) {
+				int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15, val = 0;
+				if (sz) val = bits_get(b, 1) ? p1 : m1;
+				else if (r != 15) { d->eobrun = (1u << r) + bits_get(b, r); break; }
+				/* skip r zero-history coefficients; already-nonzero ones take a correction bit */
+				for (; i <= s->Se; i++) {
+					JCOEFPTR cp = blk + zz_nat[i];
+					if (*cp) {
+						if (bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1);
+					} else if (--r < 0) break;
+				}
+				if (val && i <= s->Se) blk[zz_nat[i]] = (JCOEF)val;
+				i++;
+			}
+		}
+		if (d->eobrun) {
+			for (; i <= s->Se; i++) {
+				JCOEFPTR cp = blk + zz_nat[i];
+				if (*cp && bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1);
+			}
+			d->eobrun--;
+		}
+	}
+}
+
+static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const unsigned char *end,
+		const unsigned char **next, char *err) {
+	jq_image *im = d->im; jq_bits b; int prog = im->progressive, k, ri = im->restart_interval;
+	JDIMENSION nx, ny, x, y; unsigned count = 0, rst = 0;
+	memset(&b, 0, sizeof(b)); b.p = p; b.end = end;
+	memset(d->pred, 0, sizeof(d->pred)); d->eobrun = 0;
+	for (k = 0; k < s->ncomp; k++) {
+		int need_dc = !prog || (s->Ss == 0 && s->Ah == 0), need_ac = prog ? s->Ss > 0 : 1;
+		if ((need_dc && !d->dc[s->td[k]].present) || (need_ac && !d->ac[s->ta[k]].present)) {
+			snprintf(err, 256, "scan uses an undefined Huffman table"); return -1;
+		}
+	}
+	if (s->ncomp == 1) {
+		jpeg_component_info *c = &im->cinfo.comp_info[s->ci[0]];
+		nx = c->width_in_blocks; ny = c->height_in_blocks;
+	} else { nx = d->mcux; ny = d->mcuy; }
+	for (y = 0; y < ny; y++) for (x = 0; x < nx; x++) {
+		if (ri && count == (unsigned)ri) {              /* restart: align, expect RSTn (B.2.1, F.2.2.5) */
+			b.nbits = 0; b.buf = 0;
+			if (!b.hit_marker) {                        /* skip padding up to the marker */
+				while (b.p + 1 < b.end && !(b.p[0] == 0xFF && b.p[1] != 0 && b.p[1] != 0xFF)) b.p++;
+			}
+			if (b.p + 1 < b.end && b.p[0] == 0xFF && (b.p[1] & 0xF8) == 0xD0) b.p += 2;
+			b.hit_marker = 0; rst++; count = 0;
+			memset(d->pred, 0, sizeof(d->pred)); d->eobrun = 0;
+		}
+		count++;
+		if (s->ncomp == 1) {
+			JCOEFPTR blk = im->coef_arrays[s->ci[0]]->rows[y][x];
+			if (prog) dec_block_prog(d, &b, s, 0, blk); else dec_block_seq(d, &b, s, 0, blk);
+		} else for (k = 0; k < s->ncomp; k++) {
+			jpeg_component_info *c = &im->cinfo.comp_info[s->ci[k]]; int h, v;
+			for (v = 0; v < c->v_samp_factor; v++) for (h = 0; h < c->h_samp_factor; h++) {
+				JCOEFPTR blk = im->coef_arrays[s->ci[k]]->rows[y * c->v_samp_factor + v][x * c->h_samp_factor + h];
+				if (prog) dec_block_prog(d, &b, s, k, blk); else dec_block_seq(d, &b, s, k, blk);
+			}
+		}
+	}
+	/* position of the next marker */
+	if (!b.hit_marker) {
+		const unsigned char *q = b.p;
+		while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0 && q[1] != 0xFF && (q[1] & 0xF8) != 0xD0)) q++;
+		*next = q;
+	} else *next = b.p;
+	(void)rst;
+	return 0;
+}
+
+static unsigned be16(const unsigned char *p) { return (unsigned)p[0] << 8 | p[1]; }
+
+int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char *err) {
+	const unsigned char *p = data, *end = data + len;
+	jq_priv *pv; jq_dec *d; jq_marker **tail; int have_frame = 0, i, done = 0, adobe = -1;
+	memset(im, 0, sizeof(*im));
+	err[0] = 0;
+	if (len < 4 || p[0] != 0xFF || p[1] != 0xD8) { snprintf(err, 256, "not a JPEG file (no SOI)"); return -1; }
+	pv = (jq_priv*)calloc(1, sizeof(*pv));
+	d = (jq_dec*)calloc(1, sizeof(*d));
+	if (!pv || !d) { free(pv); free(d); snprintf(err, 256, "out of memory"); return -1; }
+	im->priv = pv; d->im = im; d->pv = pv;
+	pv->mem.pub.request_virt_barray = jq_request;
+	pv->mem.pub.realize_virt_arrays = jq_realize;
+	pv->mem.pub.access_virt_barray = jq_access;
+	im->cinfo.mem = &pv->mem.pub;
+	im->cinfo.comp_info = pv->comps;
+	tail = &im->markers;
+	p += 2;
+	while (!done) {
+		unsigned code, seglen; const unsigned char *seg;
+		while (p < end && *p != 0xFF) p++;              /* tolerate garbage between segments */
+		while (p < end && *p == 0xFF) p++;
+		if (p >= end) break;
+		code = *p++;
+		if (code == 0xD9) break;                        /* EOI */
+		if (code == 0x01 || (code >= 0xD0 && code <= 0xD7) || code == 0) continue;
+		if (p + 2 > end) break;
+		seglen = be16(p);
+		if (seglen < 2 || p + seglen > end) { snprintf(err, 256, "truncated marker segment 0x%02X", code); goto fail; }
+		seg = p + 2; p += seglen; seglen -= 2;
+		if (code == 0xDB) {                             /* DQT, B.2.4.1 */
+			while (seglen >= 65) {
+				int pq = seg[0] >> 4, tq = seg[0] & 15, n = pq ? 128 : 64;
+				if (tq >= NUM_QUANT_TBLS || seglen < (unsigned)n + 1) { snprintf(err, 256, "bad DQT"); goto fail; }
+				for (i = 0; i < 64; i++)
+					pv->qt[tq].quantval[zz_nat[i]] = (UINT16)(pq ? be16(seg + 1 + 2 * i) : seg[1 + i]);
+				im->cinfo.quant_tbl_ptrs[tq] = &pv->qt[tq];
+				seg += n + 1; seglen -= n + 1;
+			}
+		} else if (code == 0xC4) {                      /* DHT, B.2.4.2 */
+			while (seglen >= 17) {
+				int tc = seg[0] >> 4, th = seg[0] & 15, n = 0;
+				jq_dhuff *h;
+				if (tc > 1 || th > 3) { snprintf(err, 256, "bad DHT"); goto fail; }
+				h = tc ? &d->ac[th] : &d->dc[th];
+				h->bits[0] = 0;
+				for (i = 1; i <= 16; i++) { h->bits[i] = seg[i]; n += seg[i]; }
+				if (n > 256 || seglen < 17u + n) { snprintf(err, 256, "bad DHT"); goto fail; }
+				memcpy(h->val, seg + 17, n);
+				if (dhuff_build(h)) { snprintf(err, 256, "bad Huffman table"); goto fail; }
+				seg += 17 + n; seglen -= 17 + n;
+			}
+		} else if (code == 0xDD) {                      /* DRI */
+			if (seglen >= 2) im->restart_interval = be16(seg);
+		} else if (code == 0xC0 || code == 0xC1 || code == 0xC2) {      /* SOF0/1/2, B.2.2 */
+			int nf, maxh = 1, maxv = 1;
+			if (have_frame || seglen < 6) { snprintf(err, 256, "bad frame header"); goto fail; }
+			if (seg[0] != 8) { snprintf(err, 256, "%d-bit samples are not supported", seg[0]); goto fail; }
+			im->progressive = code == 0xC2;
+			im->cinfo.image_height = be16(seg + 1); im->cinfo.image_width = be16(seg + 3);
+			nf = seg[5];
+			if (nf < 1 || nf > 4 || seglen < 6u + 3 * nf || !im->cinfo.image_width || !im->cinfo.image_height) {
+				snprintf(err, 256, "unsupported frame header (%d components)", nf); goto fail;
+			}
+			im->cinfo.num_components = nf;
+			for (i = 0; i < nf; i++) {
+				jpeg_component_info *c = &pv->comps[i];
+				im->comp_id[i] = seg[6 + 3 * i];
+				c->component_id = seg[6 + 3 * i]; c->component_index = i;
+				c->h_samp_factor = seg[7 + 3 * i] >> 4; c->v_samp_factor = seg[7 + 3 * i] & 15;
+				c->quant_tbl_no = seg[8 + 3 * i] & 3;
+				if (c->h_samp_factor < 1 || c->h_samp_factor > 4 || c->v_samp_factor < 1 || c->v_samp_factor > 4) {
+					snprintf(err, 256, "bad sampling factors"); goto fail;
+				}
+				if (c->h_samp_factor > maxh) maxh = c->h_samp_factor;
+				if (c->v_samp_factor > maxv) maxv = c->v_samp_factor;
+			}
+			im->cinfo.max_h_samp_factor = maxh; im->cinfo.max_v_samp_factor = maxv;
+			d->mcux = (im->cinfo.image_width + 8 * maxh - 1) / (8 * maxh);
+			d->mcuy = (im->cinfo.image_height + 8 * maxv - 1) / (8 * maxv);
+			for (i = 0; i < nf; i++) {
+				jpeg_component_info *c = &pv->comps[i];
+				/* libjpeg geometry (jdinput.c initial_setup): not padded to the MCU */
+				c->width_in_blocks = (im->cinfo.image_width * c->h_samp_factor + 8 * maxh - 1) / (8 * maxh);
+				c->height_in_blocks = (im->cinfo.image_height * c->v_samp_factor + 8 * maxv - 1) / (8 * maxv);
+				im->coef_arrays[i] = jq_request((j_common_ptr)&im->cinfo, JPOOL_IMAGE, TRUE,
+						d->mcux * c->h_samp_factor, d->mcuy * c->v_samp_factor, 1);
+				if (!im->coef_arrays[i]) { snprintf(err, 256, "out of memory"); goto fail; }
+			}
+			/* colour space guess of jdapimin.c default_decompress_parms (JFIF / Adobe aside) */
+			im->cinfo.jpeg_color_space = nf == 1 ? JCS_GRAYSCALE : nf == 3 ? JCS_YCbCr : JCS_CMYK;
+			if (nf == 3 && im->comp_id[0] == 'R' && im->comp_id[1] == 'G' && im->comp_id[2] == 'B')
+				im->cinfo.jpeg_color_space = JCS_RGB;
+			have_frame = 1;
+		} else if (code >= 0xC3 && code <= 0xCF && code != 0xC8) {
+			snprintf(err, 256, "unsupported JPEG process (SOF%d: lossless, hierarchical or arithmetic)", code - 0xC0);
+			goto fail;
+		} else if (code == 0xDA) {                      /* SOS, B.2.3 */
+			jq_scan s; int ns;
+			if (!have_frame || seglen < 1) { snprintf(err, 256, "SOS before SOF"); goto fail; }
+			ns = seg[0];
+			if (ns < 1 || ns > 4 || seglen < 4u + 2 * ns) { snprintf(err, 256, "bad scan header"); goto fail; }
+			memset(&s, 0, sizeof(s)); s.ncomp = ns;
+			for (i = 0; i < ns; i++) {
+				int id = seg[1 + 2 * i], j;
+				for (j = 0; j < im->cinfo.num_components && im->comp_id[j] != id; j++);
+				if (j == im->cinfo.num_components) { snprintf(err, 256, "scan names an unknown component"); goto fail; }
+				s.ci[i] = j; s.td[i] = (seg[2 + 2 * i] >> 4) & 3; s.ta[i] = seg[2 + 2 * i] & 3;
+			}
+			s.Ss = seg[1 + 2 * ns]; s.Se = seg[2 + 2 * ns]; s.Ah = seg[3 + 2 * ns] >> 4; s.Al = seg[3 + 2 * ns] & 15;
+			if (!im->progressive) { s.Ss = 0; s.Se = 63; s.Ah = s.Al = 0; }
+			if (s.Ss > s.Se || s.Se > 63 || s.Al > 13 || (s.Ss > 0 && ns != 1)) { snprintf(err, 256, "bad scan parameters"); goto fail; }
+			if (dec_scan(d, &s, p, end, &p, err)) goto fail;
+		} else if ((code >= 0xE0 && code <= 0xEF) || code == 0xFE) {
+			int want = code == 0xFE ? copy > 0 : copy > 1;
+			if (code == 0xEE && seglen >= 12 && !memcmp(seg, "Adobe", 5)) {       /* transform flag, jdmarker.c */
+				adobe = seg[11];
+			}
+			if (want) {
+				jq_marker *m = (jq_marker*)calloc(1, sizeof(*m));
+				if (!m || !(m->data = (unsigned char*)malloc(seglen + 1))) { free(m); snprintf(err, 256, "out of memory"); goto fail; }
+				m->code = (int)code; m->len = seglen; memcpy(m->data, seg, seglen);
+				*tail = m; tail = &m->next;
+			}
+		}
+	}
+	if (!have_frame) { snprintf(err, 256, "no frame header found"); goto fail; }
+	if (adobe >= 0) {                                   /* jdapimin.c default_decompress_parms */
+		if (im->cinfo.num_components == 3) im->cinfo.jpeg_color_space = adobe == 0 ? JCS_RGB : JCS_YCbCr;
+		if (im->cinfo.num_components == 4) im->cinfo.jpeg_color_space = adobe == 2 ? JCS_YCCK : JCS_CMYK;
+	}
+	for (i = 0; i < im->cinfo.num_components; i++) {
+		jpeg_component_info *c = &pv->comps[i];
+		c->quant_table = im->cinfo.quant_tbl_ptrs[c->quant_tbl_no];
+		if (!c->quant_table) { snprintf(err, 256, "component %d uses an undefined quantization table", i); goto fail; }
+	}
+	free(d);
+	return 0;
+fail:
+	free(d);
+	jq_free(im);
+	return -1;
+}
+
+/* ---------------------------------------------------------------- the writer */
+typedef struct { unsigned char *p; size_t n, cap; uint64_t acc; int nacc; int fail; } jq_out;
+
+static void out_byte(jq_out *o, unsigned v) {
+	if (o->n == o->cap) {
+		size_t nc = o->cap ? o->cap * 2 : 1 << 16; unsigned char *q = (unsigned char*)realloc(o->p, nc);
+		if (!q) { o->fail = 1; return; }
+		o->p = q; o->cap = nc;
+	}
+	o->p[o->n++] = (unsigned char)v;
+}
+static void out_be16(jq_out *o, unsigned v) { out_byte(o, v >> 8); out_byte(o, v & 255); }
+static void out_bits(jq_out *o, unsigned code, int n) {
+	o->acc = (o->acc << n) | (code & ((1u << n) - 1)); o->nacc += n;
+	while (o->nacc >= 8) {
+		unsigned b = (unsigned)(o->acc >> (o->nacc - 8)) & 255;
+		out_byte(o, b); if (b == 0xFF) out_byte(o, 0);
+		o->nacc -= 8;
+	}
+}
+static void out_flush(jq_out *o) { if (o->nacc) out_bits(o, 0x7F, 8 - o->nacc); o->acc = 0; o->nacc = 0; }
+
+typedef struct { unsigned char bits[17], val[256]; int nval; unsigned code[256]; unsigned char size[256]; long freq[257]; } jq_ehuff;
+
+/* T.81 K.3.3 example tables */
+static const unsigned char std_dc_l_bits[17] = { 0, 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 };
+static const unsigned char std_dc_c_bits[17] = { 0, 0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0 };
+static const unsigned char std_dc_val[12] = { 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11 };
+static const unsigned char std_ac_l_bits[17] = { 0, 0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d };
+static const unsigned char std_ac_l_val[162] = {
+	0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71,
+	0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72,
+	0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37,
+	0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59,
+	0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83,
+	0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+	0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3,
+	0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2,
+	0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa };
+static const unsigned char std_ac_c_bits[17] = { 0, 0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77 };
+static const unsigned char std_ac_c_val[162] = {
+	0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22,
+	0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1,
+	0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36,
+	0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58,
+	0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a,
+	0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+	0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba,
+	0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda,
+	0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa };
+
+static void ehuff_set(jq_ehuff *h, const unsigned char *bits, const unsigned char *val, int n) {
+	memcpy(h->bits, bits, 17); memcpy(h->val, val, n); h->nval = n;
+}
+static void ehuff_codes(jq_ehuff *h) {                  /* T.81 C.2 */
+	int l, i, k = 0; unsigned code = 0;
+	memset(h->size, 0, sizeof(h->size));
+	for (l = 1; l <= 16; l++) {
+		for (i = 0; i < h->bits[l]; i++, k++) { h->code[h->val[k]] = code++; h->size[h->val[k]] = (unsigned char)l; }
+		code <<= 1;
+	}
+}
+/* optimal code lengths limited to 16 bits, T.81 K.2 (figures K.1 - K.4) */
+static void ehuff_optimal(jq_ehuff *h) {
+	long freq[257]; int codesize[257], others[257], bits[33], i, j, c1, c2, k;
+	memcpy(freq, h->freq, sizeof(freq));
+	memset(codesize, 0, sizeof(codesize)); memset(bits, 0, sizeof(bits));
+	for (i = 0; i < 257; i++) others[i] = -1;
+	freq[256] = 1;                                       /* reserves the all-ones code */
+	for (;;) {
+		long v = 1000000000L;
+		c1 = -1; c2 = -1;
+		for (i = 0; i <= 256; i++) if (freq[i] && freq[i] <= v) { v = freq[i]; c1 = i; }
+		v = 1000000000L;
+		for (i = 0; i <= 256; i++) if (freq[i] && freq[i] <= v && i != c1) { v = freq[i]; c2 = i; }
+		if (c2 < 0) break;
+		freq[c1] += freq[c2]; freq[c2] = 0;
+		for (codesize[c1]++; others[c1] >= 0; codesize[c1]++) c1 = others[c1];
+		others[c1] = c2;
+		for (codesize[c2]++; others[c2] >= 0; codesize[c2]++) c2 = others[c2];
+	}
+	for (i = 0; i <= 256; i++) if (codesize[i]) bits[codesize[i] > 32 ? 32 : codesize[i]]++;
+	for (i = 32; i > 16; i--) while (bits[i] > 0) {
+		for (j = i - 2; bits[j] == 0; j--);
+		bits[i] -= 2; bits[i - 1]++; bits[j + 1] += 2; bits[j]--;
+	}
+	while (bits[i] == 0) i--;
+	bits[i]--;                                           /* drop the reserved code point */
+	memset(h->bits, 0, sizeof(h->bits));
+	for (i = 1; i <= 16; i++) h->bits[i] = (unsigned char)bits[i];
+	for (k = 0, i = 1; i <= 32; i++) for (j = 0; j < 256; j++) if (codesize[j] == i) h->val[k++] = (unsigned char)j;
+	h->nval = k;
+}
+
+static int bit_size(int v) { int n = 0; if (v < 0) v = -v; while (v) { n++; v >>= 1; } return n; }
+
+/* one block: either counts symbols (o == NULL) or emits them */
+static int enc_block(jq_out *o, const JCOEF *blk, int *pred, jq_ehuff *dc, jq_ehuff *ac) {
+	int diff = blk[0] - *pred, s = bit_size(diff), i, run = 0;
+	*pred = blk[0];
+	if (s > 11) return -1;
+	if (!o) dc->freq[s]++;
+	else { out_bits(o, dc->code[s], dc->size[s]); if (s) out_bits(o, (unsigned)(diff < 0 ? diff - 1 : diff), s); }
+	for (i = 1; i < 64; i++) {
+		int v = blk[zz_nat[i]];
+		if (!v) { run++; continue; }
+		for (; run > 15; run -= 16) { if (!o) ac->freq[0xF0]++; else out_bits(o, ac->code[0xF0], ac->size[0xF0]); }
+		s = bit_size(v);
+		if (s > 10) return -1;
+		if (!o) ac->freq[run << 4 | s]++;
+		else { out_bits(o, ac->code[run << 4 | s], ac->size[run << 4 | s]); out_bits(o, (unsigned)(v < 0 ? v - 1 : v), s); }
+		run = 0;
+	}
+	if (run) { if (!o) ac->freq[0]++; else out_bits(o, ac->code[0], ac->size[0]); }
+	return 0;
+}
+
+static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff *dc, jq_ehuff *ac) {
+	struct jpeg_decompress_struct *ci = &im->cinfo;
+	int maxh = ci->max_h_samp_factor, maxv = ci->max_v_samp_factor, k, pred[MAX_COMPONENTS] = { 0 };
+	JDIMENSION mcux = (ci->image_width + 8 * maxh - 1) / (8 * maxh), mcuy = (ci->image_height + 8 * maxv - 1) / (8 * maxv), x, y;
+	static const JCOEF zero[64] = { 0 };
+	for (y = 0; y < mcuy; y++) for (x = 0; x < mcux; x++) for (k = 0; k < ci->num_components; k++) {
+		jpeg_component_info *c = &ci->comp_info[k]; int h, v, t = k ? 1 : 0;
+		for (v = 0; v < c->v_samp_factor; v++) for (h = 0; h < c->h_samp_factor; h++) {
+			JDIMENSION bx = x * c->h_samp_factor + h, by = y * c->v_samp_factor + v;
+			JCOEF dummy[64];
+			const JCOEF *blk;
+			if (bx < c->width_in_blocks && by < c->height_in_blocks)
+				blk = (*ci->mem->access_virt_barray)((j_common_ptr)ci, arrays[k], by, 1, FALSE)[0][bx];
+			else {                                       /* padding block: DC repeats, AC zero (like jctrans.c) */
+				memcpy(dummy, zero, sizeof(dummy)); dummy[0] = (JCOEF)pred[k]; blk = dummy;
+			}
+			if (enc_block(o, blk, &pred[k], &dc[t], &ac[t])) return -1;
+		}
+	}
+	return 0;
+}
+
+static void out_dht(jq_out *o, int tc_th, const jq_ehuff *h) {
+	int i;
+	out_be16(o, 0xFFC4); out_be16(o, 2 + 1 + 16 + h->nval); out_byte(o, tc_th);
+	for (i = 1; i <= 16; i++) out_byte(o, h->bits[i]);
+	for (i = 0; i < h->nval; i++) out_byte(o, h->val[i]);
+}
+
+int jq_write(jq_image *im, jvirt_barray_ptr *arrays, int optimize, unsigned char **out, size_t *outlen, char *err) {
+	struct jpeg_decompress_struct *ci = &im->cinfo;
+	jq_out o; jq_ehuff *dc, *ac; jq_marker *m; int i, k, nt = ci->num_components > 1 ? 2 : 1, blocks = 0, sof = 0xC0;
+	unsigned written_q = 0;
+	memset(&o, 0, sizeof(o)); err[0] = 0;
+	dc = (jq_ehuff*)calloc(2, sizeof(*dc)); ac = (jq_ehuff*)calloc(2, sizeof(*ac));
+	if (!dc || !ac) { free(dc); free(ac); snprintf(err, 256, "out of memory"); return -1; }
+	for (k = 0; k < ci->num_components; k++) blocks += ci->comp_info[k].h_samp_factor * ci->comp_info[k].v_samp_factor;
+	if (blocks > 10) { snprintf(err, 256, "more than 10 blocks per MCU: not written as one interleaved scan"); goto fail; }
+	if (optimize) {
+		if (enc_pass(im, arrays, NULL, dc, ac)) { snprintf(err, 256, "coefficient out of range for Huffman coding"); goto fail; }
+		for (i = 0; i < nt; i++) { ehuff_optimal(&dc[i]); ehuff_optimal(&ac[i]); }
+	} else {
+		ehuff_set(&dc[0], std_dc_l_bits, std_dc_val, 12); ehuff_set(&ac[0], std_ac_l_bits, std_ac_l_val, 162);
+		ehuff_set(&dc[1], std_dc_c_bits, std_dc_val, 12); ehuff_set(&ac[1], std_ac_c_bits, std_ac_c_val, 162);
+	}
+	for (i = 0; i < nt; i++) { ehuff_codes(&dc[i]); ehuff_codes(&ac[i]); }
+
+	out_be16(&o, 0xFFD8);
+	for (m = im->markers; m; m = m->next) {              /* jcopy_markers_execute, quantsmooth.c:581-590 */
+		out_byte(&o, 0xFF); out_byte(&o, (unsigned)m->code); out_be16(&o, (unsigned)m->len + 2);
+		for (i = 0; i < (int)m->len; i++) out_byte(&o, m->data[i]);
+	}
+	for (k = 0; k < ci->num_components; k++) {           /* DQT for every table in use */
+		int tq = ci->comp_info[k].quant_tbl_no & 3, prec = 0;
+		JQUANT_TBL *t = ci->comp_info[k].quant_table ? ci->comp_info[k].quant_table : ci->quant_tbl_ptrs[tq];
+		if (!t || (written_q >> tq & 1)) continue;
+		written_q |= 1u << tq;
+		for (i = 0; i < 64; i++) if (t->quantval[i] > 255) prec = 1;
+		if (prec) sof = 0xC1;
+		out_be16(&o, 0xFFDB); out_be16(&o, 2 + 1 + (prec ? 128 : 64)); out_byte(&o, (unsigned)(prec << 4 | tq));
+		for (i = 0; i < 64; i++) { unsigned v = t->quantval[zz_nat[i]]; if (prec) out_be16(&o, v); else out_byte(&o, v); }
+	}
+	out_be16(&o, 0xFF00 | sof); out_be16(&o, 8 + 3 * ci->num_components); out_byte(&o, 8);
+	out_be16(&o, ci->image_height); out_be16(&o, ci->image_width); out_byte(&o, ci->num_components);
+	for (k = 0; k < ci->num_components; k++) {
+		jpeg_component_info *c = &ci->comp_info[k];
+		out_byte(&o, (unsigned)im->comp_id[k]); out_byte(&o, (unsigned)(c->h_samp_factor << 4 | c->v_samp_factor));
+		out_byte(&o, (unsigned)c->quant_tbl_no);
+	}
+	for (i = 0; i < nt; i++) { out_dht(&o, i, &dc[i]); out_dht(&o, 0x10 | i, &ac[i]); }
+	out_be16(&o, 0xFFDA); out_be16(&o, 6 + 2 * ci->num_components); out_byte(&o, ci->num_components);
+	for (k = 0; k < ci->num_components; k++) { out_byte(&o, (unsigned)im->comp_id[k]); out_byte(&o, k ? 0x11 : 0x00); }
+	out_byte(&o, 0); out_byte(&o, 63); out_byte(&o, 0);
+	if (enc_pass(im, arrays, &o, dc, ac)) { snprintf(err, 256, "coefficient out of range for Huffman coding"); goto fail; }
+	out_flush(&o);
+	out_be16(&o, 0xFFD9);
+	if (o.fail) { snprintf(err, 256, "out of memory"); goto fail; }
+	free(dc); free(ac);
+	*out = o.p; *outlen = o.n;
+	return 0;
+fail:
+	free(dc); free(ac); free(o.p);
+	return -1;
+}

@@ -1,0 +1,54 @@
+/*
+ * jpegcoef.h - a small JPEG coefficient codec (ITU-T T.81 Huffman modes, 8-bit samples).
+ *
+ * The reference CLI gets its coefficient arrays from libjpeg (jpeg_read_coefficients /
+ * jpeg_write_coefficients, reference quantsmooth.c:548-596).  libjpeg's headers are not
+ * available in this build image, so the `jpegqs` tool here carries its own front/back end
+ * (SURVEY.md 8f row f1): it parses baseline, extended-sequential and progressive Huffman
+ * JPEGs into exactly the structures do_quantsmooth consumes (the compat jpeg_decompress_struct
+ * with an in-memory jpeg_memory_mgr and one virtual block array per component) and writes the
+ * arrays back as a sequential Huffman JPEG, copying APPn/COM markers.  No pixels are decoded.
+ * Arithmetic-coded, lossless, hierarchical and 12-bit files are rejected.
+ */
+#ifndef JPEGCOEF_H
+#define JPEGCOEF_H
+
+#include <stddef.h>
+#include <jpeglib.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jq_marker {
+	int code;                    /* 0xE0..0xEF (APPn) or 0xFE (COM) */
+	size_t len;                  /* payload bytes (without the 2 length bytes) */
+	unsigned char *data;
+	struct jq_marker *next;
+} jq_marker;
+
+typedef struct jq_image {
+	struct jpeg_decompress_struct cinfo;     /* what do_quantsmooth reads and rewrites */
+	jvirt_barray_ptr coef_arrays[MAX_COMPONENTS];
+	jq_marker *markers;                      /* in file order */
+	int progressive;                         /* the input was SOF2 */
+	int restart_interval;                    /* of the input (not reproduced on output) */
+	int comp_id[MAX_COMPONENTS];             /* component identifiers of the frame header */
+	void *priv;
+} jq_image;
+
+/* copy: 0 = no markers, 1 = COM only, 2 = COM + APPn (reference quantsmooth.c:541-546).
+ * Returns 0, or -1 with a message in err (>= 256 bytes). */
+int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char *err);
+
+/* Encodes im->cinfo + arrays (normally im->coef_arrays, or the arrays do_quantsmooth left in
+ * its coef_arrays argument) as one sequential Huffman JPEG.  optimize != 0 builds optimal
+ * Huffman tables (the CLI's -o, reference quantsmooth.c:553).  *out is malloc'd. */
+int jq_write(jq_image *im, jvirt_barray_ptr *arrays, int optimize, unsigned char **out, size_t *outlen, char *err);
+
+void jq_free(jq_image *im);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

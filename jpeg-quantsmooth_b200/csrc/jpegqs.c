@@ -1,0 +1,129 @@
+/*
+ * jpegqs.c - the `jpegqs` command line tool on top of the B200 back end.
+ *
+ * Same command line surface as the reference tool (reference quantsmooth.c:288-393):
+ *   jpegqs [options] input.jpg output.jpg        ("-" = stdin / stdout)
+ *     -q, --quality n    0..6, default 3 (mapped to flags exactly like quantsmooth.c:380-393)
+ *     -n, --niter n      number of iterations (default 3)
+ *     -t, --threads n    accepted, ignored (the reference's OpenMP thread count)
+ *     -o, --optimize     optimal Huffman tables in the output
+ *     -v, --verbose n    codec diagnostics
+ *     -i, --info n       info bit mask (JPEGQS_INFO_*), default 15
+ *     -p, --cpu n        CUDA device ordinal + 1 (0 = current device); the reference's SIMD cap
+ *     -f, --flags n      raw JPEGQS_* flag bits instead of -q
+ *     -c, --copy n       0 = no markers, 1 = comments, 2 = comments + APPn (default)
+ * The flow is the reference's (quantsmooth.c:494-596): read coefficients, do_quantsmooth,
+ * write coefficients + copied markers.  libjpeg is replaced by jpegcoef.c because its headers
+ * are not available in this build image.  Exit code: 0 ok, 1 usage / I/O / codec error,
+ * 2 when do_quantsmooth reported an error.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <jpeglib.h>
+#include "libjpegqs.h"
+#include "jpegcoef.h"
+
+static unsigned char *load_all(FILE *f, size_t *len) {
+	size_t cap = 1 << 20, n = 0, r; unsigned char *p = (unsigned char*)malloc(cap);
+	if (!p) return NULL;
+	while ((r = fread(p + n, 1, cap - n, f)) > 0) {
+		n += r;
+		if (n == cap) { unsigned char *q = (unsigned char*)realloc(p, cap *= 2); if (!q) { free(p); return NULL; } p = q; }
+	}
+	*len = n;
+	return p;
+}
+
+static int usage(const char *prog) {
+	fprintf(stderr,
+		"jpegqs (B200 back end) version " JPEGQS_VERSION "\n"
+		"Usage:\n  %s [options] input.jpg output.jpg\n\nOptions:\n"
+		"  -q, --quality n   Quality setting (0-6, default is 3)\n"
+		"  -n, --niter n     Number of iterations (default is 3)\n"
+		"  -t, --threads n   Ignored (CPU threads of the reference)\n"
+		"  -o, --optimize    Optimize Huffman table\n"
+		"  -v, --verbose n   Print codec debug messages\n"
+		"  -i, --info n      Print quantsmooth debug messages (default is 15)\n"
+		"  -p, --cpu n       CUDA device ordinal + 1 (0 = current device)\n"
+		"  -f, --flags n     Raw flag bits\n"
+		"  -c, --copy n      Markers to copy: 0 none, 1 comments, 2 all (default)\n", prog);
+	return 1;
+}
+
+int main(int argc, char **argv) {
+	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
+	int i, ret, flags = 0;
+	const char *in_name, *out_name;
+	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
+	jq_image im; char err[256]; jpegqs_control_t opts;
+	static const struct { char s; const char *l; int has_arg; } O[] = {
+		{ 'o', "--optimize", 0 }, { 'v', "--verbose", 1 }, { 'i', "--info", 1 }, { 'n', "--niter", 1 },
+		{ 'q', "--quality", 1 }, { 't', "--threads", 1 }, { 'f', "--flags", 1 }, { 'p', "--cpu", 1 }, { 'c', "--copy", 1 } };
+
+	for (i = 1; i < argc; i++) {
+		const char *a = argv[i], *val = NULL; int k, which = -1;
+		if (a[0] != '-' || !a[1]) break;
+		if (!strcmp(a, "--")) { i++; break; }
+		for (k = 0; k < (int)(sizeof(O) / sizeof(O[0])); k++) {
+			if (a[1] != '-' && a[1] == O[k].s) { which = k; if (a[2]) val = a + 2; break; }
+			if (!strcmp(a, O[k].l)) { which = k; break; }
+		}
+		if (which < 0) return usage(argv[0]);
+		if (O[which].has_arg) {
+			if (!val) { if (++i >= argc) return usage(argv[0]); val = argv[i]; }
+			if ((unsigned)(val[0] - '0') > 9) return usage(argv[0]);
+		} else if (val) return usage(argv[0]);
+		switch (O[which].s) {
+			case 'o': optimize = 1; break;
+			case 'v': verbose = atoi(val); break;
+			case 'i': info = atoi(val); break;
+			case 'n': niter = atoi(val); break;
+			case 'q': quality = atoi(val); break;
+			case 't': threads = atoi(val); break;
+			case 'f': cmd_flags = atoi(val) & JPEGQS_FLAGS_MASK; break;
+			case 'p': cpu = atoi(val); if (cpu > JPEGQS_CPU_MASK) cpu = JPEGQS_CPU_MASK; break;
+			case 'c': copy = atoi(val); break;
+		}
+	}
+	if (argc - i != 2) return usage(argv[0]);
+	in_name = argv[i]; out_name = argv[i + 1];
+
+	if (quality < 3) { flags |= JPEGQS_LOW_QUALITY; quality += 4; }      /* quantsmooth.c:380-393 */
+	if (quality >= 4) flags |= JPEGQS_DIAGONALS;
+	if (quality >= 5) flags |= JPEGQS_JOINT_YUV;
+	if (quality >= 6) flags |= JPEGQS_UPSAMPLE_UV;
+	memset(&opts, 0, sizeof(opts));
+	opts.niter = niter >= 0 ? niter : 3;
+	opts.flags = (cmd_flags >= 0 ? cmd_flags : flags) | JPEGQS_TRANSCODE;
+	opts.flags |= cpu << JPEGQS_CPU_SHIFT;
+	opts.flags |= info << JPEGQS_INFO_SHIFT;
+	opts.threads = threads;
+
+	f = strcmp(in_name, "-") ? fopen(in_name, "rb") : stdin;
+	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", argv[0], in_name); return 1; }
+	data = load_all(f, &len);
+	if (f != stdin) fclose(f);
+	if (!data) { fprintf(stderr, "%s: can't read input file \"%s\"\n", argv[0], in_name); return 1; }
+	if (jq_read(data, len, copy, &im, err)) { fprintf(stderr, "%s: %s\n", argv[0], err); free(data); return 1; }
+	free(data);
+	if (verbose)
+		fprintf(stderr, "%s: %ux%u, %d component(s), %s, restart interval %d\n", in_name, im.cinfo.image_width,
+				im.cinfo.image_height, im.cinfo.num_components, im.progressive ? "progressive" : "sequential",
+				im.restart_interval);
+
+	ret = do_quantsmooth(&im.cinfo, im.coef_arrays, &opts);
+	if (ret < 0) { jq_free(&im); return 2; }
+
+	if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
+		fprintf(stderr, "%s: %s\n", argv[0], err); jq_free(&im); return 1;
+	}
+	/* the output is opened after the input was read, so it may name the same file */
+	f = strcmp(out_name, "-") ? fopen(out_name, "wb") : stdout;
+	if (!f) { fprintf(stderr, "%s: can't open output file \"%s\"\n", argv[0], out_name); free(out); jq_free(&im); return 1; }
+	if (fwrite(out, 1, outlen, f) != outlen) { fprintf(stderr, "%s: write error\n", argv[0]); ret = 1; }
+	if (f != stdout) fclose(f);
+	free(out); jq_free(&im);
+	return ret > 0 ? 0 : ret;
+}

@@ -1,0 +1,135 @@
+"""The `jpegqs` command line tool (csrc/jpegqs.c) and its JPEG coefficient codec
+(csrc/jpegcoef.c).  CPU leg: the codec is a lossless transcoder (`-n 0` never reaches the
+CUDA back end) on baseline / progressive / sub-sampled / restart-marker / grayscale files
+written by Pillow's libjpeg-turbo, and markers are copied per `-c`.  GPU leg: the CUDA-backed
+tool must write byte-identical files to oracle/_ref/jpegqs_ref (the same front end linked
+against the UNMODIFIED reference do_quantsmooth, built by oracle/Makefile)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+PIL = pytest.importorskip("PIL.Image")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "jpeg-quantsmooth_b200", "csrc", "jpegqs")
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "jpegqs_ref")
+
+
+def _picture(w, h, gray, seed):
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    a = (128 + 60 * np.sin(x / 17.0) + 50 * np.cos(y / 23.0) + rng.randint(-20, 20, (h, w))).clip(0, 255).astype(np.uint8)
+    if gray:
+        return PIL.fromarray(a, "L")
+    b = (128 + 60 * np.cos(x / 11.0) + rng.randint(-30, 30, (h, w))).clip(0, 255).astype(np.uint8)
+    c = (128 + 80 * np.sin((x + y) / 29.0)).clip(0, 255).astype(np.uint8)
+    return PIL.fromarray(np.stack([a, b, c], -1), "RGB")
+
+
+FILES = [
+    ("base420", 64, 48, False, dict(quality=75)),
+    ("base444", 123, 77, False, dict(quality=90, subsampling=0)),
+    ("prog420", 200, 133, False, dict(quality=50, subsampling=2, progressive=True)),
+    ("gray", 97, 61, True, dict(quality=85)),
+    ("opt422", 160, 120, False, dict(quality=30, subsampling=1, optimize=True)),
+    ("prog444", 333, 211, False, dict(quality=95, progressive=True, subsampling=0)),
+    ("rst", 250, 190, False, dict(quality=80, restart_marker_rows=1)),
+    ("progrst", 250, 190, False, dict(quality=80, progressive=True, restart_marker_blocks=7)),
+    ("tinyprog", 17, 9, True, dict(quality=60, progressive=True)),
+]
+
+
+@pytest.fixture(scope="module")
+def jpegs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("jpegs")
+    out = {}
+    for k, (name, w, h, gray, kw) in enumerate(FILES):
+        p = str(d / (name + ".jpg"))
+        _picture(w, h, gray, k).save(p, comment=b"made by the test suite", **kw)
+        out[name] = p
+    return out
+
+
+def _pixels(path):
+    im = PIL.open(path)
+    return np.asarray(im if im.mode == "L" else im.convert("RGB"))
+
+
+def _markers(path):
+    data = open(path, "rb").read()
+    i, found = 2, []
+    while i + 4 <= len(data) and data[i] == 0xFF:
+        code = data[i + 1]
+        if code == 0xDA:
+            break
+        n = int.from_bytes(data[i + 2:i + 4], "big")
+        found.append((code, data[i + 4:i + 2 + n]))
+        i += 2 + n
+    return found
+
+
+def test_tool_is_built():
+    assert os.path.exists(EXE), "build() must produce csrc/jpegqs"
+
+
+@pytest.mark.parametrize("name", [f[0] for f in FILES])
+@pytest.mark.parametrize("optimize", [False, True])
+def test_codec_is_a_lossless_transcoder(jpegs, tmp_path, name, optimize):
+    out = str(tmp_path / "out.jpg")
+    r = subprocess.run([EXE, "-n", "0", "-i", "0"] + (["-o"] if optimize else []) + [jpegs[name], out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(_pixels(jpegs[name]), _pixels(out))
+    # re-reading our own output must be lossless as well
+    out2 = str(tmp_path / "out2.jpg")
+    assert subprocess.run([EXE, "-n", "0", "-i", "0", out, out2]).returncode == 0
+    assert np.array_equal(_pixels(out), _pixels(out2))
+
+
+def test_marker_copy_levels(jpegs, tmp_path):
+    src = jpegs["base420"]
+    for level, want_com, want_app in ((2, True, True), (1, True, False), (0, False, False)):
+        out = str(tmp_path / f"c{level}.jpg")
+        assert subprocess.run([EXE, "-n", "0", "-i", "0", "-c", str(level), src, out]).returncode == 0
+        m = _markers(out)
+        assert any(c == 0xFE and b"made by the test suite" in d for c, d in m) == want_com
+        assert any(0xE0 <= c <= 0xEF for c, _ in m) == want_app
+
+
+def test_bad_input_and_usage(tmp_path):
+    bad = tmp_path / "bad.jpg"
+    bad.write_bytes(b"this is not a jpeg")
+    r = subprocess.run([EXE, "-n", "0", str(bad), str(tmp_path / "o.jpg")], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a JPEG" in r.stderr
+    assert subprocess.run([EXE], capture_output=True).returncode == 1
+    assert subprocess.run([EXE, "-q", "x", "a", "b"], capture_output=True).returncode == 1
+
+
+def test_no_cpu_fallback_in_the_tool(jpegs, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = tmp_path / "o.jpg"
+    r = subprocess.run([EXE, "-q", "3", jpegs["base420"], str(out)], capture_output=True, text=True)
+    assert r.returncode == 2 and "CUDA back end unavailable" in r.stderr
+    assert not out.exists()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="oracle/_ref/jpegqs_ref not built")
+@pytest.mark.parametrize("name,args", [
+    ("base420", ["-q", "3"]), ("base420", ["-q", "6", "-n", "2"]), ("prog420", ["-q", "4", "-n", "2", "-o"]),
+    ("base444", ["-q", "5", "-n", "2"]), ("gray", ["-q", "3", "-n", "4"]), ("opt422", ["-q", "6"]),
+    ("prog444", ["-q", "1", "-n", "2"]), ("rst", ["-q", "0"]), ("progrst", ["-q", "2", "-o"]),
+    ("tinyprog", ["-q", "3"]), ("base420", ["-f", "16", "-n", "2"]),
+])
+def test_cuda_tool_writes_the_reference_tools_bytes(jpegs, tmp_path, name, args):
+    a, b = str(tmp_path / "cuda.jpg"), str(tmp_path / "ref.jpg")
+    r1 = subprocess.run([EXE, "-i", "0"] + args + [jpegs[name], a], capture_output=True, text=True)
+    r2 = subprocess.run([REF_EXE, "-i", "0"] + args + [jpegs[name], b], capture_output=True, text=True)
+    assert r1.returncode == 0, r1.stderr
+    assert r2.returncode == 0, r2.stderr
+    assert open(a, "rb").read() == open(b, "rb").read()
+    PIL.open(a).load()                      # and it is a decodable JPEG
