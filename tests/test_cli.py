@@ -122,10 +122,13 @@ def test_no_cpu_fallback_in_the_tool(jpegs, tmp_path):
 @pytest.mark.parametrize("name,args", [
     ("base420", ["-q", "3"]), ("base420", ["-q", "6", "-n", "2"]), ("prog420", ["-q", "4", "-n", "2", "-o"]),
     ("base444", ["-q", "5", "-n", "2"]), ("gray", ["-q", "3", "-n", "4"]), ("opt422", ["-q", "6"]),
-    ("prog444", ["-q", "1", "-n", "2"]), ("rst", ["-q", "0"]), ("progrst", ["-q", "2", "-o"]),
+    ("prog444", ["-q", "1", "-n", "2"]), ("rst", ["-q", "0"]), ("progrst", ["-q", "1", "-o"]),
+    ("opt422", ["-q", "2", "-o"]),
     ("tinyprog", ["-q", "3"]), ("base420", ["-f", "16", "-n", "2"]),
 ])
 def test_cuda_tool_writes_the_reference_tools_bytes(jpegs, tmp_path, name, args):
+    # UPSAMPLE_UV cases use widths that are multiples of the MCU: for other widths the reference
+    # reads uninitialised memory when it pads the up-sampled plane (DESIGN.md "reference quirks")
     a, b = str(tmp_path / "cuda.jpg"), str(tmp_path / "ref.jpg")
     r1 = subprocess.run([EXE, "-i", "0"] + args + [jpegs[name], a], capture_output=True, text=True)
     r2 = subprocess.run([REF_EXE, "-i", "0"] + args + [jpegs[name], b], capture_output=True, text=True)
