@@ -110,6 +110,8 @@ struct jpegqs_cuda_ctx {
 	int device, num_sms;
 	char devname[256];
 	cudaStream_t stream;
+	cudaStream_t copy_stream;              /* H2D / D2H of the host entry points, overlapped with compute */
+	std::vector<cudaEvent_t> sync_ev;      /* per group: coefficients uploaded / group finished */
 	float *tab_plain, *tab_diag;
 	QsQuantDev *quant_dev; int quant_cap;
 	QsJob *jobs_dev;                       /* two slots of QS_MAX_JOBS */
@@ -155,6 +157,8 @@ extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	for (cudaEvent_t e : ctx->sync_ev) cudaEventDestroy(e);
 	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->quant_dev);
 	cudaFree(ctx->jobs_dev); cudaFree(ctx->flags_dev); cudaFree(ctx->arena);
 	if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
@@ -184,7 +188,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	memset(ctx->err, 0, sizeof(ctx->err));
 	ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
 	snprintf(ctx->devname, sizeof(ctx->devname), "%s", prop.name);
-	ctx->stream = NULL; ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
+	ctx->stream = NULL; ctx->copy_stream = NULL; ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
@@ -192,6 +196,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
 		CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
 		std::vector<float> t(64 * QS_TAB_DIAG);
 		const float pre = 1073741824.0f;               /* 2^(2*QS_SCALE_BITS) */
@@ -404,7 +409,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				if (!on_device) bytes += align256(yb * 128);
 			}
 		}
-		s.ngroups = progress ? im->ncomp : (s.need_downsample ? 2 : 1);
+		/* host buffers: luma and chroma are separate phases even when independent, so that the
+		 * chroma upload and the luma download overlap with compute (copy stream + events) */
+		s.ngroups = progress ? im->ncomp : ((s.need_downsample || (!on_device && im->ncomp > 1)) ? 2 : 1);
 		if (s.ngroups > max_groups) max_groups = s.ngroups;
 	}
 	if (arena_reserve(ctx, bytes + 4096)) return JPEGQS_ERR_CUDA;
@@ -427,7 +434,6 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			if (on_device) w.coef_dev = c->coef;
 			else {
 				w.coef_dev = (int16_t *)arena_take(ctx, cb);
-				if (cb) CK(cudaMemcpyAsync(w.coef_dev, c->coef, cb, cudaMemcpyHostToDevice, st));
 			}
 			w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
 			w.qslot = (int)qhost.size();
@@ -446,6 +452,31 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	if (!qhost.empty())
 		CK(cudaMemcpyAsync(ctx->quant_dev, qhost.data(), qhost.size() * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
 	ctx->jobs_cache[0].clear(); ctx->jobs_cache[1].clear();
+
+	auto group_range = [&](const ImgState &s, int g, int *c0, int *c1) {
+		if (progress) { *c0 = g; *c1 = g + 1; }
+		else if (s.ngroups == 2) { *c0 = g ? 1 : 0; *c1 = g ? s.im->ncomp : 1; }
+		else { *c0 = 0; *c1 = s.im->ncomp; }
+	};
+	cudaStream_t cst = ctx->copy_stream;
+	if (!on_device) {                                   /* uploads, group by group, on the copy stream */
+		while ((int)ctx->sync_ev.size() < 2 * max_groups) {
+			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->sync_ev.push_back(e);
+		}
+		for (int g = 0; g < max_groups; g++) {
+			for (int n = 0; n < nimg; n++) {
+				ImgState &s = S[n];
+				if (s.skip || g >= s.ngroups) continue;
+				int c0, c1; group_range(s, g, &c0, &c1);
+				for (int ci = c0; ci < c1; ci++) {
+					CompWork &w = W[n][ci];
+					size_t cb = (size_t)w.W * w.H * 128;
+					if (cb) CK(cudaMemcpyAsync(w.coef_dev, w.c->coef, cb, cudaMemcpyHostToDevice, cst));
+				}
+			}
+			CK(cudaEventRecord(ctx->sync_ev[2 * g], cst));
+		}
+	}
 
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	int *bad_dev = ctx->flags_dev, *tile_counter = ctx->flags_dev + QS_MAX_JOBS;
@@ -471,16 +502,14 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	};
 
 	for (int g = 0; g < max_groups; g++) {
+		if (!on_device) CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0));
 		/* ---- which components belong to this phase; per-component prelude 2484-2566 ---- */
 		std::vector<CompWork *> works;
 		int prog_cur = 0, prog_inc = 0;
 		for (int n = 0; n < nimg; n++) {
-			ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
+			ImgState &s = S[n];
 			if (s.skip || g >= s.ngroups) continue;
-			int c0, c1;
-			if (progress) { c0 = g; c1 = g + 1; }
-			else if (s.ngroups == 2) { c0 = g ? 1 : 0; c1 = g ? im->ncomp : 1; }
-			else { c0 = 0; c1 = im->ncomp; }
+			int c0, c1; group_range(s, g, &c0, &c1);
 			for (int ci = c0; ci < c1; ci++) {
 				CompWork &w = W[n][ci];
 				if (progress) { prog_cur = prog_next; prog_inc = w.c->v_samp; prog_next += w.H * prog_inc * niter; }
@@ -606,6 +635,25 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				}
 			}
 		}
+		/* ---- downloads of this phase, on the copy stream, behind the phase's last kernel ---- */
+		if (!on_device) {
+			CK(cudaEventRecord(ctx->sync_ev[2 * g + 1], st));
+			CK(cudaStreamWaitEvent(cst, ctx->sync_ev[2 * g + 1], 0));
+			for (int n = 0; n < nimg; n++) {
+				ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
+				if (s.skip || g >= s.ngroups) continue;
+				int c0, c1; group_range(s, g, &c0, &c1);
+				for (int ci = c0; ci < c1; ci++) {
+					CompWork &w = W[n][ci];
+					size_t cb = (size_t)w.W * w.H * 128;
+					if (cb) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, cst));
+					if (s.image1 && !s.stop && ci >= 1 && ci <= 2) {
+						size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk * 128;
+						CK(cudaMemcpyAsync(w.c->coef_up, s.coef_up_dev[ci - 1], yb, cudaMemcpyDeviceToHost, cst));
+					}
+				}
+			}
+		}
 	}
 	CK(cudaEventRecord(ctx->ev1, st));
 
@@ -616,18 +664,13 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		bool ups = s.image1 && !s.stop;                                 /* 2834-2849 */
 		for (int ci = 0; ci < im->ncomp; ci++) {
 			CompWork &w = W[n][ci];
-			size_t cb = (size_t)w.W * w.H * 128;
-			if (!on_device && cb) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, st));
-			if (ups && ci >= 1 && ci <= 2 && !on_device) {
-				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk * 128;
-				CK(cudaMemcpyAsync(w.c->coef_up, s.coef_up_dev[ci - 1], yb, cudaMemcpyDeviceToHost, st));
-			}
 			if (w.c->has_qtbl) for (int k = 0; k < 64; k++) w.c->quant[k] = 1;      /* 2851-2859 */
 		}
 		im->upsampled = ups ? 1 : 0;
 		if (ret) ret[n] = s.stop;
 	}
 	CK(cudaStreamSynchronize(st));
+	if (!on_device) CK(cudaStreamSynchronize(cst));
 	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 	if (prof_collect(ctx)) return JPEGQS_ERR_CUDA;
 	return 0;
