@@ -256,7 +256,19 @@ def main():
             ret, _ = ctx.run_device(im, [t.data_ptr() for t in dev_bufs[i]], [], FLAGS, NITER, stream)
             return ret
     else:
-        passes = mg.CudaPasses(ctx, stream)
+        class TimedPasses(mg.CudaPasses):
+            """CUDA events around every smoothing pass (on the launching stream) for the roofline."""
+            events = []
+            timing = False
+
+            def smooth(self, *a, **k):
+                if not self.timing:
+                    return super().smooth(*a, **k)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(); super().smooth(*a, **k); e1.record()
+                self.events.append((e0, e1))
+
+        passes = TimedPasses(ctx, stream)
         planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev)
                   for c in im.comps]
         allreduce_flag = mg.make_flag_allreduce(dist, dev)
@@ -282,6 +294,8 @@ def main():
     launches = 0
     smooth_ms, smooth_n, idct_ms, idct_n = 0.0, 0, 0.0, 0
     barrier()
+    if world > 1:
+        passes.timing = True
     sampler.t0 = time.perf_counter()
     e0.record()
     for i in range(K):
@@ -296,6 +310,10 @@ def main():
     barrier()
     sampler.t1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        passes.timing = False
+        smooth_ms = sum(a.elapsed_time(b) for a, b in passes.events)
+        smooth_n = len(passes.events)
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -310,7 +328,7 @@ def main():
     # ---- roofline of the dominant kernel (smoothing pass) -------------------------------
     peak, peak_src = peaks()
     roofline = None
-    if world == 1 and smooth_n:
+    if smooth_n:
         bytes_per_launch = ALGO_BYTES_PER_BLOCK_ITER * nblocks_rank
         avg_ms = smooth_ms / smooth_n
         achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
@@ -319,7 +337,8 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "qs_smooth_kernel", "achieved": round(achieved, 2),
+        roofline = {"bound": "hbm", "kernel": "qs_smooth_kernel" + ("" if world == 1 else " (rank 0's slab)"),
+                    "achieved": round(achieved, 2),
                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
                     "peak_source": peak_src, "avg_launch_ms": round(avg_ms, 4),
                     "algorithmic_bytes_per_launch": bytes_per_launch,
