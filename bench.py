@@ -276,7 +276,7 @@ def main():
         def step(i):
             comps = [mg.SlabComp(dev_bufs[i][k], planes[k], c.wblk, c.hblk, c.quant, k == 0)
                      for k, c in enumerate(im.comps)]
-            return mg.run_slab(passes, comps, FLAGS, NITER, rank, world, dist, allreduce_flag)
+            return mg.run_slab(passes, comps, FLAGS, NITER, rank, world, dist, allreduce_flag)[0]
 
     def barrier():
         torch.cuda.synchronize()

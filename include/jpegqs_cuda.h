@@ -131,6 +131,23 @@ int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job
 int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jobs, int flags,
 		int clamp_out, void *stream);
 
+/* luma -> chroma hand-over for slabs (JOINT_YUV / UPSAMPLE_UV): the down-sampled luma plane
+ * of quantsmooth.h:2753-2815 for one slab.  Rows are addressed inside the WHOLE component:
+ * y_row0 / c_row0 = first luma / chroma block row of the slab, *_hblk_total = block rows of the
+ * whole component.  Writes the slab's rows of plane2 (chroma slab geometry, c_rows block rows)
+ * incl. the left/right border and, at an image edge, the replicated border rows; interior
+ * halo rows (row -1 / row c_rows*8 of the slab) must be exchanged by the caller. */
+int jpegqs_cuda_pass_downsample(jpegqs_cuda_ctx *ctx, const uint8_t *yplane, uint32_t y_wblk,
+		uint32_t y_row0, uint32_t y_hblk_total, uint8_t *plane2, uint32_t c_wblk, uint32_t c_rows, uint32_t c_row0,
+		uint32_t c_hblk_total, int ws, int hs, int top_edge, int bottom_edge, void *stream);
+/* upsample_row + FDCT (quantsmooth.h:2691-2752) for one chroma component of one slab: fills
+ * coef_up [y_rows][y_wblk][64]; scratch = y_wblk*8 * y_rows*8 bytes of device memory.  The
+ * chroma plane and plane2 need valid halo rows (3x3 windows). */
+int jpegqs_cuda_pass_upsample(jpegqs_cuda_ctx *ctx, const uint8_t *cplane, const uint8_t *plane2,
+		uint32_t c_wblk, const uint8_t *yplane, uint32_t y_wblk, uint32_t y_rows, uint32_t y_row0,
+		int16_t *coef_up, uint8_t *scratch, int ws, int hs, uint32_t image_width, uint32_t image_height,
+		void *stream);
+
 /* ---- introspection used by the parity tests ------------------------------------------- */
 /* the 64 weight tables exactly as the device consumes them but WITHOUT the power-of-two
  * pre-scale, natural coefficient order, 160 (or 272 with JPEGQS_DIAGONALS) floats each;

@@ -618,7 +618,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				int W0 = im->comp[0].wblk, H0 = im->comp[0].hblk;
 				uint8_t *mem = s.mem_buf[w->ci - 1];
 				CK(qs_launch_upsample(w->plane, s.image2, QS_PLANE_STRIDE(w->W), s.image1, QS_PLANE_STRIDE(W0),
-						mem, W0 * 8, w1, h1, ws, hs, W0 * 8, H0 * 8, st));
+						mem, W0 * 8, w1, h1, ws, hs, W0 * 8, H0 * 8, 0, st));
 				CK(qs_launch_fdct_plane(mem, W0 * 8, s.coef_up_dev[w->ci - 1], W0, H0, st));
 				ctx->launches += 2;
 			} else if (w->ci == 0 && s.need_downsample) {
@@ -754,5 +754,39 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, st));
 	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+	return 0;
+}
+
+/* ---- luma -> chroma hand-over for slabs (JOINT_YUV / UPSAMPLE_UV across GPUs) ------------- */
+extern "C" int jpegqs_cuda_pass_downsample(jpegqs_cuda_ctx *ctx, const uint8_t *yplane, uint32_t y_wblk,
+		uint32_t y_row0, uint32_t y_hblk_total, uint8_t *plane2, uint32_t c_wblk, uint32_t c_rows, uint32_t c_row0,
+		uint32_t c_hblk_total, int ws, int hs, int top_edge, int bottom_edge, void *stream) {
+	if (!ctx || !yplane || !plane2 || ws < 1 || hs < 1) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	int h = (int)y_hblk_total * 8, h2 = (int)c_hblk_total * 8, h1_total = (h + hs - 1) / hs;
+	int first = top_edge ? -1 : (int)c_row0 * 8;
+	int last = bottom_edge ? h2 : (int)(c_row0 + c_rows) * 8 - 1;
+	int dstride = QS_PLANE_STRIDE(c_wblk);
+	if (last < first) return 0;
+	CK(qs_launch_downsample(yplane, QS_PLANE_STRIDE(y_wblk), (int)y_wblk * 8, h,
+			plane2 + (size_t)(first - (int)c_row0 * 8 + 1) * dstride, dstride, (int)c_wblk * 8, h2, ws, hs,
+			(int)y_row0 * 8, first, last - first + 1, h1_total, st));
+	return 0;
+}
+
+extern "C" int jpegqs_cuda_pass_upsample(jpegqs_cuda_ctx *ctx, const uint8_t *cplane, const uint8_t *plane2,
+		uint32_t c_wblk, const uint8_t *yplane, uint32_t y_wblk, uint32_t y_rows, uint32_t y_row0,
+		int16_t *coef_up, uint8_t *scratch, int ws, int hs, uint32_t image_width, uint32_t image_height,
+		void *stream) {
+	if (!ctx || !cplane || !plane2 || !yplane || !coef_up || !scratch || ws < 1 || hs < 1) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	int w1 = ((int)image_width + ws - 1) / ws, h1 = ((int)image_height + hs - 1) / hs;
+	int ww = (int)y_wblk * 8, hh = (int)y_rows * 8;
+	if (!ww || !hh) return 0;
+	CK(qs_launch_upsample(cplane, plane2, QS_PLANE_STRIDE(c_wblk), yplane, QS_PLANE_STRIDE(y_wblk),
+			scratch, ww, w1, h1, ws, hs, ww, hh, (int)y_row0 * 8, st));
+	CK(qs_launch_fdct_plane(scratch, ww, coef_up, (int)y_wblk, (int)y_rows, st));
 	return 0;
 }

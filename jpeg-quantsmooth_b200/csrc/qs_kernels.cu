@@ -911,12 +911,14 @@ __global__ void qs_downsample_kernel(const uint8_t *__restrict__ src, int sstrid
  * ------------------------------------------------------------------------------------------ */
 __global__ void qs_upsample_kernel(const uint8_t *__restrict__ C, const uint8_t *__restrict__ Yd, int cstride,
 		const uint8_t *__restrict__ Yf, int ystride, uint8_t *__restrict__ out, int ostride,
-		int w1, int h1, int ws, int hs, int ww, int hh) {
+		int w1, int h1, int ws, int hs, int ww, int hh, int oy0) {
+	/* oy0 = first output (luma) pixel row of this slab inside the whole component: planes and
+	 * `out` are slab-local, w1/h1 are whole-image quantities (0 for a single-GPU run) */
 	int ox = blockIdx.x * blockDim.x + threadIdx.x;     /* output pixel */
 	int oy = blockIdx.y * blockDim.y + threadIdx.y;
 	if (ox >= ww || oy >= hh) return;
-	int sx = min(ox, w1 * ws - 1), sy = min(oy, h1 * hs - 1);
-	int x = sx / ws, y = sy / hs;
+	int sx = min(ox, w1 * ws - 1), sy = min(oy + oy0, h1 * hs - 1) - oy0;
+	int x = sx / ws, y = (sy + oy0) / hs - oy0 / hs;
 	const uint8_t *pc = C + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
 	const uint8_t *pd = Yd + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
 	int sA, sB;
@@ -1046,9 +1048,9 @@ cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, 
 }
 
 cudaError_t qs_launch_upsample(const uint8_t *C, const uint8_t *Yd, int cstride, const uint8_t *Yf, int ystride,
-		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, cudaStream_t st) {
+		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, int oy0, cudaStream_t st) {
 	dim3 blk(64, 4), grd((ww + 63) / 64, (hh + 3) / 4);
-	qs_upsample_kernel<<<grd, blk, 0, st>>>(C, Yd, cstride, Yf, ystride, out, ostride, w1, h1, ws, hs, ww, hh);
+	qs_upsample_kernel<<<grd, blk, 0, st>>>(C, Yd, cstride, Yf, ystride, out, ostride, w1, h1, ws, hs, ww, hh, oy0);
 	return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, 
 		int w2, int h2, int ws, int hs, int src_row0, int dst_row_first, int dst_rows, int h1_total,
 		cudaStream_t st);
 cudaError_t qs_launch_upsample(const uint8_t *C, const uint8_t *Yd, int cstride, const uint8_t *Yf, int ystride,
-		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, cudaStream_t st);
+		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, int oy0, cudaStream_t st);
 cudaError_t qs_launch_fdct_plane(const uint8_t *px, int pstride, int16_t *coef, int W, int H, cudaStream_t st);
 extern "C" int qs_host_orig_coef(int c, int q);
 #endif

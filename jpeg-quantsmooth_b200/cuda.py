@@ -87,6 +87,12 @@ def load():
                                           C.POINTER(C.c_int), C.c_void_p]
     lib.jpegqs_cuda_pass_smooth.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Job), C.c_int, C.c_int,
                                             C.c_void_p]
+    lib.jpegqs_cuda_pass_downsample.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.jpegqs_cuda_pass_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                              C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.jpegqs_cuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.jpegqs_cuda_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                              C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -309,6 +315,18 @@ class QsContext:
         arr = (_Job * len(jobs))(*jobs)
         self._check(self.lib.jpegqs_cuda_pass_smooth(self.h, len(jobs), arr, flags & 0x7f, int(clamp_out),
                                                      C.c_void_p(stream or None)))
+
+    def pass_downsample(self, yplane, y_wblk, y_row0, y_hblk_total, plane2, c_wblk, c_rows, c_row0,
+                        c_hblk_total, ws, hs, top_edge, bottom_edge, stream: int = 0):
+        self._check(self.lib.jpegqs_cuda_pass_downsample(
+            self.h, yplane, y_wblk, y_row0, y_hblk_total, plane2, c_wblk, c_rows, c_row0, c_hblk_total,
+            ws, hs, int(top_edge), int(bottom_edge), C.c_void_p(stream or None)))
+
+    def pass_upsample(self, cplane, plane2, c_wblk, yplane, y_wblk, y_rows, y_row0, coef_up, scratch,
+                      ws, hs, image_width, image_height, stream: int = 0):
+        self._check(self.lib.jpegqs_cuda_pass_upsample(
+            self.h, cplane, plane2, c_wblk, yplane, y_wblk, y_rows, y_row0, coef_up, scratch, ws, hs,
+            image_width, image_height, C.c_void_p(stream or None)))
 
     def plane_bytes(self, wblk, hblk) -> int:
         return int(self.lib.jpegqs_cuda_plane_bytes(wblk, hblk))

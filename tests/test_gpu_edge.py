@@ -151,6 +151,28 @@ def test_pass_level_slabs_are_shard_invariant(ctx, nshards, flags):
         assert np.array_equal(g, c.coef)
 
 
+@pytest.mark.parametrize("flags,ss,w,h", [(3, "420", 256, 208), (7, "420", 250, 130), (15, "420", 128, 96),
+                                          (7, "444", 96, 64), (7, "422", 128, 64)])
+def test_run_slab_pass_level_luma_chroma_handover(ctx, flags, ss, w, h):
+    """The pass-level path incl. jpegqs_cuda_pass_downsample / _upsample (one slab = the whole
+    image) against the oracle; the multi-slab logic on top is covered over gloo on the CPU."""
+    import torch
+    dev = torch.device("cuda", 0)
+    im = qs.synth.make_image(w, h, ss)
+    comps = [mg.SlabComp(torch.from_numpy(np.ascontiguousarray(c.coef)).to(dev),
+                         torch.zeros((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev),
+                         c.wblk, c.hblk, c.quant, k == 0, c.h_samp, c.v_samp, 0, c.hblk)
+             for k, c in enumerate(im.comps)]
+    passes = mg.CudaPasses(ctx, torch.cuda.current_stream().cuda_stream)
+    stop, ups = mg.run_slab(passes, comps, flags, 2, 0, 1, None, None, mg.SlabGeom(True, w, h))
+    torch.cuda.synchronize()
+    oret, want = ol.run_oracle(im, flags, 2)
+    assert stop == oret
+    for k, (c, o) in enumerate(zip(comps, want.comps)):
+        got = (c.coef_up if ups and k in (1, 2) else c.coef).cpu().numpy()
+        assert got.shape == o.coef.shape and np.array_equal(got, o.coef), k
+
+
 def test_tuning_variants_are_bit_identical(ctx):
     im = qs.synth.make_image(320, 240, "420")
     _, want = ol.run_oracle(im, 1, 2)

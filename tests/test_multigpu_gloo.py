@@ -49,16 +49,21 @@ def _worker(rank, world, port, cfg, outdir):
         slab = qs.synth.make_image(w, h, ss, mcu_rows=rng)
         comps_src = [(c.coef, c) for c in slab.comps]
     comps = []
+    geom_src = full if kind else qs.synth.make_image(w, h, ss, mcu_rows=(0, 0))
+    fullh = [qs.blocks_for(h, c.v_samp, max(cc.v_samp for cc in geom_src.comps)) for c in geom_src.comps]
     for k, (coef, c) in enumerate(comps_src):
         rows = coef.shape[0]
+        r0, _ = mg.comp_block_rows(rng, c.v_samp, fullh[k])
         comps.append(mg.SlabComp(torch.from_numpy(np.ascontiguousarray(coef)),
                                  torch.zeros((rows * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8),
-                                 c.wblk, rows, c.quant, k == 0 or ss == "gray"))
+                                 c.wblk, rows, c.quant, k == 0 or ss == "gray", c.h_samp, c.v_samp, r0, fullh[k]))
+    geom = mg.SlabGeom(ss != "gray", w, h)
 
     allreduce_flag = mg.make_flag_allreduce(dist, torch.device('cpu'))
 
-    stop = mg.run_slab(OraclePasses(flags), comps, flags, niter, rank, world, dist, allreduce_flag)
-    np.savez(os.path.join(outdir, f"r{rank}.npz"), stop=stop, **{f"c{k}": c.coef.numpy() for k, c in enumerate(comps)})
+    stop, ups = mg.run_slab(OraclePasses(flags), comps, flags, niter, rank, world, dist, allreduce_flag, geom)
+    outs = {f"c{k}": (c.coef_up if ups and k in (1, 2) else c.coef).numpy() for k, c in enumerate(comps)}
+    np.savez(os.path.join(outdir, f"r{rank}.npz"), stop=stop, ups=int(ups), **outs)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,6 +74,11 @@ CFGS = [
     (2, (48, 40, "gray", 16, 3, None)),        # NO_REBALANCE, 8-row MCUs
     (2, (0, 0, "420", 0, 2, "badcoef")),       # stop semantics across ranks
     (2, (64, 96, "420", 8, 2, None)),          # LOW_QUALITY
+    (2, (96, 80, "420", 3, 2, None)),          # JOINT_YUV: luma plane handed to the chroma phase
+    (3, (64, 112, "420", 7, 2, None)),         # + UPSAMPLE_UV, uneven split
+    (2, (48, 64, "444", 7, 2, None)),          # 4:4:4: the luma plane itself is the predictor
+    (2, (90, 72, "420", 7, 1, None)),          # ragged size: edge replication inside the last slab
+    (2, (0, 0, "420", 7, 2, "badcoef")),       # stop in the chroma phase
 ]
 
 

@@ -100,11 +100,15 @@ def sharded(cfg, size, flags, niter, check):
     total = (size + 15) // 16
     rng = mg.split_mcu_rows(total, world)[rank]
     slab = qs.synth.make_image_torch(size, size, "420", mcu_rows=rng, device=dev)
+    geom = mg.SlabGeom(True, size, size)
+    fullh = [qs.blocks_for(size, c.v_samp, 2) for c in slab.comps]
     src = [c.coef for c in slab.comps]
     work = [torch.empty_like(t) for t in src]
     planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev) for c in slab.comps]
     passes = mg.CudaPasses(ctx, stream)
     allreduce_flag = mg.make_flag_allreduce(dist, dev) if dist is not None else None
+
+    state = {}
 
     def copy_only():
         for a, b in zip(work, src):
@@ -112,8 +116,10 @@ def sharded(cfg, size, flags, niter, check):
 
     def fn():
         copy_only()
-        comps = [mg.SlabComp(work[k], planes[k], c.wblk, c.hblk, c.quant, k == 0) for k, c in enumerate(slab.comps)]
-        mg.run_slab(passes, comps, flags, niter, rank, world, dist, allreduce_flag)
+        comps = [mg.SlabComp(work[k], planes[k], c.wblk, c.hblk, c.quant, k == 0, c.h_samp, c.v_samp,
+                             mg.comp_block_rows(rng, c.v_samp, fullh[k])[0], fullh[k]) for k, c in enumerate(slab.comps)]
+        state["ups"] = mg.run_slab(passes, comps, flags, niter, rank, world, dist, allreduce_flag, geom)[1]
+        state["comps"] = comps
     ms = timed(fn, args.reps) - timed(copy_only, args.reps)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -127,12 +133,18 @@ def sharded(cfg, size, flags, niter, check):
         torch.cuda.synchronize()
         full = qs.synth.make_image_torch(size, size, "420", device=dev)
         fw = [c.coef.clone() for c in full.comps]
-        ctx.run_device(full, [t.data_ptr() for t in fw], [], flags, niter, stream)
+        y = full.comps[0]
+        fup = [torch.empty((y.hblk, y.wblk, 64), dtype=torch.int16, device=dev) for _ in range(2)]
+        _, ups1 = ctx.run_device(full, [t.data_ptr() for t in fw], [None] + [t.data_ptr() for t in fup], flags, niter, stream)
         torch.cuda.synchronize()
-        bad = 0
+        bad = int(ups1 != state["ups"])
         for k, c in enumerate(full.comps):
-            r0, r1 = mg.comp_block_rows(rng, c.v_samp, c.hblk)
-            bad += int((fw[k][r0:r1] != work[k]).sum().item())
+            if ups1 and k in (1, 2):
+                r0, r1 = mg.comp_block_rows(rng, 2, y.hblk)
+                bad += int((fup[k - 1][r0:r1] != state["comps"][k].coef_up).sum().item())
+            else:
+                r0, r1 = mg.comp_block_rows(rng, c.v_samp, c.hblk)
+                bad += int((fw[k][r0:r1] != work[k]).sum().item())
         b = torch.tensor([bad], dtype=torch.int64, device=dev)
         if dist is not None:
             dist.all_reduce(b)
@@ -151,5 +163,7 @@ for cfg in [int(x) for x in args.configs.split(",")]:
             batch(4, n, 0, 3)
     elif cfg == 5:
         sharded(5, args.size, 1, 5, args.check)
+    elif cfg == 6:                      # q6 sharded (JOINT_YUV + UPSAMPLE_UV across slabs)
+        sharded("6 (q6 sharded)", args.size, 7, 3, args.check)
 if dist is not None:
     dist.destroy_process_group()
