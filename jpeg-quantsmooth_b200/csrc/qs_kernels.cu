@@ -328,9 +328,16 @@ __device__ __forceinline__ void qs_term(float ds, float nad, float w, float Rs, 
 	a3 = FA(a3, FM(a1, a1));
 }
 
-template <int N, int NT>
+/* one pixel of a packed row: word 0 = pixels 0..3, word 1 = pixels 4..7 */
+__device__ __forceinline__ float qs_px8(uint2 w, int j) { return j < 4 ? qs_px(w.x, j) : qs_px(w.y, j - 4); }
+
+/* All terms of one row step for the N coefficients of a chunk.  `prep(c)` is called after each
+ * coefficient's terms: it expands a slice of the NEXT row's pixels, so the PRMTs (ALU pipe,
+ * half rate) are interleaved with the FP work instead of forming a burst at the loop end
+ * where, in lock step, all four warps of the sub-partition would queue on the ALU pipe. */
+template <int N, int NT, class Prep>
 __device__ __forceinline__ void qs_terms_row(const float *d, const float *const *tab, int off,
-		const float *Rs, float *a2, float *a3) {
+		const float *Rs, float *a2, float *a3, Prep prep) {
 	float nad[8];
 #pragma unroll
 	for (int x = 0; x < NT; x++) nad[x] = -fabsf(d[x]);
@@ -340,14 +347,21 @@ __device__ __forceinline__ void qs_terms_row(const float *d, const float *const 
 		float w[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
 #pragma unroll
 		for (int x = 0; x < NT; x++) qs_term(d[x], nad[x], w[x], Rs[c], a2[c], a3[c]);
+		prep(c);
 	}
 }
 
+/* expands pixels [c*8/N, (c+1)*8/N) (rounded so that the N slices cover 0..7) of word w */
+template <int N>
+__device__ __forceinline__ void qs_prep_slice(uint2 w, float *f, int c) {
+#pragma unroll
+	for (int j = 0; j < 8; j++) if (j * N / 8 == c) f[j] = qs_px8(w, j);
+}
+
 /* The four sections below are software pipelined by hand: the packed pixel words of the
- * NEXT row are loaded before the current row's ~28*N FP instructions and expanded / differenced
- * after them, so neither the LDS latency nor the PRMT->FADD chain sits in front of the FP work
- * (in lock step all warps of a sub-partition would otherwise wait for their LDS at the same
- * time; the first lock-step capture had 34 % of the stall samples on these lines). */
+ * NEXT row are loaded before the current row's ~28*N FP instructions, expanded in slices
+ * between the coefficients and differenced afterwards, so neither the LDS latency nor the
+ * PRMT->FADD chain sits in front of the FP work. */
 
 /* horizontal pairs, quantsmooth.h:1527 */
 template <int N>
@@ -363,9 +377,8 @@ __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *ta
 #pragma unroll 1
 	for (int y = 0; y < 8; y++) {
 		uint2 wn = pw[((y + 1) & 7) * 32];              /* next row (wraps on the last pass) */
-		qs_terms_row<N, 7>(d, tab, y * 8, Rs, a2, a3);
 		float f[8];
-		qs_unpack8(wn, f);
+		qs_terms_row<N, 7>(d, tab, y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, f, c); });
 #pragma unroll
 		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
 	}
@@ -388,9 +401,9 @@ __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *cons
 		int sn = (s + 1) & 3;
 		int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;     /* word of the block edge for step sn */
 		uint2 wa = pw[wi * 32], wb = pw[(10 + sn) * 32];
-		qs_terms_row<N, 8>(d, tab, 64 + s * 8, Rs, a2, a3);
 		float fa[8], fb[8];
-		qs_unpack8(wa, fa); qs_unpack8(wb, fb);
+		qs_terms_row<N, 8>(d, tab, 64 + s * 8, Rs, a2, a3,
+				[&](int c) { qs_prep_slice<N>(wa, fa, c); qs_prep_slice<N>(wb, fb, c); });
 #pragma unroll
 		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
 	}
@@ -410,15 +423,14 @@ __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *ta
 #pragma unroll 1
 	for (int y = 0; y < 7; y++) {
 		uint2 wn = pw[min(y + 2, 7) * 32];
-		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3);
 		float fn[8];
-		qs_unpack8(wn, fn);
+		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, fn, c); });
 #pragma unroll
 		for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
 	}
 }
 
-/* diagonal pairs, quantsmooth.h:1533-1540: per (y,x) first "\" then "/" */
+/* diagonal pairs, quantsmooth.h:1533-1540: per (y,x) first "\\" then "/" */
 template <int N>
 __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
@@ -432,6 +444,7 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 #pragma unroll 1
 	for (int y = 0; y < 7; y++) {
 		uint2 wn = pw[min(y + 2, 7) * 32];
+		float fn[8];
 #pragma unroll
 		for (int c = 0; c < N; c++) {
 			const float *t = tab[c] + 160 + y * 16;
@@ -444,9 +457,8 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 				qs_term(d1[x], -fabsf(d1[x]), w1[x], Rs[c], a2[c], a3[c]);
 				qs_term(d2[x], -fabsf(d2[x]), w2[x], Rs[c], a2[c], a3[c]);
 			}
+			qs_prep_slice<N>(wn, fn, c);
 		}
-		float fn[8];
-		qs_unpack8(wn, fn);
 #pragma unroll
 		for (int x = 0; x < 7; x++) { d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]); }
 #pragma unroll
