@@ -148,6 +148,16 @@ int jpegqs_cuda_pass_upsample(jpegqs_cuda_ctx *ctx, const uint8_t *cplane, const
 		int16_t *coef_up, uint8_t *scratch, int ws, int hs, uint32_t image_width, uint32_t image_height,
 		void *stream);
 
+/* ---- decode to interleaved 8-bit RGB -----------------------------
+ * What libjpeg produces after the reference's jpegqs_start_decompress (quantsmooth.h:2880-2904):
+ * islow IDCT, libjpeg's "fancy" chroma up-sampling (h2v1 / h2v2; other ratios: replication),
+ * YCbCr -> RGB with libjpeg's fixed-point constants.  1 or 3 components.  Components whose
+ * quant table is not all ones are de-quantized first, so the call also decodes an untouched
+ * coefficient set.  rgb: image_width * image_height * 3 bytes (host, or device if on_device;
+ * device coefficient arrays that still carry quant tables are de-quantized in place). */
+int jpegqs_cuda_render_rgb(jpegqs_cuda_ctx *ctx, const jpegqs_cuda_image *img, int on_device,
+		uint8_t *rgb, void *stream);
+
 /* ---- introspection used by the parity tests ------------------------------------------- */
 /* the 64 weight tables exactly as the device consumes them but WITHOUT the power-of-two
  * pre-scale, natural coefficient order, 160 (or 272 with JPEGQS_DIAGONALS) floats each;

@@ -12,6 +12,9 @@
  *     -p, --cpu n        CUDA device ordinal + 1 (0 = current device); the reference's SIMD cap
  *     -f, --flags n      raw JPEGQS_* flag bits instead of -q
  *     -c, --copy n       0 = no markers, 1 = comments, 2 = comments + APPn (default)
+ *     --ppm              (extension) write the decoded RGB image as binary PPM/PGM instead of a
+ *                        JPEG: the device-side equivalent of the reference's example.c
+ *                        (JPEG -> pixels through jpegqs_start_decompress)
  * The flow is the reference's (quantsmooth.c:494-596): read coefficients, do_quantsmooth,
  * write coefficients + copied markers.  libjpeg is replaced by jpegcoef.c because its headers
  * are not available in this build image.  Exit code: 0 ok, 1 usage / I/O / codec error,
@@ -24,6 +27,7 @@
 #include <jpeglib.h>
 #include "libjpegqs.h"
 #include "jpegcoef.h"
+#include "jpegqs_cuda.h"
 
 static unsigned char *load_all(FILE *f, size_t *len) {
 	size_t cap = 1 << 20, n = 0, r; unsigned char *p = (unsigned char*)malloc(cap);
@@ -54,7 +58,7 @@ static int usage(const char *prog) {
 
 int main(int argc, char **argv) {
 	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
-	int i, ret, flags = 0;
+	int i, ret, flags = 0, ppm = 0;
 	const char *in_name, *out_name;
 	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
 	jq_image im; char err[256]; jpegqs_control_t opts;
@@ -66,6 +70,7 @@ int main(int argc, char **argv) {
 		const char *a = argv[i], *val = NULL; int k, which = -1;
 		if (a[0] != '-' || !a[1]) break;
 		if (!strcmp(a, "--")) { i++; break; }
+		if (!strcmp(a, "--ppm")) { ppm = 1; continue; }
 		for (k = 0; k < (int)(sizeof(O) / sizeof(O[0])); k++) {
 			if (a[1] != '-' && a[1] == O[k].s) { which = k; if (a[2]) val = a + 2; break; }
 			if (!strcmp(a, O[k].l)) { which = k; break; }
@@ -116,7 +121,42 @@ int main(int argc, char **argv) {
 	ret = do_quantsmooth(&im.cinfo, im.coef_arrays, &opts);
 	if (ret < 0) { jq_free(&im); return 2; }
 
-	if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
+	if (ppm) {                                          /* decode to RGB on the device */
+		jpegqs_cuda_ctx *ctx = NULL; jpegqs_cuda_image ci; int c, nc = im.cinfo.num_components, rc;
+		int16_t *bufs[MAX_COMPONENTS] = { 0 }; unsigned char *rgb; char hdr[64]; int hl;
+		size_t npx = (size_t)im.cinfo.image_width * im.cinfo.image_height;
+		if (jpegqs_cuda_create(cpu ? cpu - 1 : -1, &ctx)) {
+			fprintf(stderr, "%s: CUDA back end unavailable: %s\n", argv[0], jpegqs_cuda_last_error(NULL));
+			jq_free(&im); return 2;
+		}
+		memset(&ci, 0, sizeof(ci));
+		ci.ncomp = nc; ci.is_ycbcr = im.cinfo.jpeg_color_space == JCS_YCbCr;
+		ci.image_width = im.cinfo.image_width; ci.image_height = im.cinfo.image_height;
+		for (c = 0; c < nc; c++) {
+			jpeg_component_info *k = &im.cinfo.comp_info[c]; JDIMENSION y;
+			size_t rowb = (size_t)k->width_in_blocks * sizeof(JBLOCK);
+			bufs[c] = (int16_t*)malloc(rowb * k->height_in_blocks + 1);
+			for (y = 0; y < k->height_in_blocks; y++)
+				memcpy((char*)bufs[c] + y * rowb, (*im.cinfo.mem->access_virt_barray)((j_common_ptr)&im.cinfo,
+						im.coef_arrays[c], y, 1, FALSE)[0], rowb);
+			ci.comp[c].coef = bufs[c]; ci.comp[c].wblk = k->width_in_blocks; ci.comp[c].hblk = k->height_in_blocks;
+			ci.comp[c].h_samp = k->h_samp_factor; ci.comp[c].v_samp = k->v_samp_factor;
+			ci.comp[c].has_qtbl = k->quant_table != NULL;
+			if (k->quant_table) memcpy(ci.comp[c].quant, k->quant_table->quantval, sizeof(ci.comp[c].quant));
+		}
+		rgb = (unsigned char*)malloc(npx * 3 + 1);
+		rc = jpegqs_cuda_render_rgb(ctx, &ci, 0, rgb, NULL);
+		if (rc) fprintf(stderr, "%s: render failed (%d): %s\n", argv[0], rc, jpegqs_cuda_last_error(ctx));
+		for (c = 0; c < nc; c++) free(bufs[c]);
+		jpegqs_cuda_destroy(ctx);
+		if (rc) { free(rgb); jq_free(&im); return 2; }
+		if (nc == 1) { size_t k; for (k = 0; k < npx; k++) rgb[k] = rgb[3 * k]; }
+		hl = snprintf(hdr, sizeof(hdr), "P%d\n%u %u\n255\n", nc == 1 ? 5 : 6, im.cinfo.image_width, im.cinfo.image_height);
+		outlen = hl + npx * (nc == 1 ? 1 : 3);
+		out = (unsigned char*)malloc(outlen);
+		memcpy(out, hdr, hl); memcpy(out + hl, rgb, outlen - hl);
+		free(rgb);
+	} else if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
 		fprintf(stderr, "%s: %s\n", argv[0], err); jq_free(&im); return 1;
 	}
 	/* the output is opened after the input was read, so it may name the same file */

@@ -790,3 +790,70 @@ extern "C" int jpegqs_cuda_pass_upsample(jpegqs_cuda_ctx *ctx, const uint8_t *cp
 	CK(qs_launch_fdct_plane(scratch, ww, coef_up, (int)y_wblk, (int)y_rows, st));
 	return 0;
 }
+
+/* ---- decode to RGB --------------------------------------------------- */
+extern "C" int jpegqs_cuda_render_rgb(jpegqs_cuda_ctx *ctx, const jpegqs_cuda_image *img, int on_device,
+		uint8_t *rgb, void *stream) {
+	if (!ctx || !img || !rgb) return JPEGQS_ERR_ARG;
+	int nc = img->ncomp;
+	if (nc != 1 && nc != 3) {
+		snprintf(ctx->err, sizeof(ctx->err), "render_rgb supports 1 or 3 components (got %d)", nc);
+		return JPEGQS_ERR_UNSUPPORTED;
+	}
+	CK(cudaSetDevice(ctx->device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+	int maxh = 1, maxv = 1;
+	for (int c = 0; c < nc; c++) {
+		if (img->comp[c].h_samp < 1 || img->comp[c].v_samp < 1 || !img->comp[c].coef) return JPEGQS_ERR_ARG;
+		if (img->comp[c].h_samp > maxh) maxh = img->comp[c].h_samp;
+		if (img->comp[c].v_samp > maxv) maxv = img->comp[c].v_samp;
+	}
+	size_t bytes = 0, rgb_bytes = (size_t)img->image_width * img->image_height * 3;
+	for (int c = 0; c < nc; c++) {
+		size_t cb = (size_t)img->comp[c].wblk * img->comp[c].hblk * 128;
+		if (!on_device) bytes += align256(cb);
+		bytes += align256(QS_PLANE_BYTES(img->comp[c].wblk, img->comp[c].hblk));
+	}
+	if (!on_device) bytes += align256(rgb_bytes);
+	if (arena_reserve(ctx, bytes + 4096)) return JPEGQS_ERR_CUDA;
+	if (quant_reserve(ctx, nc)) return JPEGQS_ERR_CUDA;
+	std::vector<QsJob> jobs[2]; std::vector<QsQuantDev> q(nc);
+	const uint8_t *planes[3]; int strides[3], cw[3], ch[3], hs[3], vs[3];
+	for (int c = 0; c < nc; c++) {
+		const jpegqs_cuda_comp *cc = &img->comp[c];
+		size_t cb = (size_t)cc->wblk * cc->hblk * 128; int val;
+		int16_t *cd = cc->coef;
+		if (!on_device) {
+			cd = (int16_t *)arena_take(ctx, cb);
+			if (cb) CK(cudaMemcpyAsync(cd, cc->coef, cb, cudaMemcpyHostToDevice, st));
+		}
+		uint8_t *pl = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(cc->wblk, cc->hblk));
+		quant_prepare(cc->quant, &q[c], &val);
+		QsJob j; memset(&j, 0, sizeof(j));
+		j.coef = cd; j.plane = pl; j.quant = ctx->quant_dev + c;
+		j.wblk = cc->wblk; j.hblk = cc->hblk; j.stride = QS_PLANE_STRIDE(cc->wblk); j.nblocks = cc->wblk * cc->hblk;
+		j.top_edge = j.bottom_edge = 1;
+		/* tables that are not all ones: the coefficients are still quantized (plain decode).
+		 * NOTE: on_device coefficients are de-quantized in place in that case. */
+		jobs[cc->has_qtbl && val > 1 ? 1 : 0].push_back(j);
+		planes[c] = pl; strides[c] = j.stride;
+		cw[c] = (int)((img->image_width * (unsigned)cc->h_samp + maxh - 1) / maxh);
+		ch[c] = (int)((img->image_height * (unsigned)cc->v_samp + maxv - 1) / maxv);
+		hs[c] = maxh / cc->h_samp; vs[c] = maxv / cc->v_samp;
+	}
+	CK(cudaMemcpyAsync(ctx->quant_dev, q.data(), nc * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
+	ctx->jobs_cache[0].clear(); ctx->jobs_cache[1].clear();
+	for (int m = 0; m < 2; m++) {
+		if (jobs[m].empty()) continue;
+		const QsJob *jd; int tiles;
+		if (upload_jobs(ctx, m, jobs[m], st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+		CK(cudaMemsetAsync(ctx->flags_dev, 0, jobs[m].size() * sizeof(int), st));
+		CK(qs_launch_idct_pass(jd, (int)jobs[m].size(), tiles, m ? QS_IDCT_DEQUANT : 0, ctx->flags_dev, st));
+	}
+	uint8_t *out = on_device ? rgb : (uint8_t *)arena_take(ctx, rgb_bytes);
+	CK(qs_launch_render_rgb(planes, strides, cw, ch, hs, vs, nc, (int)img->image_width, (int)img->image_height,
+			img->is_ycbcr, out, st));
+	if (!on_device) CK(cudaMemcpyAsync(rgb, out, rgb_bytes, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	return 0;
+}

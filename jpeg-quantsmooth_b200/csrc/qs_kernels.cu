@@ -1072,3 +1072,80 @@ cudaError_t qs_launch_fdct_plane(const uint8_t *px, int pstride, int16_t *coef, 
 	qs_fdct_plane_kernel<<<(n + 127) / 128, 128, 0, st>>>(px, pstride, coef, W, n);
 	return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Render to interleaved RGB: what libjpeg does after the reference's
+ * jpegqs_start_decompress hands the smoothed coefficients back (quantsmooth.h:2861-2904):
+ * islow IDCT (already in the planes), "fancy" triangle up-sampling of sub-sampled chroma
+ * (libjpeg jdsample.c h2v1_fancy_upsample / h2v2_fancy_upsample), YCbCr -> RGB with the
+ * fixed-point tables of jdcolor.c.  All integer, restated from the published algorithms;
+ * parity is checked against Pillow's libjpeg-turbo decode of the same file.
+ * One thread per output pixel.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+	const uint8_t *plane[3];
+	int stride[3];
+	int cw[3], ch[3];        /* real (not block padded) component size: libjpeg downsampled_width/height */
+	int hs[3], vs[3];        /* expansion factors max_samp / samp of each component */
+	int ncomp, width, height, ycc;
+} QsRenderArgs;
+
+__device__ __forceinline__ int qs_plane_px(const uint8_t *p, int stride, int x, int y) {
+	return p[(size_t)(y + 1) * stride + QS_PLANE_PAD + x];
+}
+
+/* one up-sampled sample of component c at output pixel (ox, oy) */
+__device__ __forceinline__ int qs_upsampled(const QsRenderArgs &a, int c, int ox, int oy) {
+	const uint8_t *p = a.plane[c]; int st = a.stride[c], hs = a.hs[c], vs = a.vs[c], cw = a.cw[c], ch = a.ch[c];
+	if (hs == 1 && vs == 1) return qs_plane_px(p, st, ox, oy);
+	if (hs == 2 && vs == 1 && cw > 2) {                 /* h2v1_fancy_upsample */
+		int x = ox >> 1, v = qs_plane_px(p, st, x, oy);
+		if (ox & 1) return x == cw - 1 ? v : (v * 3 + qs_plane_px(p, st, x + 1, oy) + 2) >> 2;
+		return x == 0 ? v : (v * 3 + qs_plane_px(p, st, x - 1, oy) + 1) >> 2;
+	}
+	if (hs == 2 && vs == 2 && cw > 2) {                 /* h2v2_fancy_upsample */
+		int x = ox >> 1, y = oy >> 1;
+		int y1 = (oy & 1) ? min(y + 1, ch - 1) : max(y - 1, 0);   /* nearer neighbour row, edge replicated */
+		int cur = qs_plane_px(p, st, x, y) * 3 + qs_plane_px(p, st, x, y1);
+		if (ox & 1) {
+			if (x == cw - 1) return (cur * 4 + 7) >> 4;
+			return (cur * 3 + qs_plane_px(p, st, x + 1, y) * 3 + qs_plane_px(p, st, x + 1, y1) + 7) >> 4;
+		}
+		if (x == 0) return (cur * 4 + 8) >> 4;
+		return (cur * 3 + qs_plane_px(p, st, x - 1, y) * 3 + qs_plane_px(p, st, x - 1, y1) + 8) >> 4;
+	}
+	if (hs == 1 && vs == 2) {                           /* h1v2_fancy_upsample (libjpeg-turbo >= 2.0) */
+		int y = oy >> 1, y1 = (oy & 1) ? min(y + 1, ch - 1) : max(y - 1, 0);
+		return (qs_plane_px(p, st, ox, y) * 3 + qs_plane_px(p, st, ox, y1) + ((oy & 1) ? 2 : 1)) >> 2;
+	}
+	return qs_plane_px(p, st, min(ox / hs, cw - 1), min(oy / vs, ch - 1));   /* box replication (int_upsample) */
+}
+
+__global__ void qs_render_rgb_kernel(QsRenderArgs a, uint8_t *__restrict__ rgb) {
+	int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+	if (ox >= a.width || oy >= a.height) return;
+	uint8_t *o = rgb + ((size_t)oy * a.width + ox) * 3;
+	int y = qs_upsampled(a, 0, ox, oy);
+	if (a.ncomp < 3) { o[0] = o[1] = o[2] = (uint8_t)y; return; }
+	int c1 = qs_upsampled(a, 1, ox, oy), c2 = qs_upsampled(a, 2, ox, oy);
+	if (!a.ycc) { o[0] = (uint8_t)y; o[1] = (uint8_t)c1; o[2] = (uint8_t)c2; return; }
+	/* jdcolor.c build_ycc_rgb_table / ycc_rgb_convert, SCALEBITS 16 */
+	int cb = c1 - 128, cr = c2 - 128;
+	int r = y + ((91881 * cr + 32768) >> 16);
+	int g = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+	int b = y + ((116130 * cb + 32768) >> 16);
+	o[0] = (uint8_t)min(max(r, 0), 255); o[1] = (uint8_t)min(max(g, 0), 255); o[2] = (uint8_t)min(max(b, 0), 255);
+}
+
+cudaError_t qs_launch_render_rgb(const uint8_t *const *planes, const int *strides, const int *cw, const int *ch,
+		const int *hs, const int *vs, int ncomp, int width, int height, int ycc, uint8_t *rgb, cudaStream_t st) {
+	QsRenderArgs a;
+	for (int c = 0; c < 3; c++) {
+		int k = c < ncomp ? c : 0;
+		a.plane[c] = planes[k]; a.stride[c] = strides[k]; a.cw[c] = cw[k]; a.ch[c] = ch[k]; a.hs[c] = hs[k]; a.vs[c] = vs[k];
+	}
+	a.ncomp = ncomp; a.width = width; a.height = height; a.ycc = ycc;
+	dim3 blk(32, 8), grd((width + 31) / 32, (height + 7) / 8);
+	qs_render_rgb_kernel<<<grd, blk, 0, st>>>(a, rgb);
+	return cudaGetLastError();
+}

@@ -93,6 +93,7 @@ def load():
     lib.jpegqs_cuda_pass_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                               C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                               C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.jpegqs_cuda_render_rgb.argtypes = [C.c_void_p, C.POINTER(_Image), C.c_int, C.c_void_p, C.c_void_p]
     lib.jpegqs_cuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.jpegqs_cuda_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                              C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -246,6 +247,21 @@ class QsContext:
                 c.h_samp = c.v_samp = 1
             if c.quant is not None:
                 c.quant = np.array(list(ci.comp[i].quant), dtype=np.uint16)
+
+    def render_rgb(self, image: CoefImage) -> np.ndarray:
+        """Decode a coefficient image (smoothed, or still quantized) to RGB [H, W, 3] uint8 the way
+        libjpeg would (islow IDCT, fancy up-sampling, fixed-point YCbCr->RGB)."""
+        ptrs = []
+        keep = []
+        for c in image.comps:
+            a = np.ascontiguousarray(c.coef, dtype=np.int16)
+            keep.append(a)
+            ptrs.append(a.ctypes.data)
+        ci = _Image()
+        _fill_image(ci, image, ptrs, [])
+        out = np.zeros((image.height, image.width, 3), dtype=np.uint8)
+        self._check(self.lib.jpegqs_cuda_render_rgb(self.h, C.byref(ci), 0, out.ctypes.data, None))
+        return out
 
     def run_batch_host(self, images: List[CoefImage], flags: int, niter: int):
         outs = [im.clone() for im in images]

@@ -136,3 +136,29 @@ def test_cuda_tool_writes_the_reference_tools_bytes(jpegs, tmp_path, name, args)
     assert r2.returncode == 0, r2.stderr
     assert open(a, "rb").read() == open(b, "rb").read()
     PIL.open(a).load()                      # and it is a decodable JPEG
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [f[0] for f in FILES])
+def test_device_decode_equals_libjpeg_turbo(jpegs, tmp_path, name):
+    """--ppm with -n 0 is a plain decoder: islow IDCT + fancy up-sampling + YCbCr->RGB on the
+    device must reproduce Pillow's libjpeg-turbo decode of the same file exactly."""
+    out = str(tmp_path / "o.ppm")
+    r = subprocess.run([EXE, "-n", "0", "-i", "0", "--ppm", jpegs[name], out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = np.asarray(PIL.open(out))
+    want = np.asarray(PIL.open(jpegs[name]))
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), f"max diff {np.abs(got.astype(int) - want.astype(int)).max()}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,args", [("base420", ["-q", "3"]), ("prog420", ["-q", "6"]), ("gray", ["-q", "4"]),
+                                       ("opt422", ["-q", "5", "-n", "2"])])
+def test_smoothed_pixels_equal_decoding_the_smoothed_file(jpegs, tmp_path, name, args):
+    """jpegqs_start_decompress semantics (quantsmooth.h:2880-2904): the pixels libjpeg would
+    deliver for the smoothed coefficients = decoding the transcoded file."""
+    ppm, jpg = str(tmp_path / "o.ppm"), str(tmp_path / "o.jpg")
+    assert subprocess.run([EXE, "-i", "0"] + args + ["--ppm", jpegs[name], ppm]).returncode == 0
+    assert subprocess.run([EXE, "-i", "0"] + args + [jpegs[name], jpg]).returncode == 0
+    assert np.array_equal(np.asarray(PIL.open(ppm)), np.asarray(PIL.open(jpg)))
