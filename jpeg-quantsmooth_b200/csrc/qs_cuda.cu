@@ -695,9 +695,18 @@ extern "C" int jpegqs_cuda_run_device(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *i
 
 extern "C" int jpegqs_cuda_run_batch(jpegqs_cuda_ctx *ctx, int nimages, jpegqs_cuda_image *imgs, int flags,
 		int niter, int on_device, int *ret, void *stream) {
-	if (!ctx) return JPEGQS_ERR_ARG;
-	return run_images(ctx, nimages, imgs, flags, niter, 0, NULL, NULL, on_device != 0, ret,
-			stream ? (cudaStream_t)stream : ctx->stream);
+	if (!ctx || nimages < 0) return JPEGQS_ERR_ARG;
+	/* a launch carries at most QS_MAX_JOBS components: larger batches run as several sub-batches */
+	for (int i = 0; i < nimages; ) {
+		int n = 0, jobs = 0;
+		while (i + n < nimages && imgs[i + n].ncomp > 0 && jobs + imgs[i + n].ncomp <= QS_MAX_JOBS) jobs += imgs[i + n++].ncomp;
+		if (!n) return JPEGQS_ERR_ARG;
+		int rc = run_images(ctx, n, imgs + i, flags, niter, 0, NULL, NULL, on_device != 0, ret ? ret + i : NULL,
+				stream ? (cudaStream_t)stream : ctx->stream);
+		if (rc) return rc;
+		i += n;
+	}
+	return 0;
 }
 
 /* ------------------------------------------------------------------------------------------

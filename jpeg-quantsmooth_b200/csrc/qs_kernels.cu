@@ -982,13 +982,11 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
 static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
+	(void)gs;    /* 2-3 independent groups per sub-partition were tried and rejected (profiles/README.md) */
 	if (wps == 6) {
-		if (gs == 3) return diag ? QS_V(true, 2, 6, 3) : QS_V(false, 2, 6, 3);
-		if (gs == 2) return diag ? QS_V(true, 2, 6, 2) : QS_V(false, 2, 6, 2);
 		if (diag) return sync == 2 ? QS_V(true, 2, 6, 1) : QS_V(true, 1, 6, 1);
 		return sync == 2 ? QS_V(false, 2, 6, 1) : QS_V(false, 1, 6, 1);
 	}
-	if (gs == 2) return diag ? QS_V(true, 2, 4, 2) : QS_V(false, 2, 4, 2);
 	if (diag) return sync == 2 ? QS_V(true, 2, 4, 1) : sync ? QS_V(true, 1, 4, 1) : QS_V(true, 0, 4, 1);
 	return sync == 2 ? QS_V(false, 2, 4, 1) : sync ? QS_V(false, 1, 4, 1) : QS_V(false, 0, 4, 1);
 }

@@ -110,6 +110,17 @@ def test_batch_entry_point(ctx):
             assert r == wr and ol.images_equal(o, want)
 
 
+def test_batch_larger_than_one_launch(ctx):
+    """More components than one launch carries (QS_MAX_JOBS = 1024): split into sub-batches."""
+    base = [qs.synth.make_image(48, 32, "420", seed=s) for s in range(4)]
+    ims = [base[i % 4] for i in range(400)]
+    rets, outs = ctx.run_batch_host(ims, 0, 1)
+    wants = [ol.run_oracle(b, 0, 1)[1] for b in base]
+    assert not any(rets)
+    for i, o in enumerate(outs):
+        assert ol.images_equal(o, wants[i % 4])
+
+
 def _run_slabs_one_gpu(ctx, im, flags, niter, nshards):
     """Emulates the multi-GPU schedule on one device: slabs are separate job sets, halo rows
     are copied by hand between the IDCT and smoothing passes."""
