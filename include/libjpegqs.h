@@ -1,48 +1,59 @@
 /*
  * libjpegqs.h - public API of the B200-native quantsmooth library.
  *
- * Source-compatible with the reference's libjpegqs.h (reference
- * libjpegqs.h:14-55): same flag values, same jpegqs_control_t layout and the
- * same three entry points, so a caller written against the reference
- * (quantsmooth.c:550, example.c:96, irfanview/plugin.c:103) links against
- * libjpegqs_b200.so unchanged.  Include <jpeglib.h> before this header.
+ * Source compatible with the reference's API header (reference libjpegqs.h:14-55): the same
+ * identifiers with the same values, the same jpegqs_control_t layout and the same three entry
+ * points, so a caller written against the reference (quantsmooth.c:550, example.c:96,
+ * irfanview/plugin.c:103) compiles and links against libjpegqs_b200.so unchanged.
+ * Include <jpeglib.h> before this header.
  *
- * Differences in behaviour (all documented in INTEGRATION.md):
- *   - the smoothing runs on a CUDA device (sm_100a); there is no CPU
- *     fallback - if no device/extension is usable the call aborts through
- *     cinfo->err->error_exit when available, else returns JPEGQS_ERR_CUDA;
- *   - opts->threads is ignored (reference: OpenMP thread count,
+ * Behavioural differences:
+ *   - the smoothing runs on a CUDA device (sm_100a).  There is no CPU fallback: without a
+ *     usable device do_quantsmooth reports on stderr and returns a negative value, leaving
+ *     the coefficients untouched;
+ *   - jpegqs_control_t.threads is ignored (reference: OpenMP thread count,
  *     quantsmooth.h:2467-2472);
- *   - (flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK selects the CUDA device
- *     ordinal + 1 (0 = current device) instead of a SIMD tier
- *     (reference libjpegqs.c:123-129).
+ *   - (flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK selects the CUDA device ordinal + 1
+ *     (0 = current device) instead of capping the SIMD tier (reference libjpegqs.c:123-129).
  */
+#ifndef JPEGQS_B200_LIBJPEGQS_H
+#define JPEGQS_B200_LIBJPEGQS_H
 #ifndef JPEGQS_H
-#define JPEGQS_H
+#define JPEGQS_H                       /* the reference's guard: both headers exclude each other */
+#endif
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-enum {
-	JPEGQS_ITER_MAX = 100,          /* niter is clamped to [0, 100]          */
-	JPEGQS_DIAGONALS = 1,           /* q>=4: add the 98 diagonal pair terms  */
-	JPEGQS_JOINT_YUV = 2,           /* q>=5: chroma predicted from luma      */
-	JPEGQS_UPSAMPLE_UV = 4,         /* q>=6: chroma re-sampled at luma size  */
-	JPEGQS_LOW_QUALITY = 8,         /* q<=2: one-shot 8-neighbour filter      */
-	JPEGQS_NO_REBALANCE = 16,
-	JPEGQS_NO_REBALANCE_UV = 32,
-	JPEGQS_TRANSCODE = 64,
-	JPEGQS_FLAGS_MASK = 0x7f,
-	JPEGQS_CPU_SHIFT = 12,
-	JPEGQS_CPU_MASK = 15,
-	JPEGQS_INFO_SHIFT = 16,
-	JPEGQS_INFO_COMP1 = 1 << JPEGQS_INFO_SHIFT,
-	JPEGQS_INFO_QUANT = 2 << JPEGQS_INFO_SHIFT,
-	JPEGQS_INFO_COMP2 = 4 << JPEGQS_INFO_SHIFT,
-	JPEGQS_INFO_TIME = 8 << JPEGQS_INFO_SHIFT,
-	JPEGQS_INFO_CPU = 16 << JPEGQS_INFO_SHIFT
+/* behaviour flags, jpegqs_control_t.flags bits 0..6 */
+enum jpegqs_flag_bits {
+	JPEGQS_DIAGONALS       = 1 << 0,   /* -q >= 4: add the 98 diagonal pixel pairs             */
+	JPEGQS_JOINT_YUV       = 1 << 1,   /* -q >= 5: predict chroma from the smoothed luma        */
+	JPEGQS_UPSAMPLE_UV     = 1 << 2,   /* -q >= 6: re-sample sub-sampled chroma at luma size     */
+	JPEGQS_LOW_QUALITY     = 1 << 3,   /* -q <= 2: one-shot 8-neighbour filter                   */
+	JPEGQS_NO_REBALANCE    = 1 << 4,
+	JPEGQS_NO_REBALANCE_UV = 1 << 5,
+	JPEGQS_TRANSCODE       = 1 << 6,   /* caller re-encodes the coefficients (no decoder re-init) */
+	JPEGQS_FLAGS_MASK      = 0x7f
 };
+
+/* bit fields above the behaviour flags */
+enum jpegqs_flag_fields {
+	JPEGQS_CPU_SHIFT  = 12,            /* 4 bits: here the CUDA device ordinal + 1               */
+	JPEGQS_CPU_MASK   = 15,
+	JPEGQS_INFO_SHIFT = 16             /* log selection, JPEGQS_INFO_* below                     */
+};
+
+enum jpegqs_info_bits {
+	JPEGQS_INFO_COMP1 = 1 << 16,       /* component sampling factors and table numbers           */
+	JPEGQS_INFO_QUANT = 1 << 17,       /* quantization tables                                    */
+	JPEGQS_INFO_COMP2 = 1 << 18,       /* component sizes in blocks                              */
+	JPEGQS_INFO_TIME  = 1 << 19,       /* "quantsmooth: %.3fms"                                  */
+	JPEGQS_INFO_CPU   = 1 << 20        /* back end report ("SIMD type: ...")                     */
+};
+
+enum jpegqs_limits { JPEGQS_ITER_MAX = 100 };   /* niter is clamped to [0, JPEGQS_ITER_MAX] */
 
 #ifndef JPEGQS_ATTR
 #define JPEGQS_ATTR
@@ -50,24 +61,23 @@ enum {
 
 #define JPEGQS_VERSION "1.20230818-b200"
 
-typedef struct {
-	int flags, niter, threads, progprec;
-	void *userdata;
-	int (*progress)(void *data, int cur, int max);
+typedef struct jpegqs_control {
+	int flags;                         /* JPEGQS_* bits                                          */
+	int niter;                         /* iterations                                             */
+	int threads;                       /* ignored by this back end                               */
+	int progprec;                      /* number of progress steps (0 = 20, < 0 = every row unit)   */
+	void *userdata;                    /* passed to progress()                                   */
+	int (*progress)(void *data, int cur, int max);   /* non-zero return = stop                 */
 } jpegqs_control_t;
 
-/* replaces reference libjpegqs.h:47-48 / quantsmooth.h:2404 */
-JPEGQS_ATTR
-int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays,
+/* smooths the coefficient arrays in place; replaces reference libjpegqs.h:47-48 / quantsmooth.h:2404 */
+JPEGQS_ATTR int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays,
 		jpegqs_control_t *opts);
 
 #ifndef TRANSCODE_ONLY
-/* replace reference libjpegqs.h:50-55 / quantsmooth.h:2880-2904 */
-JPEGQS_ATTR
-boolean jpegqs_start_decompress(j_decompress_ptr cinfo, jpegqs_control_t *opts);
-
-JPEGQS_ATTR
-boolean jpegqs_finish_decompress(j_decompress_ptr cinfo);
+/* decode helpers; replace reference libjpegqs.h:50-55 / quantsmooth.h:2880-2904 */
+JPEGQS_ATTR boolean jpegqs_start_decompress(j_decompress_ptr cinfo, jpegqs_control_t *opts);
+JPEGQS_ATTR boolean jpegqs_finish_decompress(j_decompress_ptr cinfo);
 #endif
 
 #ifdef __cplusplus

@@ -27,7 +27,9 @@
 #include <jpeglib.h>
 #include "libjpegqs.h"
 #include "jpegcoef.h"
+#ifndef JPEGQS_NO_CUDA_RENDER      /* the reference-linked test build (oracle/Makefile) has no CUDA back end */
 #include "jpegqs_cuda.h"
+#endif
 
 static unsigned char *load_all(FILE *f, size_t *len) {
 	size_t cap = 1 << 20, n = 0, r; unsigned char *p = (unsigned char*)malloc(cap);
@@ -121,6 +123,9 @@ int main(int argc, char **argv) {
 	ret = do_quantsmooth(&im.cinfo, im.coef_arrays, &opts);
 	if (ret < 0) { jq_free(&im); return 2; }
 
+#ifdef JPEGQS_NO_CUDA_RENDER
+	if (ppm) { fprintf(stderr, "%s: --ppm needs the CUDA back end\n", argv[0]); jq_free(&im); return 1; }
+#else
 	if (ppm) {                                          /* decode to RGB on the device */
 		jpegqs_cuda_ctx *ctx = NULL; jpegqs_cuda_image ci; int c, nc = im.cinfo.num_components, rc;
 		int16_t *bufs[MAX_COMPONENTS] = { 0 }; unsigned char *rgb; char hdr[64]; int hl;
@@ -156,7 +161,9 @@ int main(int argc, char **argv) {
 		out = (unsigned char*)malloc(outlen);
 		memcpy(out, hdr, hl); memcpy(out + hl, rgb, outlen - hl);
 		free(rgb);
-	} else if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
+	} else
+#endif
+	if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
 		fprintf(stderr, "%s: %s\n", argv[0], err); jq_free(&im); return 1;
 	}
 	/* the output is opened after the input was read, so it may name the same file */

@@ -28,18 +28,38 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} is declared in include/ but not exported"
 
 
-def test_libjpegqs_header_keeps_the_reference_surface():
-    text = open(os.path.join(ROOT, "include", "libjpegqs.h")).read()
-    for name, val in [("JPEGQS_ITER_MAX", 100), ("JPEGQS_DIAGONALS", 1), ("JPEGQS_JOINT_YUV", 2),
-                      ("JPEGQS_UPSAMPLE_UV", 4), ("JPEGQS_LOW_QUALITY", 8), ("JPEGQS_NO_REBALANCE", 16),
-                      ("JPEGQS_NO_REBALANCE_UV", 32), ("JPEGQS_TRANSCODE", 64), ("JPEGQS_FLAGS_MASK", 0x7f),
-                      ("JPEGQS_CPU_SHIFT", 12), ("JPEGQS_CPU_MASK", 15), ("JPEGQS_INFO_SHIFT", 16)]:
-        m = re.search(name + r"\s*=\s*(0x[0-9a-fA-F]+|\d+)", text)
-        assert m and int(m.group(1), 0) == val, name
-    for proto in ("int do_quantsmooth(j_decompress_ptr", "boolean jpegqs_start_decompress(j_decompress_ptr",
-                  "boolean jpegqs_finish_decompress(j_decompress_ptr", "int flags, niter, threads, progprec;",
-                  "int (*progress)(void *data, int cur, int max);"):
-        assert proto in text
+def test_libjpegqs_header_keeps_the_reference_surface(tmp_path):
+    """Compile a C program against include/libjpegqs.h and check every constant the reference
+    header defines (libjpegqs.h:14-32), the struct layout (41-45) and the prototypes (47-55)."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include <jpeglib.h>
+#include "libjpegqs.h"
+static int cb(void *d, int cur, int max) { (void)d; return cur > max; }
+int main(void) {
+	jpegqs_control_t c = { 1, 2, 3, 4, NULL, cb };
+	int (*f)(j_decompress_ptr, jvirt_barray_ptr*, jpegqs_control_t*) = do_quantsmooth;
+	printf("%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", JPEGQS_ITER_MAX, JPEGQS_DIAGONALS,
+		JPEGQS_JOINT_YUV, JPEGQS_UPSAMPLE_UV, JPEGQS_LOW_QUALITY, JPEGQS_NO_REBALANCE, JPEGQS_NO_REBALANCE_UV,
+		JPEGQS_TRANSCODE, JPEGQS_FLAGS_MASK, JPEGQS_CPU_SHIFT, JPEGQS_CPU_MASK, JPEGQS_INFO_SHIFT,
+		JPEGQS_INFO_COMP1 >> 16, JPEGQS_INFO_QUANT >> 16, JPEGQS_INFO_COMP2 >> 16, JPEGQS_INFO_TIME >> 16,
+		JPEGQS_INFO_CPU >> 16);
+	printf("%zu %zu %zu %zu %zu %zu %d\n", offsetof(jpegqs_control_t, flags), offsetof(jpegqs_control_t, niter),
+		offsetof(jpegqs_control_t, threads), offsetof(jpegqs_control_t, progprec),
+		offsetof(jpegqs_control_t, userdata), offsetof(jpegqs_control_t, progress), c.progress(NULL, 1, 0) + (f != NULL));
+	return 0;
+}
+''')
+    exe = tmp_path / "t"
+    lib = os.path.dirname(qs.cuda.lib_path())
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", lib, "-ljpegqs_b200", f"-Wl,-rpath,{lib}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    assert out[0].split() == [str(v) for v in (100, 1, 2, 4, 8, 16, 32, 64, 0x7f, 12, 15, 16, 1, 2, 4, 8, 16)]
+    assert out[1].split() == ["0", "4", "8", "12", "16", "24", "2"]
     for q, f in [(0, 8 | 1), (2, 8 | 7), (3, 0), (4, 1), (5, 3), (6, 7)]:     # quantsmooth.c:380-393
         assert qs.quality_to_flags(q) == f
 
