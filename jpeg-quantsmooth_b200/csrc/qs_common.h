@@ -71,4 +71,16 @@ typedef struct {
 } QsChunk;
 #define QS_MAX_CHUNKS 64
 
+/* Pair schedule (packed FP32x2 path): every coefficient of an anti-diagonal belongs to one
+ * pair slot (two coefficients that advance through the same terms in the two lanes of
+ * FMUL2/FADD2; a coefficient without partner gets an all-zero dummy lane).  Each slot owns an
+ * interleaved weight table float[TS][2]; sections a lane does not have (row-0 coefficients:
+ * vertical, column-0 coefficients: horizontal) are simply zero there, which makes those terms
+ * exact no-ops.  A chunk is 1 or 2 pair slots sharing the pixel work. */
+typedef struct {
+	uint8_t np, first, slot[2];
+	uint8_t idx[4];                 /* natural coefficient index per lane, 0xFF = dummy lane */
+} QsChunk2;
+#define QS_MAX_SLOTS 40
+
 #endif

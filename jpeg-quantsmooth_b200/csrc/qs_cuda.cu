@@ -105,6 +105,49 @@ static int build_chunks(QsChunk *ch, int maxn) {
 	return n;
 }
 
+/* pair schedule + interleaved pair tables of the packed FP32x2 path (qs_common.h QsChunk2):
+ * per anti-diagonal the two edge coefficients form one pair, the others pair up in order, a
+ * left-over coefficient gets a dummy lane.  out_tab: [nslots][size][2] floats. */
+static int build_pairs(QsChunk2 *ch, int *nslots_out, int maxpairs, uint8_t lanes[][2]) {
+	int n = 0, ns = 0;
+	for (int s = 14; s >= 1; s--) {
+		int list[8], nl = 0;
+		if (s <= 7) { list[nl++] = s; list[nl++] = s * 8; }       /* row-0 and column-0 coefficient */
+		for (int u = 1; u < 8; u++) { int v = s - u; if (v >= 1 && v <= 7) list[nl++] = v * 8 + u; }
+		int npairs = (nl + 1) / 2; bool first = true;
+		for (int p0 = 0; p0 < npairs; p0 += maxpairs) {
+			QsChunk2 c; memset(&c, 0xFF, sizeof(c));
+			c.np = (uint8_t)((npairs - p0) < maxpairs ? (npairs - p0) : maxpairs);
+			c.first = first; first = false;
+			for (int k = 0; k < c.np; k++) {
+				int a = list[2 * (p0 + k)], b = 2 * (p0 + k) + 1 < nl ? list[2 * (p0 + k) + 1] : 0xFF;
+				c.slot[k] = (uint8_t)ns; c.idx[2 * k] = (uint8_t)a; c.idx[2 * k + 1] = (uint8_t)b;
+				lanes[ns][0] = (uint8_t)a; lanes[ns][1] = (uint8_t)b; ns++;
+			}
+			ch[n++] = c;
+		}
+	}
+	*nslots_out = ns;
+	return n;
+}
+
+static void build_pair_tables(int flags, const uint8_t lanes[][2], int nslots, float prescale, float *out) {
+	const int size = (flags & QS_DIAGONALS) ? QS_TAB_DIAG : QS_TAB_PLAIN;
+	std::vector<float> t(64 * size);
+	build_tables(flags, t.data(), prescale);
+	for (int sl = 0; sl < nslots; sl++) for (int h = 0; h < 2; h++) {
+		int i = lanes[sl][h];
+		for (int p = 0; p < size; p++) {
+			float v = i < 64 ? t[i * size + p] : 0.0f;
+			/* the reference skips these sections (quantsmooth.h:1527, 1531); a zero weight makes
+			 * the term an exact no-op (adds +-0 to a2 and +0 to a3) */
+			if (i < 64 && (i & 7) == 0 && p < 64) v = 0.0f;
+			if (i < 64 && i <= 7 && p >= 96 && p < 160) v = 0.0f;
+			out[((size_t)sl * size + p) * 2 + h] = v;
+		}
+	}
+}
+
 /* ------------------------------------------------------------------------------------------ */
 struct jpegqs_cuda_ctx {
 	int device, num_sms;
@@ -113,6 +156,7 @@ struct jpegqs_cuda_ctx {
 	cudaStream_t copy_stream;              /* H2D / D2H of the host entry points, overlapped with compute */
 	std::vector<cudaEvent_t> sync_ev;      /* per group: coefficients uploaded / group finished */
 	float *tab_plain, *tab_diag;
+	float *tab2_plain, *tab2_diag; int nslots2;   /* pair tables of the FP32x2 path */
 	QsQuantDev *quant_dev; int quant_cap;
 	QsJob *jobs_dev;                       /* two slots of QS_MAX_JOBS */
 	std::vector<QsJob> jobs_cache[2];
@@ -123,7 +167,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
-	int tune_sync, tune_maxn, tune_wpg, tune_gs;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
+	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -159,7 +203,7 @@ extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
 	if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (cudaEvent_t e : ctx->sync_ev) cudaEventDestroy(e);
-	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->quant_dev);
+	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->tab2_plain); cudaFree(ctx->tab2_diag); cudaFree(ctx->quant_dev);
 	cudaFree(ctx->jobs_dev); cudaFree(ctx->flags_dev); cudaFree(ctx->arena);
 	if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -188,11 +232,12 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	memset(ctx->err, 0, sizeof(ctx->err));
 	ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
 	snprintf(ctx->devname, sizeof(ctx->devname), "%s", prop.name);
+	ctx->tab2_plain = ctx->tab2_diag = NULL; ctx->nslots2 = 0;
 	ctx->stream = NULL; ctx->copy_stream = NULL; ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1;
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_x2 = 1;
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -209,6 +254,19 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 		QsChunk ch[QS_MAX_CHUNKS];
 		int n = build_chunks(ch, 4);
 		CK(qs_set_chunks(ch, n));
+		{
+			QsChunk2 ch2[QS_MAX_CHUNKS]; uint8_t lanes[QS_MAX_SLOTS][2]; int ns = 0;
+			int n2 = build_pairs(ch2, &ns, 2, lanes);
+			CK(qs_set_chunks2(ch2, n2, ns));
+			ctx->nslots2 = ns;
+			std::vector<float> t2((size_t)ns * QS_TAB_DIAG * 2);
+			build_pair_tables(0, lanes, ns, pre, t2.data());
+			CK(cudaMalloc(&ctx->tab2_plain, (size_t)ns * QS_TAB_PLAIN * 2 * sizeof(float)));
+			CK(cudaMemcpy(ctx->tab2_plain, t2.data(), (size_t)ns * QS_TAB_PLAIN * 2 * sizeof(float), cudaMemcpyHostToDevice));
+			build_pair_tables(QS_DIAGONALS, lanes, ns, pre, t2.data());
+			CK(cudaMalloc(&ctx->tab2_diag, (size_t)ns * QS_TAB_DIAG * 2 * sizeof(float)));
+			CK(cudaMemcpy(ctx->tab2_diag, t2.data(), (size_t)ns * QS_TAB_DIAG * 2 * sizeof(float), cudaMemcpyHostToDevice));
+		}
 		CK(qs_smooth_configure());
 		CK(cudaMalloc(&ctx->jobs_dev, 2 * QS_MAX_JOBS * sizeof(QsJob)));
 		CK(cudaMalloc(&ctx->flags_dev, (QS_MAX_JOBS + 1) * sizeof(int)));
@@ -316,6 +374,7 @@ extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->p
 extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) {
 	if (!ctx) return JPEGQS_ERR_ARG;
 	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 1 : value; return 0; }
+	if (key == 4) { ctx->tune_x2 = value ? 1 : 0; return 0; }
 	if (key == 3) { ctx->tune_gs = value < 1 || value > 3 ? 1 : value; return 0; }
 	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
 	if (key == 1) {
@@ -585,6 +644,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
 				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
 				if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, (int)jobs.size(), tiles, flags, clampv, st));
+				else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, (int)jobs.size(), tiles,
+						(flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain, ctx->nslots2, tile_counter, flags, clampv,
+						ctx->num_sms, ctx->tune_sync, st));
 				else CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 				ctx->launches++;
@@ -762,6 +824,8 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, st));
+	else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, njobs, tiles, (flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain,
+			ctx->nslots2, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, st));
 	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
 	return 0;
 }

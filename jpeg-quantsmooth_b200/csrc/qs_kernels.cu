@@ -27,6 +27,9 @@
 
 __constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
 __constant__ int c_nchunks;
+__constant__ QsChunk2 c_chunks2[QS_MAX_CHUNKS];
+__constant__ int c_nchunks2, c_nslots2;
+__constant__ unsigned long long c_one2;      /* {1.0f, 1.0f}, deliberately opaque to ptxas (see qs_add2) */
 
 /* ------------------------------------------------------------------------------------------
  * small helpers
@@ -476,9 +479,10 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
  * drift against each other, so the ALU-heavy refresh of one overlaps the FMA-heavy sums of
  * the other while the L0 instruction cache still only sees GS loop bodies. */
 #define QS_SYNC(level, wps, gs) ((level) + 16 * (wps) + 256 * (gs))
+#define QS_SYNC_X2 4096              /* packed FP32x2 pair path */
 #define QS_SYNC_LEVEL(s) ((s) & 15)
 #define QS_SYNC_WPS(s) (((s) >> 4) & 15)
-#define QS_SYNC_GS(s) ((s) >> 8)
+#define QS_SYNC_GS(s) (((s) >> 8) & 15)
 template <int SYNC>
 __device__ __forceinline__ void qs_group_sync(int grp) {
 	/* grp = barrier id | (participating threads << 8), see qs_smooth_kernel */
@@ -549,6 +553,175 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 	qs_section_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Packed FP32x2 path.  Blackwell's FMUL2 / FADD2 (PTX mul/add.rn.f32x2) perform two IEEE-RN
+ * FP32 operations per lane per issue slot at full rate (tools/ubench_f32x2.cu: 253 FP32
+ * ops/clk/SM vs 114 scalar).  Two coefficients of an anti-diagonal advance through the same
+ * pixel-difference terms in the two halves of 64-bit register pairs: per (term, pair)
+ * 2 FADD.SAT + 5 FMUL2 + 2 FADD2 = 9 issue slots instead of 16, each lane still being the
+ * reference's sequential, separately rounded sum (.rn forbids contraction into FFMA2).
+ * ------------------------------------------------------------------------------------------ */
+typedef unsigned long long qs_u64;
+__device__ __forceinline__ qs_u64 qs_pk(float lo, float hi) {
+	qs_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void qs_unpk(qs_u64 v, float &lo, float &hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ qs_u64 qs_mul2(qs_u64 a, qs_u64 b) {
+	qs_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+/* a + b, per lane, IEEE RN.  NOT written as add.rn.f32x2: ptxas 12.9 contracts a mul.rn.f32x2
+ * feeding an add.rn.f32x2 into one FFMA2 even with -fmad=false (it keeps the scalar mul.rn/add.rn
+ * pair apart), which would drop the rounding of the product.  fma(b, 1.0, a) with the 1.0 pair
+ * in a register ptxas cannot see through is exact (b*1 is exact, one rounding of the sum) and
+ * cannot be merged with the producer of b. */
+__device__ __forceinline__ qs_u64 qs_add2(qs_u64 a, qs_u64 b, qs_u64 one) {
+	qs_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(b), "l"(one), "l"(a)); return r;
+}
+
+/* CORE (quantsmooth.h:1519-1520) for the two lanes of a pair; dd = {ds, ds}, w = {w_a, w_b} */
+__device__ __forceinline__ void qs_term2(qs_u64 dd, float nad, qs_u64 w, float Rsa, float Rsb,
+		qs_u64 &a2, qs_u64 &a3, qs_u64 one) {
+	float ta, tb;
+	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(ta) : "f"(Rsa), "f"(nad));
+	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(tb) : "f"(Rsb), "f"(nad));
+	qs_u64 t = qs_pk(ta, tb);
+	t = qs_mul2(t, t);
+	qs_u64 a0 = qs_mul2(dd, t), a1 = qs_mul2(w, t);
+	a2 = qs_add2(a2, qs_mul2(a0, a1), one);
+	a3 = qs_add2(a3, qs_mul2(a1, a1), one);
+}
+
+/* all terms of one row step for NP pairs; tab[c] = pair table (float2 per term) */
+template <int NP, int NT, class Prep>
+__device__ __forceinline__ void qs_terms_row2(const float *d, const float *const *tab, int off,
+		const float *Rs, qs_u64 *a2, qs_u64 *a3, qs_u64 one, Prep prep) {
+	qs_u64 dd[8]; float nad[8];
+#pragma unroll
+	for (int x = 0; x < NT; x++) { dd[x] = qs_pk(d[x], d[x]); nad[x] = -fabsf(d[x]); }
+#pragma unroll
+	for (int c = 0; c < NP; c++) {
+		const ulonglong2 *t = (const ulonglong2 *)(tab[c] + off * 2);
+		qs_u64 w[8];
+#pragma unroll
+		for (int k = 0; k < 4; k++) { ulonglong2 v = t[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+#pragma unroll
+		for (int x = 0; x < NT; x++) qs_term2(dd[x], nad[x], w[x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
+		prep(c);
+	}
+}
+
+template <int NP>
+__device__ __forceinline__ void qs_prep_slice2(uint2 w, float *f, int c) {
+#pragma unroll
+	for (int j = 0; j < 8; j++) if (j * NP / 8 == c) f[j] = qs_px8(w, j);
+}
+
+template <int NP, bool DIAG>
+__device__ __forceinline__ void qs_pair_sections(const uint2 *pw, const float *const *tab, const float *Rs,
+		qs_u64 *a2, qs_u64 *a3) {
+	float d[8];
+	const qs_u64 one = c_one2;
+	{                                                   /* horizontal, quantsmooth.h:1527 */
+		float f[8];
+		qs_unpack8(pw[0], f);
+#pragma unroll
+		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
+#pragma unroll 1
+		for (int y = 0; y < 8; y++) {
+			uint2 wn = pw[((y + 1) & 7) * 32];
+			qs_terms_row2<NP, 7>(d, tab, y * 8, Rs, a2, a3, one, [&](int c) { qs_prep_slice2<NP>(wn, f, c); });
+#pragma unroll
+			for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
+		}
+	}
+	{                                                   /* border, quantsmooth.h:1529-1530 */
+		float fa[8], fb[8];
+		qs_unpack8(pw[0], fa); qs_unpack8(pw[10 * 32], fb);
+#pragma unroll
+		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
+#pragma unroll 1
+		for (int s = 0; s < 4; s++) {
+			int sn = (s + 1) & 3;
+			int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;
+			uint2 wa = pw[wi * 32], wb = pw[(10 + sn) * 32];
+			qs_terms_row2<NP, 8>(d, tab, 64 + s * 8, Rs, a2, a3, one,
+					[&](int c) { qs_prep_slice2<NP>(wa, fa, c); qs_prep_slice2<NP>(wb, fb, c); });
+#pragma unroll
+			for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
+		}
+	}
+	{                                                   /* vertical, quantsmooth.h:1531 */
+		float fp[8], fn[8];
+		qs_unpack8(pw[0], fn); qs_unpack8(pw[32], fp);
+#pragma unroll
+		for (int x = 0; x < 8; x++) d[x] = FS(fn[x], fp[x]);
+#pragma unroll 1
+		for (int y = 0; y < 7; y++) {
+			uint2 wn = pw[min(y + 2, 7) * 32];
+			qs_terms_row2<NP, 8>(d, tab, 96 + y * 8, Rs, a2, a3, one, [&](int c) { qs_prep_slice2<NP>(wn, fn, c); });
+#pragma unroll
+			for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
+		}
+	}
+	if (DIAG) {                                         /* diagonals, quantsmooth.h:1533-1540 */
+		float fp[8], fn[8], d1[8], d2[8];
+		qs_unpack8(pw[0], fn); qs_unpack8(pw[32], fp);
+#pragma unroll
+		for (int x = 0; x < 7; x++) { d1[x] = FS(fn[x], fp[x + 1]); d2[x] = FS(fn[x + 1], fp[x]); }
+#pragma unroll 1
+		for (int y = 0; y < 7; y++) {
+			uint2 wn = pw[min(y + 2, 7) * 32];
+			qs_u64 e1[8], e2[8];
+#pragma unroll
+			for (int x = 0; x < 7; x++) { e1[x] = qs_pk(d1[x], d1[x]); e2[x] = qs_pk(d2[x], d2[x]); }
+#pragma unroll
+			for (int c = 0; c < NP; c++) {
+				const ulonglong2 *t = (const ulonglong2 *)(tab[c] + (160 + y * 16) * 2);
+				qs_u64 w[16];
+#pragma unroll
+				for (int k = 0; k < 8; k++) { ulonglong2 v = t[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+#pragma unroll
+				for (int x = 0; x < 7; x++) {
+					qs_term2(e1[x], -fabsf(d1[x]), w[x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
+					qs_term2(e2[x], -fabsf(d2[x]), w[8 + x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
+				}
+				qs_prep_slice2<NP>(wn, fn, c);
+			}
+#pragma unroll
+			for (int x = 0; x < 7; x++) { d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]); }
+#pragma unroll
+			for (int x = 0; x < 8; x++) fp[x] = fn[x];
+		}
+	}
+}
+
+template <int NP, bool DIAG>
+__device__ __forceinline__ void qs_chunk_pairs(const QsChunk2 &ch, const float *tabs, const uint2 *pw,
+		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	const float *tab[NP]; float Rs[2 * NP]; qs_u64 a2[NP], a3[NP];
+	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+#pragma unroll
+	for (int c = 0; c < NP; c++) {
+		tab[c] = tabs + (int)ch.slot[c] * TS * 2;
+		a2[c] = 0ull; a3[c] = 0ull;
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			int i = ch.idx[2 * c + h];
+			Rs[2 * c + h] = i < 64 ? __ldg(&qd->Rs[i]) : 0.0f;
+		}
+	}
+	qs_pair_sections<NP, DIAG>(pw, tab, Rs, a2, a3);
+#pragma unroll
+	for (int c = 0; c < NP; c++) {
+		float x2a, x2b, x3a, x3b;
+		qs_unpk(a2[c], x2a, x2b); qs_unpk(a3[c], x3a, x3b);
+		if (ch.idx[2 * c] < 64) qs_coef_update(x2a, x3a, ch.idx[2 * c], qd, cs);
+		if (ch.idx[2 * c + 1] < 64) qs_coef_update(x2b, x3b, ch.idx[2 * c + 1], qd, cs);
+	}
 }
 
 /* IDCT of the lane's block from shared coefficients into the shared pixel words */
@@ -647,17 +820,19 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	extern __shared__ __align__(16) uint32_t smem[];
 	__shared__ int s_tile[16];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+	const bool X2 = (SYNC & QS_SYNC_X2) != 0;
+	const int tab_words = X2 ? c_nslots2 * 2 * TS : 64 * TS;
 	float *tabs = (float *)smem;
 	{
 		const float4 *src = (const float4 *)tables_g; float4 *dst = (float4 *)tabs;
-		for (int i = threadIdx.x; i < 64 * TS / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+		for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
 	}
 	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int NG = 4 * QS_SYNC_GS(SYNC);                /* lock-step groups in this CTA */
 	const int WPG = QS_SYNC_WPS(SYNC) / QS_SYNC_GS(SYNC);   /* warps per group, all on one sub-partition */
 	int grp = warp % NG, wig = warp / NG;
-	uint32_t *wbase = smem + 64 * TS + warp * QS_WARP_WORDS;
+	uint32_t *wbase = smem + tab_words + warp * QS_WARP_WORDS;
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
 	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
@@ -735,7 +910,18 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			pw[13 * 32] = make_uint2(r0, r1);
 		}
 
-		int nch = c_nchunks;
+		if (X2) {
+			int nch2 = c_nchunks2;
+#pragma unroll 1
+			for (int ci = 0; ci < nch2; ci++) {
+				QsChunk2 ch = c_chunks2[ci];
+				qs_group_sync<SYNC>(gsync);
+				if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+				if (ch.np == 2) qs_chunk_pairs<2, DIAG>(ch, tabs, pw, qd, cs);
+				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
+			}
+		}
+		int nch = X2 ? 0 : c_nchunks;
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
 			QsChunk ch = c_chunks[ci];
@@ -981,6 +1167,10 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
+static qs_smooth_fn qs_smooth_variant_x2(int diag, int sync) {
+	if (diag) return sync == 1 ? qs_smooth_kernel<true, QS_SYNC(1, 4, 1) + QS_SYNC_X2> : qs_smooth_kernel<true, QS_SYNC(2, 4, 1) + QS_SYNC_X2>;
+	return sync == 1 ? qs_smooth_kernel<false, QS_SYNC(1, 4, 1) + QS_SYNC_X2> : qs_smooth_kernel<false, QS_SYNC(2, 4, 1) + QS_SYNC_X2>;
+}
 static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
 	(void)gs;    /* 2-3 independent groups per sub-partition were tried and rejected (profiles/README.md) */
 	if (wps == 6) {
@@ -994,6 +1184,19 @@ static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
 size_t qs_smooth_smem_bytes(int diag, int wpg) {
 	return (size_t)64 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 + (size_t)(wpg * 4) * QS_WARP_WORDS * 4;
 }
+size_t qs_smooth_smem_bytes_x2(int diag, int nslots) {
+	return (size_t)nslots * 2 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 + (size_t)16 * QS_WARP_WORDS * 4;
+}
+cudaError_t qs_set_chunks2(const QsChunk2 *chunks, int n, int nslots) {
+	cudaError_t e = cudaMemcpyToSymbol(c_chunks2, chunks, sizeof(QsChunk2) * n);
+	if (e != cudaSuccess) return e;
+	e = cudaMemcpyToSymbol(c_nchunks2, &n, sizeof(int));
+	if (e != cudaSuccess) return e;
+	e = cudaMemcpyToSymbol(c_nslots2, &nslots, sizeof(int));
+	if (e != cudaSuccess) return e;
+	const unsigned long long one = 0x3f8000003f800000ull;
+	return cudaMemcpyToSymbol(c_one2, &one, sizeof(one));
+}
 
 cudaError_t qs_smooth_configure(void) {
 	for (int d = 0; d < 2; d++) for (int wps = 4; wps <= 6; wps += 2) for (int gs = 1; gs <= 3; gs++)
@@ -1003,7 +1206,25 @@ cudaError_t qs_smooth_configure(void) {
 					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wps));
 			if (e != cudaSuccess) return e;
 		}
+	for (int d = 0; d < 2; d++) for (int sy = 1; sy <= 2; sy++) {
+		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant_x2(d, sy),
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes_x2(d, QS_MAX_SLOTS));
+		if (e != cudaSuccess) return e;
+	}
 	return cudaSuccess;
+}
+
+cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
+		int nslots, int *tile_counter, int flags, int clamp_out, int num_sms, int sync, cudaStream_t st) {
+	if (total_tiles <= 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
+	if (e != cudaSuccess) return e;
+	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
+	int grid = (total_tiles + 15) / 16;
+	if (grid > num_sms) grid = num_sms;
+	qs_smooth_variant_x2(diag, sync == 1 ? 1 : 2)<<<grid, 512, qs_smooth_smem_bytes_x2(diag, nslots), st>>>(
+			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+	return cudaGetLastError();
 }
 
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,

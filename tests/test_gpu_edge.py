@@ -193,11 +193,12 @@ def test_tuning_variants_are_bit_identical(ctx):
             for sync in (0, 1, 2):
                 for maxn in (1, 2, 3, 4):
                     ctx.set_tuning(0, sync); ctx.set_tuning(1, maxn); ctx.set_tuning(2, wpg)
+                    ctx.set_tuning(4, maxn & 1)        # alternate scalar / packed FP32x2 path
                     _, out = ctx.do_quantsmooth(im, 1 if wpg == 4 else 0, 2)
                     ref = want if wpg == 4 else want0
                     assert ol.images_equal(out, ref), (sync, maxn, wpg)
     finally:
-        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4)
+        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4); ctx.set_tuning(4, 1)
 
 
 # ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----
