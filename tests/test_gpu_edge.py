@@ -198,7 +198,7 @@ def test_tuning_variants_are_bit_identical(ctx):
                     ref = want if wpg == 4 else want0
                     assert ol.images_equal(out, ref), (sync, maxn, wpg)
     finally:
-        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4); ctx.set_tuning(4, 1)
+        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4); ctx.set_tuning(4, 0)
 
 
 # ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----

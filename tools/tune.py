@@ -32,7 +32,7 @@ ref_hash = None
 for v in args.variants.split(","):
     f = [int(x) for x in v.split(":")]
     sync, maxn, wpg, gs = f[0], f[1], (f[2] if len(f) > 2 else 4), (f[3] if len(f) > 3 else 1)
-    x2 = f[4] if len(f) > 4 else 1
+    x2 = f[4] if len(f) > 4 else 0
     ctx.set_tuning(4, x2)
     ctx.set_tuning(0, sync)
     ctx.set_tuning(1, maxn)
