@@ -50,3 +50,25 @@ CASES = [
 def test_parity(ctx, w, h, ss, flags, niter, quality):
     im = qs.synth.make_image(w, h, ss, quality=quality)
     _check(ctx, im, flags, niter)
+
+
+def test_randomized_configurations(ctx):
+    """Seeded sweep over geometry, sub-sampling, quality (incl. extreme tables), flag combinations
+    and iteration counts - every case bit-exact against the oracle."""
+    rng = np.random.RandomState(20260923)
+    modes = ["gray", "444", "422", "420", "440"]
+    for case in range(48):
+        ss = modes[rng.randint(len(modes))]
+        w, h = int(rng.randint(8, 180)), int(rng.randint(8, 140))
+        quality = int(rng.choice([3, 10, 25, 50, 75, 90, 97, 100]))
+        flags = int(rng.randint(0, 64))          # all 6 behaviour bits
+        if (flags & 4) and ss in ("420", "422", "440"):
+            # UPSAMPLE_UV on a sub-sampled image: keep the geometry where the reference is
+            # well defined (DESIGN.md "reference quirks"): width a multiple of the MCU
+            w = max(16, w // 16 * 16)
+        niter = int(rng.randint(1, 4))
+        im = qs.synth.make_image(w, h, ss, quality=quality, seed=1000 + case, noise=int(rng.randint(0, 12)))
+        ret, out = ctx.do_quantsmooth(im, flags, niter)
+        oret, want = ol.run_oracle(im, flags, niter)
+        assert ret == oret, (case, w, h, ss, quality, flags, niter)
+        assert ol.images_equal(out, want), (case, w, h, ss, quality, flags, niter, ol.diff_count(out, want))

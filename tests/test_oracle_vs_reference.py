@@ -139,3 +139,22 @@ def test_progress_sequence_and_cancel():
     r2, o2 = ol.run_oracle(im, 0, 3, progprec=7, progress=mk(s2))
     assert r1 == r2 == 5 and s1 == s2
     assert ol.images_equal(o1, o2)
+
+
+def test_randomized_sweep_matches_reference():
+    """The same seeded sweep the GPU parity test runs (tests/test_gpu_parity.py), here pinning
+    the checker itself against the unmodified reference."""
+    rng = np.random.RandomState(20260923)
+    modes = ["gray", "444", "422", "420", "440"]
+    for case in range(48):
+        ss = modes[rng.randint(len(modes))]
+        w, h = int(rng.randint(8, 180)), int(rng.randint(8, 140))
+        quality = int(rng.choice([3, 10, 25, 50, 75, 90, 97, 100]))
+        flags = int(rng.randint(0, 64))
+        if (flags & 4) and ss in ("420", "422", "440"):
+            w = max(16, w // 16 * 16)
+        niter = int(rng.randint(1, 4))
+        im = qs.synth.make_image(w, h, ss, quality=quality, seed=1000 + case, noise=int(rng.randint(0, 12)))
+        r1, o1 = ol.run_reference(im, flags, niter)
+        r2, o2 = ol.run_oracle(im, flags, niter)
+        assert r1 == r2 and ol.images_equal(o1, o2), (case, w, h, ss, quality, flags, niter)
