@@ -824,10 +824,26 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	const int tab_words = X2 ? c_nslots2 * 2 * TS : 64 * TS;
 	float *tabs = (float *)smem;
 	{
-		const float4 *src = (const float4 *)tables_g; float4 *dst = (float4 *)tabs;
-		for (int i = threadIdx.x; i < tab_words / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+		/* Stage the weight tables (40-80 KB) with one TMA bulk copy (cp.async.bulk, UBLKCP in
+		 * SASS) completing on an mbarrier: the persistent CTA does this once, all 16 warps
+		 * wait on phase 0. */
+		__shared__ __align__(8) unsigned long long tab_bar;
+		uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tab_bar);
+		uint32_t dst = (uint32_t)__cvta_generic_to_shared(tabs);
+		uint32_t bytes = (uint32_t)tab_words * 4;
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					:: "r"(dst), "l"(tables_g), "r"(bytes), "r"(bar) : "memory");
+		}
+		asm volatile("{\n\t.reg .pred p;\n\tQS_TAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+				"@!p bra QS_TAB_WAIT;\n\t}" :: "r"(bar) : "memory");
 	}
-	__syncthreads();
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int NG = 4 * QS_SYNC_GS(SYNC);                /* lock-step groups in this CTA */
 	const int WPG = QS_SYNC_WPS(SYNC) / QS_SYNC_GS(SYNC);   /* warps per group, all on one sub-partition */
