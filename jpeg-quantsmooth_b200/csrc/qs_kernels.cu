@@ -925,6 +925,20 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			pw[12 * 32] = make_uint2(l0, l1);
 			pw[13 * 32] = make_uint2(r0, r1);
 		}
+		/* The first refresh of a block would re-render exactly what the IDCT pass just wrote to
+		 * the plane (same coefficients, deterministic IDCT), so those 64 pixels are loaded
+		 * instead of computed - unless the JOINT_YUV predictor changed the coefficients. */
+		const bool fresh_px = job->plane2 == NULL;
+		if (fresh_px) {
+			uint32_t lo[8], hi[8];
+#pragma unroll
+			for (int y = 0; y < 8; y++) {
+				uint2 v = *(const uint2 *)(img + (size_t)y * stride);
+				lo[y] = v.x; hi[y] = v.y; pw[y * 32] = v;
+			}
+			pw[8 * 32] = qs_gather_col(lo, 0);
+			pw[9 * 32] = qs_gather_col(hi, 3);
+		}
 
 		if (X2) {
 			int nch2 = c_nchunks2;
@@ -932,7 +946,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			for (int ci = 0; ci < nch2; ci++) {
 				QsChunk2 ch = c_chunks2[ci];
 				qs_group_sync<SYNC>(gsync);
-				if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+				if (ch.first && !(ci == 0 && fresh_px)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 				if (ch.np == 2) qs_chunk_pairs<2, DIAG>(ch, tabs, pw, qd, cs);
 				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
 			}
@@ -944,7 +958,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			qs_group_sync<SYNC>(gsync);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
-			if (ch.first) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+			if (ch.first && !(ci == 0 && fresh_px)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
 			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
 			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
