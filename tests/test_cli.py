@@ -162,3 +162,40 @@ def test_smoothed_pixels_equal_decoding_the_smoothed_file(jpegs, tmp_path, name,
     assert subprocess.run([EXE, "-i", "0"] + args + ["--ppm", jpegs[name], ppm]).returncode == 0
     assert subprocess.run([EXE, "-i", "0"] + args + [jpegs[name], jpg]).returncode == 0
     assert np.array_equal(np.asarray(PIL.open(ppm)), np.asarray(PIL.open(jpg)))
+
+
+def test_codec_survives_corrupt_input(jpegs, tmp_path):
+    """Mutated / truncated files must be rejected or decoded, never crash: the codec is built
+    with AddressSanitizer + UBSan (do_quantsmooth stubbed out) and fed 300 seeded mutations."""
+    exe = str(tmp_path / "jq_asan")
+    stub = tmp_path / "stub.c"
+    stub.write_text('#include <jpeglib.h>\n#include "libjpegqs.h"\n'
+                    "int do_quantsmooth(j_decompress_ptr a, jvirt_barray_ptr *b, jpegqs_control_t *c)"
+                    " { (void)a; (void)b; (void)c; return 0; }\n")
+    csrc = os.path.join(ROOT, "jpeg-quantsmooth_b200", "csrc")
+    r = subprocess.run(["/usr/bin/gcc", "-O1", "-g", "-fsanitize=address,undefined", "-DJPEGQS_NO_CUDA_RENDER",
+                        "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                        "-o", exe, os.path.join(csrc, "jpegqs.c"), os.path.join(csrc, "jpegcoef.c"), str(stub)],
+                       capture_output=True, text=True)
+    if r.returncode:
+        pytest.skip("sanitizer build unavailable: " + r.stderr[-200:])
+    rng = np.random.RandomState(7)
+    seeds = [open(jpegs[n], "rb").read() for n in ("base420", "prog420", "gray", "rst", "tinyprog")]
+    for it in range(300):
+        d = bytearray(seeds[it % len(seeds)])
+        mode = rng.randint(4)
+        if mode == 0:
+            for _ in range(rng.randint(1, 6)):
+                d[rng.randint(len(d))] = rng.randint(256)
+        elif mode == 1:
+            d = d[:rng.randint(2, len(d))]
+        elif mode == 2:
+            i = rng.randint(2, len(d) - 4)
+            d[i:i + 4] = bytes(rng.randint(0, 256, 4).tolist())
+        else:
+            i = rng.randint(len(d))
+            d = d[:i] + bytes(rng.randint(0, 256, rng.randint(1, 40)).tolist()) + d[i:]
+        f = tmp_path / "f.jpg"
+        f.write_bytes(bytes(d))
+        r = subprocess.run([exe, "-n", "0", "-i", "0", str(f), str(tmp_path / "o.jpg")], capture_output=True, timeout=60)
+        assert r.returncode in (0, 1), (it, r.returncode, r.stderr.decode()[-800:])
