@@ -77,8 +77,8 @@ class ClockSampler:
         inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= self.t1 + 0.03]
         scope = "timed region"
         if len(inside) < 2:                 # region shorter than the sampling period: use the
-            inside = [ln for (t, ln) in self.lines]     # whole loaded phase (warm-up .. end)
-            scope = "warm-up + timed region"
+            inside = [ln for (t, ln) in self.lines if self.t0 is None or t >= self.t0 - 0.5]   # loaded phase
+            scope = "timed region + end-to-end phase"
         for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -232,6 +232,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = qs.cuda.QsContext(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                   # started early: nvidia-smi needs a moment before its first line
     ctx.set_profiling(True)
 
     im, mcu_rng, mcu_total = make_workload(world, rank)
@@ -284,9 +287,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if rank == 0 and sampler.proc is not None:
+        t_wait = time.perf_counter()
+        while not sampler.lines and time.perf_counter() - t_wait < 10.0:
+            time.sleep(0.05)
     for i in range(Wm):
         step(i)
     barrier()
@@ -314,7 +318,6 @@ def main():
         passes.timing = False
         smooth_ms = sum(a.elapsed_time(b) for a, b in passes.events)
         smooth_n = len(passes.events)
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -324,38 +327,6 @@ def main():
         total_blocks = int(nb.item())
     ms_per_step = ms_total / K
     value = mpix_job / (ms_per_step / 1e3)
-
-    # ---- roofline of the dominant kernel (smoothing pass) -------------------------------
-    peak, peak_src = peaks()
-    roofline = None
-    if smooth_n:
-        bytes_per_launch = ALGO_BYTES_PER_BLOCK_ITER * nblocks_rank
-        avg_ms = smooth_ms / smooth_n
-        achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "smooth_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "qs_smooth_kernel" + ("" if world == 1 else " (rank 0's slab)"),
-                    "achieved": round(achieved, 2),
-                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
-                    "peak_source": peak_src, "avg_launch_ms": round(avg_ms, 4),
-                    "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "share_of_step": round(smooth_ms / (ms_total if ms_total else 1), 4),
-                    "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md 8d, DESIGN.md 4); "
-                            "see roofline_fp32"}
-        # FP32-issue roofline: 8 FP32 pipe instructions per (term, coefficient), 8288 terms per block
-        fp_inst = 8288 * 8 * nblocks_rank / 32.0                       # warp instructions per launch
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        issue_peak = 148 * 4 * sm_mhz * 1e6                            # warp-instr/s at 1 per SMSP per clock
-        roofline_fp32 = {"bound": "fp32-issue", "achieved": round(fp_inst / (avg_ms / 1e3) / 1e12, 4),
-                         "peak": round(issue_peak / 1e12, 4), "unit": "T warp-instr/s",
-                         "frac": round(fp_inst / (avg_ms / 1e3) / issue_peak, 4),
-                         "note": "minimum FP32-pipe instructions of the order-exact arithmetic / (148 SM x 4 "
-                                 "sub-partitions x measured SM clock)"}
-    else:
-        roofline_fp32 = None
 
     # ---- e2e: the public host-buffer call (pinned host in, pinned host out) -------------
     e2e = None
@@ -408,6 +379,40 @@ def main():
         for row in pinned:
             for p in row:
                 p.close()
+
+    clocks = sampler.stop() if rank == 0 else None     # after the e2e phase: more samples under load
+
+    # ---- roofline of the dominant kernel (smoothing pass) -------------------------------
+    peak, peak_src = peaks()
+    roofline = None
+    if smooth_n:
+        bytes_per_launch = ALGO_BYTES_PER_BLOCK_ITER * nblocks_rank
+        avg_ms = smooth_ms / smooth_n
+        achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "smooth_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "qs_smooth_kernel" + ("" if world == 1 else " (rank 0's slab)"),
+                    "achieved": round(achieved, 2),
+                    "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic,
+                    "peak_source": peak_src, "avg_launch_ms": round(avg_ms, 4),
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "share_of_step": round(smooth_ms / (ms_total if ms_total else 1), 4),
+                    "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md 8d, DESIGN.md 4); "
+                            "see roofline_fp32"}
+        # FP32-issue roofline: 8 FP32 pipe instructions per (term, coefficient), 8288 terms per block
+        fp_inst = 8288 * 8 * nblocks_rank / 32.0                       # warp instructions per launch
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6                            # warp-instr/s at 1 per SMSP per clock
+        roofline_fp32 = {"bound": "fp32-issue", "achieved": round(fp_inst / (avg_ms / 1e3) / 1e12, 4),
+                         "peak": round(issue_peak / 1e12, 4), "unit": "T warp-instr/s",
+                         "frac": round(fp_inst / (avg_ms / 1e3) / issue_peak, 4),
+                         "note": "minimum FP32-pipe instructions of the order-exact arithmetic / (148 SM x 4 "
+                                 "sub-partitions x measured SM clock)"}
+    else:
+        roofline_fp32 = None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------
     cpu = None
