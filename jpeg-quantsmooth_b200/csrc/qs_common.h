@@ -30,12 +30,27 @@
 #define QS_TAB_PLAIN 160
 #define QS_TAB_DIAG 272
 
+/* chunk schedule of the 63 AC coefficients: 14 anti-diagonal groups (reverse zig-zag,
+ * quantsmooth.h:313-322, 1403-1409) split into chunks of <= 4 coefficients that share the
+ * pixel-difference work.  type 1 = the group's two edge coefficients (row 0: no vertical
+ * terms; column 0: no horizontal terms; quantsmooth.h:1527, 1531); type 2 = a chunk whose
+ * coefficients all have the same quant value, so t = max(R-|d|,0)^2 and a0 = d*t are
+ * computed once per term and shared (3 + 5n FP ops per term instead of 8n).  The schedule is
+ * built per quant table on the host (qs_cuda.cu::build_chunks). */
+typedef struct {
+	uint8_t type, n, first, pad;
+	uint8_t idx[8];
+} QsChunk;
+#define QS_MAX_CHUNKS 64
+
 /* per-quant-table constants, device resident */
 typedef struct {
 	float Rs[64];        /* 2*q[i] * 2^-QS_SCALE_BITS  (range of quantsmooth.h:1406, scaled) */
 	uint32_t m31[64];    /* ceil(2^31 / q[i]): exact floor-division magic, see qs_orig_coef */
 	uint16_t q[64];      /* quantval with 0 -> 1 (quantsmooth.h:2508-2511) */
 	uint16_t qraw[64];   /* raw quantval, used only by the iteration-0 dequantize (2598) */
+	int32_t nchunks;     /* chunk schedule of this table */
+	QsChunk chunks[QS_MAX_CHUNKS];
 } QsQuantDev;
 
 /* one component (or one slab of block rows of it) taking part in a launch */
@@ -60,16 +75,6 @@ typedef struct {
 #define QS_IDCT_DEQUANT 1     /* multiply by qraw, range-check (iteration 0) */
 #define QS_IDCT_CLAMP 2       /* write coefficients back clamped to +-1023 (2670-2689) */
 #define QS_IDCT_NOPLANE 4     /* do not render pixels (dequantize/clamp only) */
-
-/* chunk schedule of the 63 AC coefficients: 14 anti-diagonal groups (reverse zig-zag,
- * quantsmooth.h:313-322, 1403-1409) split into chunks of <= 7 coefficients that share the
- * pixel-difference work.  type 1 = the group's two edge coefficients (row 0: no vertical
- * terms; column 0: no horizontal terms; quantsmooth.h:1527, 1531). */
-typedef struct {
-	uint8_t type, n, first, pad;
-	uint8_t idx[8];
-} QsChunk;
-#define QS_MAX_CHUNKS 64
 
 /* Pair schedule (packed FP32x2 path): every coefficient of an anti-diagonal belongs to one
  * pair slot (two coefficients that advance through the same terms in the two lanes of

@@ -74,9 +74,11 @@ static int build_tables(int flags, float *out, float prescale) {
 	return size;
 }
 
-/* chunk schedule: anti-diagonals s = 14..1 of the 8x8 coefficient grid in the reference's
- * visiting order (reverse zig-zag, quantsmooth.h:1403 + zigzag_refresh 313-322) */
-static int build_chunks(QsChunk *ch, int maxn) {
+/* chunk schedule of one quant table: anti-diagonals s = 14..1 of the 8x8 coefficient grid in the
+ * reference's visiting order (reverse zig-zag, quantsmooth.h:1403 + zigzag_refresh 313-322).
+ * Inside an anti-diagonal the coefficients are independent, so they may be regrouped: runs of
+ * equal quant value become "uniform" chunks (type 2) that share t and d*t per term. */
+static int build_chunks(QsChunk *ch, int maxn, const uint16_t *q, int uniform) {
 	int n = 0;
 	for (int s = 14; s >= 1; s--) {
 		int full[8], nf = 0; bool first = true;
@@ -92,12 +94,32 @@ static int build_chunks(QsChunk *ch, int maxn) {
 			c.idx[1] = (uint8_t)(s * 8);    /* column 0: border + vertical   (+diag) */
 			ch[n++] = c;
 		}
-		int parts = (nf + maxn - 1) / maxn, pos = 0;
+		int rest[8], nr = 0; bool used[8] = { false };
+		if (uniform && q && maxn >= 2) {
+			for (int a = 0; a < nf; a++) {
+				if (used[a]) continue;
+				int run[8], rl = 0;
+				for (int b = a; b < nf; b++) if (!used[b] && q[full[b]] == q[full[a]]) run[rl++] = b;
+				if (rl < 2) continue;
+				for (int pos = 0; pos < rl; ) {
+					int len = rl - pos > maxn ? maxn : rl - pos;
+					if (rl - pos - len == 1) len--;            /* never leave a run member alone */
+					if (len < 2) break;
+					QsChunk c; memset(&c, 0, sizeof(c));
+					c.type = 2; c.n = (uint8_t)len; c.first = first; first = false;
+					for (int k = 0; k < len; k++) { c.idx[k] = (uint8_t)full[run[pos + k]]; used[run[pos + k]] = true; }
+					pos += len;
+					ch[n++] = c;
+				}
+			}
+		}
+		for (int a = 0; a < nf; a++) if (!used[a]) rest[nr++] = full[a];
+		int parts = (nr + maxn - 1) / maxn, pos = 0;
 		for (int p = 0; p < parts; p++) {
-			int len = (nf - pos + (parts - p) - 1) / (parts - p);
+			int len = (nr - pos + (parts - p) - 1) / (parts - p);
 			QsChunk c; memset(&c, 0, sizeof(c));
 			c.type = 0; c.n = (uint8_t)len; c.first = first; first = false;
-			for (int k = 0; k < len; k++) c.idx[k] = (uint8_t)full[pos + k];
+			for (int k = 0; k < len; k++) c.idx[k] = (uint8_t)rest[pos + k];
 			pos += len;
 			ch[n++] = c;
 		}
@@ -167,7 +189,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
-	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
+	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2, tune_uni;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -237,7 +259,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -251,9 +273,6 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 		build_tables(QS_DIAGONALS, t.data(), pre);
 		CK(cudaMalloc(&ctx->tab_diag, 64 * QS_TAB_DIAG * sizeof(float)));
 		CK(cudaMemcpy(ctx->tab_diag, t.data(), 64 * QS_TAB_DIAG * sizeof(float), cudaMemcpyHostToDevice));
-		QsChunk ch[QS_MAX_CHUNKS];
-		int n = build_chunks(ch, 4);
-		CK(qs_set_chunks(ch, n));
 		{
 			QsChunk2 ch2[QS_MAX_CHUNKS]; uint8_t lanes[QS_MAX_SLOTS][2]; int ns = 0;
 			int n2 = build_pairs(ch2, &ns, 2, lanes);
@@ -297,7 +316,7 @@ static void *arena_take(jpegqs_cuda_ctx *ctx, size_t bytes) {
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out) {
+static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int maxn = 4, int uniform = 1) {
 	int val = 0;
 	for (int i = 0; i < 64; i++) {
 		int v = raw[i]; val |= v;
@@ -306,6 +325,7 @@ static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out) {
 		q->Rs[i] = (float)(2 * qq) * (1.0f / (float)(1 << QS_SCALE_BITS));
 		q->m31[i] = (uint32_t)(((1ull << 31) + (uint32_t)qq - 1) / (uint32_t)qq);
 	}
+	q->nchunks = build_chunks(q->chunks, maxn, q->q, uniform);
 	*val_out = val;
 }
 
@@ -379,16 +399,10 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
 	if (key == 1) {
 		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
-		CK(cudaSetDevice(ctx->device));
-		CK(cudaStreamSynchronize(ctx->stream));
-		CK(cudaDeviceSynchronize());
-		QsChunk ch[QS_MAX_CHUNKS * 2];
-		int n = build_chunks(ch, value);
-		if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
-		CK(qs_set_chunks(ch, n));
-		ctx->tune_maxn = value;
+		ctx->tune_maxn = value;            /* takes effect with the next quant-table upload */
 		return 0;
 	}
+	if (key == 5) { ctx->tune_uni = value ? 1 : 0; return 0; }
 	return JPEGQS_ERR_ARG;
 }
 extern "C" void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
@@ -496,7 +510,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			}
 			w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
 			w.qslot = (int)qhost.size();
-			QsQuantDev q; quant_prepare(c->quant, &q, &qval[n][ci]); qhost.push_back(q);
+			QsQuantDev q; quant_prepare(c->quant, &q, &qval[n][ci], ctx->tune_maxn, ctx->tune_uni); qhost.push_back(q);
 		}
 		bool sub = s.need_downsample && !(im->comp[0].h_samp == 1 && im->comp[0].v_samp == 1);
 		if (sub) {
@@ -781,7 +795,7 @@ static int stage_jobs(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jo
 	if (quant_reserve(ctx, QS_MAX_JOBS)) return JPEGQS_ERR_CUDA;
 	std::vector<QsQuantDev> q(njobs); std::vector<QsJob> v(njobs);
 	for (int i = 0; i < njobs; i++) {
-		int val; quant_prepare(jobs[i].quant, &q[i], &val);
+		int val; quant_prepare(jobs[i].quant, &q[i], &val, ctx->tune_maxn, ctx->tune_uni);
 		QsJob &j = v[i]; memset(&j, 0, sizeof(j));
 		j.coef = jobs[i].coef; j.plane = jobs[i].plane; j.plane2 = jobs[i].plane2;
 		j.quant = ctx->quant_dev + i;

@@ -25,8 +25,6 @@
 #include "qs_common.h"
 #include "qs_kernels.h"
 
-__constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
-__constant__ int c_nchunks;
 __constant__ QsChunk2 c_chunks2[QS_MAX_CHUNKS];
 __constant__ int c_nchunks2, c_nslots2;
 __constant__ unsigned long long c_one2;      /* {1.0f, 1.0f}, deliberately opaque to ptxas (see qs_add2) */
@@ -338,18 +336,34 @@ __device__ __forceinline__ float qs_px8(uint2 w, int j) { return j < 4 ? qs_px(w
  * coefficient's terms: it expands a slice of the NEXT row's pixels, so the PRMTs (ALU pipe,
  * half rate) are interleaved with the FP work instead of forming a burst at the loop end
  * where, in lock step, all four warps of the sub-partition would queue on the ALU pipe. */
-template <int N, int NT, class Prep>
+template <int N, int NT, bool UNI, class Prep>
 __device__ __forceinline__ void qs_terms_row(const float *d, const float *const *tab, int off,
 		const float *Rs, float *a2, float *a3, Prep prep) {
-	float nad[8];
+	float nad[8], t[8], a0[8];
 #pragma unroll
 	for (int x = 0; x < NT; x++) nad[x] = -fabsf(d[x]);
+	if (UNI) {
+		/* all coefficients of the chunk share the quant value: t and a0 = d*t are the same
+		 * numbers for each of them, computed once (identical roundings, so still bit-exact) */
+#pragma unroll
+		for (int x = 0; x < NT; x++) {
+			asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(t[x]) : "f"(Rs[0]), "f"(nad[x]));
+			t[x] = FM(t[x], t[x]);
+			a0[x] = FM(d[x], t[x]);
+		}
+	}
 #pragma unroll
 	for (int c = 0; c < N; c++) {
 		float4 wa = *(const float4 *)(tab[c] + off), wb = *(const float4 *)(tab[c] + off + 4);
 		float w[8] = { wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w };
 #pragma unroll
-		for (int x = 0; x < NT; x++) qs_term(d[x], nad[x], w[x], Rs[c], a2[c], a3[c]);
+		for (int x = 0; x < NT; x++) {
+			if (UNI) {
+				float a1 = FM(w[x], t[x]);
+				a2[c] = FA(a2[c], FM(a0[x], a1));
+				a3[c] = FA(a3[c], FM(a1, a1));
+			} else qs_term(d[x], nad[x], w[x], Rs[c], a2[c], a3[c]);
+		}
 		prep(c);
 	}
 }
@@ -367,7 +381,7 @@ __device__ __forceinline__ void qs_prep_slice(uint2 w, float *f, int c) {
  * PRMT->FADD chain sits in front of the FP work. */
 
 /* horizontal pairs, quantsmooth.h:1527 */
-template <int N>
+template <int N, bool UNI>
 __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
 	float d[8];
@@ -381,7 +395,7 @@ __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *ta
 	for (int y = 0; y < 8; y++) {
 		uint2 wn = pw[((y + 1) & 7) * 32];              /* next row (wraps on the last pass) */
 		float f[8];
-		qs_terms_row<N, 7>(d, tab, y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, f, c); });
+		qs_terms_row<N, 7, UNI>(d, tab, y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, f, c); });
 #pragma unroll
 		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
 	}
@@ -389,7 +403,7 @@ __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *ta
 
 /* top, bottom, left, right border pairs, quantsmooth.h:1529-1530:
  * (row 0, above), (row 7, below), (column 0, left), (column 7, right) */
-template <int N>
+template <int N, bool UNI>
 __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
 	float d[8];
@@ -405,7 +419,7 @@ __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *cons
 		int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;     /* word of the block edge for step sn */
 		uint2 wa = pw[wi * 32], wb = pw[(10 + sn) * 32];
 		float fa[8], fb[8];
-		qs_terms_row<N, 8>(d, tab, 64 + s * 8, Rs, a2, a3,
+		qs_terms_row<N, 8, UNI>(d, tab, 64 + s * 8, Rs, a2, a3,
 				[&](int c) { qs_prep_slice<N>(wa, fa, c); qs_prep_slice<N>(wb, fb, c); });
 #pragma unroll
 		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
@@ -413,7 +427,7 @@ __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *cons
 }
 
 /* vertical pairs, quantsmooth.h:1531 */
-template <int N>
+template <int N, bool UNI>
 __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
 	float fp[8], d[8];
@@ -427,14 +441,14 @@ __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *ta
 	for (int y = 0; y < 7; y++) {
 		uint2 wn = pw[min(y + 2, 7) * 32];
 		float fn[8];
-		qs_terms_row<N, 8>(d, tab, 96 + y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, fn, c); });
+		qs_terms_row<N, 8, UNI>(d, tab, 96 + y * 8, Rs, a2, a3, [&](int c) { qs_prep_slice<N>(wn, fn, c); });
 #pragma unroll
 		for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
 	}
 }
 
 /* diagonal pairs, quantsmooth.h:1533-1540: per (y,x) first "\\" then "/" */
-template <int N>
+template <int N, bool UNI>
 __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const *tab, const float *Rs,
 		float *a2, float *a3) {
 	float fp[8], d1[8], d2[8];
@@ -447,7 +461,16 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 #pragma unroll 1
 	for (int y = 0; y < 7; y++) {
 		uint2 wn = pw[min(y + 2, 7) * 32];
-		float fn[8];
+		float fn[8], t1[8], t2[8], p1[8], p2[8];
+		if (UNI) {
+#pragma unroll
+			for (int x = 0; x < 7; x++) {
+				asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(t1[x]) : "f"(Rs[0]), "f"(-fabsf(d1[x])));
+				asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(t2[x]) : "f"(Rs[0]), "f"(-fabsf(d2[x])));
+				t1[x] = FM(t1[x], t1[x]); t2[x] = FM(t2[x], t2[x]);
+				p1[x] = FM(d1[x], t1[x]); p2[x] = FM(d2[x], t2[x]);
+			}
+		}
 #pragma unroll
 		for (int c = 0; c < N; c++) {
 			const float *t = tab[c] + 160 + y * 16;
@@ -457,8 +480,15 @@ __device__ __forceinline__ void qs_sec_diag(const uint2 *pw, const float *const 
 			float w2[8] = { wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w };
 #pragma unroll
 			for (int x = 0; x < 7; x++) {
-				qs_term(d1[x], -fabsf(d1[x]), w1[x], Rs[c], a2[c], a3[c]);
-				qs_term(d2[x], -fabsf(d2[x]), w2[x], Rs[c], a2[c], a3[c]);
+				if (UNI) {
+					float a1 = FM(w1[x], t1[x]);
+					a2[c] = FA(a2[c], FM(p1[x], a1)); a3[c] = FA(a3[c], FM(a1, a1));
+					a1 = FM(w2[x], t2[x]);
+					a2[c] = FA(a2[c], FM(p2[x], a1)); a3[c] = FA(a3[c], FM(a1, a1));
+				} else {
+					qs_term(d1[x], -fabsf(d1[x]), w1[x], Rs[c], a2[c], a3[c]);
+					qs_term(d2[x], -fabsf(d2[x]), w2[x], Rs[c], a2[c], a3[c]);
+				}
 			}
 			qs_prep_slice<N>(wn, fn, c);
 		}
@@ -511,7 +541,7 @@ __device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const
 	}
 }
 
-template <int N, bool DIAG, int SYNC>
+template <int N, bool DIAG, int SYNC, bool UNI>
 __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
 		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp) {
 	const float *tab[N]; float Rs[N], a2[N], a3[N];
@@ -521,12 +551,12 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 		int i = ch.idx[c];
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
-	qs_sec_h<N>(pw, tab, Rs, a2, a3);
+	qs_sec_h<N, UNI>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
-	qs_sec_border<N>(pw, tab, Rs, a2, a3);
+	qs_sec_border<N, UNI>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
-	qs_sec_v<N>(pw, tab, Rs, a2, a3);
-	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<N>(pw, tab, Rs, a2, a3); }
+	qs_sec_v<N, UNI>(pw, tab, Rs, a2, a3);
+	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<N, UNI>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
@@ -544,12 +574,12 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 		int i = ch.idx[c];
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
-	qs_sec_h<1>(pw, tab, Rs, a2, a3);
+	qs_sec_h<1, false>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
-	qs_sec_border<2>(pw, tab, Rs, a2, a3);
+	qs_sec_border<2, false>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
-	qs_sec_v<1>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
-	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<2>(pw, tab, Rs, a2, a3); }
+	qs_sec_v<1, false>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
+	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<2, false>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
 #pragma unroll
 	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
@@ -951,19 +981,31 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
 			}
 		}
-		int nch = X2 ? 0 : c_nchunks;
+		int nch = X2 ? 0 : __ldg(&qd->nchunks);
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
-			QsChunk ch = c_chunks[ci];
+			QsChunk ch;
+			{
+				const uint32_t *cp = (const uint32_t *)&qd->chunks[ci];     /* 12 bytes, warp-uniform */
+				uint32_t c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+				ch.type = c0 & 255; ch.n = (c0 >> 8) & 255; ch.first = (c0 >> 16) & 255; ch.pad = 0;
+				ch.idx[0] = c1 & 255; ch.idx[1] = (c1 >> 8) & 255; ch.idx[2] = (c1 >> 16) & 255; ch.idx[3] = c1 >> 24;
+				ch.idx[4] = c2 & 255; ch.idx[5] = (c2 >> 8) & 255; ch.idx[6] = (c2 >> 16) & 255; ch.idx[7] = c2 >> 24;
+			}
 			qs_group_sync<SYNC>(gsync);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first && !(ci == 0 && fresh_px)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
-			if (ch.type) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
-			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
-			else qs_chunk_full<1, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.type == 2) {
+				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
+				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
+				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
+			}
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
+			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
 		}
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
@@ -1189,12 +1231,6 @@ __global__ void qs_fdct_plane_kernel(const uint8_t *__restrict__ px, int pstride
 /* ------------------------------------------------------------------------------------------
  * launch wrappers
  * ------------------------------------------------------------------------------------------ */
-cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
-	cudaError_t e = cudaMemcpyToSymbol(c_chunks, chunks, sizeof(QsChunk) * n);
-	if (e != cudaSuccess) return e;
-	return cudaMemcpyToSymbol(c_nchunks, &n, sizeof(int));
-}
-
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
 static qs_smooth_fn qs_smooth_variant_x2(int diag, int sync) {

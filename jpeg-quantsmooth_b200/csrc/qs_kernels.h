@@ -4,7 +4,6 @@
 #include <cuda_runtime.h>
 #include "qs_common.h"
 
-cudaError_t qs_set_chunks(const QsChunk *chunks, int n);
 size_t qs_smooth_smem_bytes(int diag, int wpg);
 cudaError_t qs_smooth_configure(void);
 cudaError_t qs_set_chunks2(const QsChunk2 *chunks, int n, int nslots);
