@@ -82,6 +82,8 @@ void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *i
  * key 2: warps per SM sub-partition (4 or 6, default 4; 6 = 80 registers per thread)
  * key 3: (retired experiment, ignored)
  * key 5: uniform-quant chunks share t and d*t (default 1)
+ * key 6: slab-pipelined upload/download in the host entry points (default 1)
+ * key 7: blocks per slab wave for key 6; 0 = SM count x resident warps x 32 (tests force small values)
  * key 4: 1 = packed FP32x2 pair path (FMUL2/FFMA2; exact, but measured slower), 0 = scalar (default) */
 int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value);
 

@@ -177,6 +177,7 @@ struct jpegqs_cuda_ctx {
 	cudaStream_t stream;
 	cudaStream_t copy_stream;              /* H2D / D2H of the host entry points, overlapped with compute */
 	std::vector<cudaEvent_t> sync_ev;      /* per group: coefficients uploaded / group finished */
+	std::vector<cudaEvent_t> slab_ev;      /* per slab of a pipelined group: uploaded / smoothed */
 	float *tab_plain, *tab_diag;
 	float *tab2_plain, *tab2_diag; int nslots2;   /* pair tables of the FP32x2 path */
 	QsQuantDev *quant_dev; int quant_cap;
@@ -189,7 +190,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
-	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2, tune_uni;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
+	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2, tune_uni, tune_slabs, tune_wave;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -225,6 +226,7 @@ extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
 	if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
 	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
 	for (cudaEvent_t e : ctx->sync_ev) cudaEventDestroy(e);
+	for (cudaEvent_t e : ctx->slab_ev) cudaEventDestroy(e);
 	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->tab2_plain); cudaFree(ctx->tab2_diag); cudaFree(ctx->quant_dev);
 	cudaFree(ctx->jobs_dev); cudaFree(ctx->flags_dev); cudaFree(ctx->arena);
 	if (ctx->flags_host) cudaFreeHost(ctx->flags_host);
@@ -259,7 +261,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_slabs = 1; ctx->tune_wave = 0; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -403,6 +405,8 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 		return 0;
 	}
 	if (key == 5) { ctx->tune_uni = value ? 1 : 0; return 0; }
+	if (key == 6) { ctx->tune_slabs = value ? 1 : 0; return 0; }
+	if (key == 7) { if (value < 0) return JPEGQS_ERR_ARG; ctx->tune_wave = value; return 0; }
 	return JPEGQS_ERR_ARG;
 }
 extern "C" void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
@@ -425,6 +429,7 @@ struct CompWork {
 	bool iterate;          /* takes part in the IDCT / smoothing iterations */
 	bool dequant_only;     /* stop was already set: quantsmooth.h:2551-2566 */
 	bool done_clamp;
+	bool downloaded;       /* the slab pipeline already sent the coefficients back */
 };
 
 struct ImgState {
@@ -437,6 +442,15 @@ struct ImgState {
 	int16_t *coef_up_dev[2];
 	int ngroups;
 };
+
+/* Host entry points, one large image: a group's block rows are cut into slabs of about one
+ * wave of the persistent smoothing kernel.  Iteration 0 then follows the upload slab by slab
+ * (IDCT pass of slab k, smoothing of slab k-1 - which needs the first pixel row of slab k), and
+ * the last iteration hands its slabs to the download as they finish, so that only the first
+ * slab's upload and the last slab's download are not hidden behind kernels.  Results do not
+ * depend on this: a pass reads only start-of-pass neighbour pixels (quantsmooth.h:1396-1401). */
+#define QS_MAX_SLABS 8
+struct SlabPlan { int K; int r[QS_MAX_SLABS + 1]; };
 
 static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, int flags, int niter,
 		int progprec, jpegqs_cuda_progress_fn progress, void *userdata, bool on_device, int *ret,
@@ -532,11 +546,63 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		else { *c0 = 0; *c1 = s.im->ncomp; }
 	};
 	cudaStream_t cst = ctx->copy_stream;
+	std::vector<SlabPlan> plan(max_groups > 0 ? max_groups : 1);
+	for (SlabPlan &pl : plan) pl.K = 0;
 	if (!on_device) {                                   /* uploads, group by group, on the copy stream */
 		while ((int)ctx->sync_ev.size() < 2 * max_groups) {
 			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->sync_ev.push_back(e);
 		}
+		while ((int)ctx->slab_ev.size() < 2 * max_groups * QS_MAX_SLABS) {
+			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->slab_ev.push_back(e);
+		}
 		for (int g = 0; g < max_groups; g++) {
+			if (nimg == 1 && !progress && ctx->tune_slabs && !ctx->tune_x2 && !(flags & QS_LOW_QUALITY) &&
+					!S[0].skip && g < S[0].ngroups && niter >= 1) {
+				/* slab plan of this group: all its components alike and certain to iterate */
+				ImgState &s = S[0];
+				int c0, c1; group_range(s, g, &c0, &c1);
+				bool ok = c1 > c0;
+				for (int ci = c0; ci < c1 && ok; ci++) {
+					CompWork &w = W[0][ci];
+					ok = w.c->has_qtbl && qval[0][ci] > 1 && qval[0][ci] < 0x800 && w.W > 0 && w.H > 0 &&
+							w.W == W[0][c0].W && w.H == W[0][c0].H;
+					if (ok) {
+						/* pageable host memory makes every async copy block the calling thread:
+						 * the pipeline only pays off (and only then is used) with pinned buffers */
+						cudaPointerAttributes at;
+						if (cudaPointerGetAttributes(&at, w.c->coef) != cudaSuccess) { cudaGetLastError(); ok = false; }
+						else ok = at.type == cudaMemoryTypeHost;
+					}
+				}
+				if (ok) {
+					int Wb = W[0][c0].W, Hb = W[0][c0].H, nc = c1 - c0;
+					long wave = (long)ctx->num_sms * ctx->tune_wpg * 4 * 32;     /* blocks in flight */
+					if (ctx->tune_wave) wave = ctx->tune_wave;
+					int rpw = (int)(wave / ((long)nc * Wb));
+					if (rpw >= 1) {
+						int waves = (Hb + rpw - 1) / rpw;
+						int m = (waves + QS_MAX_SLABS - 1) / QS_MAX_SLABS;
+						int K = (Hb + m * rpw - 1) / (m * rpw);
+						if (K >= 2) {
+							plan[g].K = K;
+							for (int k = 0; k <= K; k++) plan[g].r[k] = (int)((long)k * Hb / K);
+						}
+					}
+				}
+			}
+			if (plan[g].K) {
+				int c0, c1; group_range(S[0], g, &c0, &c1);
+				for (int k = 0; k < plan[g].K; k++) {
+					for (int ci = c0; ci < c1; ci++) {
+						CompWork &w = W[0][ci];
+						size_t off = (size_t)plan[g].r[k] * w.W * 64, cnt = (size_t)(plan[g].r[k + 1] - plan[g].r[k]) * w.W * 64;
+						CK(cudaMemcpyAsync(w.coef_dev + off, w.c->coef + off, cnt * 2, cudaMemcpyHostToDevice, cst));
+					}
+					CK(cudaEventRecord(ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k], cst));
+				}
+				CK(cudaEventRecord(ctx->sync_ev[2 * g], cst));
+				continue;
+			}
 			for (int n = 0; n < nimg; n++) {
 				ImgState &s = S[n];
 				if (s.skip || g >= s.ngroups) continue;
@@ -573,9 +639,30 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		j.luma = w.luma; j.top_edge = 1; j.bottom_edge = 1;
 		return j;
 	};
+	auto make_slab_job = [&](const CompWork &w, const uint8_t *plane2, int r0, int r1) {
+		QsJob j = make_job(w, plane2);
+		size_t poff = (size_t)r0 * 8 * j.stride;
+		j.coef += (size_t)r0 * w.W * 64; j.plane += poff;
+		if (plane2) j.plane2 += poff;
+		j.hblk = r1 - r0; j.nblocks = w.W * (r1 - r0);
+		j.top_edge = r0 == 0; j.bottom_edge = r1 == w.H;
+		return j;
+	};
+	auto launch_smooth = [&](const QsJob *jd, int nj, int tiles, int clampv) -> int {
+		if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
+		if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, nj, tiles, flags, clampv, st));
+		else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, nj, tiles,
+				(flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain, ctx->nslots2, tile_counter, flags, clampv,
+				ctx->num_sms, ctx->tune_sync, st));
+		else CK(qs_launch_smooth(jd, nj, tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+		if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
+		ctx->launches++;
+		return 0;
+	};
 
 	for (int g = 0; g < max_groups; g++) {
-		if (!on_device) CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0));
+		bool slab_in = !on_device && plan[g].K > 0 && !S[0].stop;
+		if (!on_device && !slab_in) CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0));
 		/* ---- which components belong to this phase; per-component prelude 2484-2566 ---- */
 		std::vector<CompWork *> works;
 		int prog_cur = 0, prog_inc = 0;
@@ -604,7 +691,59 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 
 		int max_pass = 0;
 		for (CompWork *w : works) if (w->niter2 + w->extra > max_pass) max_pass = w->niter2 + w->extra;
+		auto p2_of = [&](const CompWork *w) -> const uint8_t * {
+			ImgState &s = S[w->img];
+			return (s.image2 && (flags & QS_JOINT_YUV) && w->ci > 0) ? s.image2 : NULL;
+		};
+		if (slab_in) {
+			int c0, c1; group_range(S[0], g, &c0, &c1);
+			bool ok = (int)works.size() == c1 - c0;
+			for (CompWork *w : works) ok = ok && w->niter2 == works[0]->niter2 && w->extra == works[0]->extra && w->niter2 >= 1;
+			if (!ok) { slab_in = false; CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0)); }
+		}
+		bool slab_out = slab_in && works[0]->niter2 >= 2 && !works[0]->extra;
 		for (int iter = 0; iter < max_pass; iter++) {
+			if (iter == 0 && slab_in) {
+				/* ---- iteration 0 behind the upload, slab by slab ---- */
+				const SlabPlan &pl = plan[g];
+				int cl = (works[0]->niter2 == 1 && !works[0]->extra) ? 1 : 0;
+				CK(cudaMemsetAsync(bad_dev, 0, works.size() * sizeof(int), st));
+				for (int k = 0; k <= pl.K; k++) {
+					const QsJob *jd; int tiles;
+					if (k < pl.K) {
+						CK(cudaStreamWaitEvent(st, ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k], 0));
+						std::vector<QsJob> jobs;
+						for (CompWork *w : works) jobs.push_back(make_slab_job(*w, NULL, pl.r[k], pl.r[k + 1]));
+						if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+						if (prof_begin(ctx, 0, st)) return JPEGQS_ERR_CUDA;
+						CK(qs_launch_idct_pass(jd, (int)jobs.size(), tiles, QS_IDCT_DEQUANT, bad_dev, st));
+						if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
+						ctx->launches++;
+					}
+					if (k >= 1) {
+						std::vector<QsJob> jobs;
+						for (CompWork *w : works) jobs.push_back(make_slab_job(*w, p2_of(w), pl.r[k - 1], pl.r[k]));
+						if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+						if (launch_smooth(jd, (int)jobs.size(), tiles, cl)) return JPEGQS_ERR_CUDA;
+					}
+				}
+				CK(cudaMemcpyAsync(ctx->flags_host, bad_dev, works.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				bool bad = false;
+				for (size_t k = 0; k < works.size(); k++) bad = bad || ctx->flags_host[k];
+				if (!bad) {
+					if (cl) for (CompWork *w : works) w->done_clamp = true;
+					continue;
+				}
+				/* a coefficient left the legal range (quantsmooth.h:2602): the reference stops
+				 * before smoothing anything of that component.  The host copy is still intact:
+				 * fetch the group again and take the plain path, which implements the stop. */
+				for (CompWork *w : works) {
+					size_t cb = (size_t)w->W * w->H * 128;
+					CK(cudaMemcpyAsync(w->coef_dev, w->c->coef, cb, cudaMemcpyHostToDevice, st));
+				}
+				slab_in = slab_out = false;
+			}
 			/* ---- IDCT pass, 2589-2620.  The extra (render-only) pass also applies the
 			 *      final +-1023 clamp of 2670-2689 after rendering from unclamped values. */
 			for (int clampv = 0; clampv < 2; clampv++) {
@@ -643,27 +782,38 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				}
 			}
 			/* ---- smoothing pass, 2627-2640 ---- */
+			if (slab_out && iter == works[0]->niter2 - 1) {
+				/* last iteration: each finished slab goes straight to the download */
+				const SlabPlan &pl = plan[g];
+				for (int k = 0; k < pl.K; k++) {
+					std::vector<QsJob> jobs;
+					for (CompWork *w : works) jobs.push_back(make_slab_job(*w, p2_of(w), pl.r[k], pl.r[k + 1]));
+					const QsJob *jd; int tiles;
+					if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
+					if (launch_smooth(jd, (int)jobs.size(), tiles, 1)) return JPEGQS_ERR_CUDA;
+					cudaEvent_t e = ctx->slab_ev[(2 * g + 1) * QS_MAX_SLABS + k];
+					CK(cudaEventRecord(e, st));
+					CK(cudaStreamWaitEvent(cst, e, 0));
+					for (CompWork *w : works) {
+						size_t off = (size_t)pl.r[k] * w->W * 64, cnt = (size_t)(pl.r[k + 1] - pl.r[k]) * w->W * 64;
+						CK(cudaMemcpyAsync(w->c->coef + off, w->coef_dev + off, cnt * 2, cudaMemcpyDeviceToHost, cst));
+					}
+				}
+				for (CompWork *w : works) { w->done_clamp = true; w->downloaded = true; }
+				continue;
+			}
 			for (int clampv = 0; clampv < 2; clampv++) {
 				std::vector<QsJob> jobs; std::vector<CompWork *> who;
 				for (CompWork *w : works) {
 					if (!w->iterate || iter >= w->niter2) continue;
 					int cl = (iter == w->niter2 - 1 && !w->extra) ? 1 : 0;
 					if (cl != clampv) continue;
-					ImgState &s = S[w->img];
-					const uint8_t *p2 = (s.image2 && (flags & QS_JOINT_YUV) && w->ci > 0) ? s.image2 : NULL;
-					jobs.push_back(make_job(*w, p2)); who.push_back(w);
+					jobs.push_back(make_job(*w, p2_of(w))); who.push_back(w);
 				}
 				if (jobs.empty()) continue;
 				const QsJob *jd; int tiles;
 				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
-				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
-				if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, (int)jobs.size(), tiles, flags, clampv, st));
-				else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, (int)jobs.size(), tiles,
-						(flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain, ctx->nslots2, tile_counter, flags, clampv,
-						ctx->num_sms, ctx->tune_sync, st));
-				else CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
-				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
-				ctx->launches++;
+				if (launch_smooth(jd, (int)jobs.size(), tiles, clampv)) return JPEGQS_ERR_CUDA;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
 			}
 			if (progress && works.size() == 1 && works[0]->iterate && iter < works[0]->niter2) {   /* 2656-2664 */
@@ -722,7 +872,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				for (int ci = c0; ci < c1; ci++) {
 					CompWork &w = W[n][ci];
 					size_t cb = (size_t)w.W * w.H * 128;
-					if (cb) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, cst));
+					if (cb && !w.downloaded) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, cst));
 					if (s.image1 && !s.stop && ci >= 1 && ci <= 2) {
 						size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk * 128;
 						CK(cudaMemcpyAsync(w.c->coef_up, s.coef_up_dev[ci - 1], yb, cudaMemcpyDeviceToHost, cst));

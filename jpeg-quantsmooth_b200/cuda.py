@@ -211,13 +211,21 @@ class QsContext:
 
     # ---- whole image, host buffers (the call a user of the reference makes) ----
     def do_quantsmooth(self, image: CoefImage, flags: int, niter: int, progprec: int = 0,
-                       progress=None, inplace: bool = False):
+                       progress=None, inplace: bool = False, pinned: bool = False):
+        """pinned=True stages the coefficient arrays in page-locked memory (what the C entry
+        point do_quantsmooth does): only then the upload/download slab pipeline is used."""
         out = image if inplace else image.clone()
         keep = []
         ptrs, ups = [], []
         for c in out.comps:
             c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
-            ptrs.append(c.coef.ctypes.data)
+            if pinned and c.coef.size:
+                pa = PinnedArray(c.coef.shape)
+                pa.array[...] = c.coef
+                keep.append((pa, c))
+                ptrs.append(pa.array.ctypes.data)
+            else:
+                ptrs.append(c.coef.ctypes.data)
         up_arrays = []
         if len(out.comps) >= 3:
             y = out.comps[0]
@@ -235,6 +243,11 @@ class QsContext:
         ret = self._check(self.lib.jpegqs_cuda_run_host(
             self.h, C.byref(ci), flags & 0x7f, niter, progprec,
             C.cast(cb, C.c_void_p) if cb else None, None))
+        for item in keep:
+            if isinstance(item, tuple):
+                pa, c = item
+                c.coef[...] = pa.array
+                pa.close()
         self._collect(out, ci, up_arrays)
         return ret, out
 
