@@ -50,6 +50,7 @@ typedef struct {
 	uint16_t q[64];      /* quantval with 0 -> 1 (quantsmooth.h:2508-2511) */
 	uint16_t qraw[64];   /* raw quantval, used only by the iteration-0 dequantize (2598) */
 	int32_t nchunks;     /* chunk schedule of this table */
+	int32_t sched_slot;  /* index of the first table of this upload with the same schedule */
 	QsChunk chunks[QS_MAX_CHUNKS];
 } QsQuantDev;
 

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unordered_map>
 #include <vector>
 #include "qs_common.h"
 #include "qs_kernels.h"
@@ -276,6 +277,11 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 		CK(cudaMalloc(&ctx->tab_diag, 64 * QS_TAB_DIAG * sizeof(float)));
 		CK(cudaMemcpy(ctx->tab_diag, t.data(), 64 * QS_TAB_DIAG * sizeof(float), cudaMemcpyHostToDevice));
 		{
+			QsChunk ch[QS_MAX_CHUNKS * 2];
+			int n = build_chunks(ch, ctx->tune_maxn, NULL, 0);
+			CK(qs_set_chunks(ch, n));
+		}
+		{
 			QsChunk2 ch2[QS_MAX_CHUNKS]; uint8_t lanes[QS_MAX_SLOTS][2]; int ns = 0;
 			int n2 = build_pairs(ch2, &ns, 2, lanes);
 			CK(qs_set_chunks2(ch2, n2, ns));
@@ -328,6 +334,7 @@ static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int 
 		q->m31[i] = (uint32_t)(((1ull << 31) + (uint32_t)qq - 1) / (uint32_t)qq);
 	}
 	q->nchunks = build_chunks(q->chunks, maxn, q->q, uniform);
+	q->sched_slot = 0;      /* callers that smooth run assign_sched_slots over the upload */
 	*val_out = val;
 }
 
@@ -340,6 +347,24 @@ static int quant_reserve(jpegqs_cuda_ctx *ctx, int n) {
 		ctx->quant_cap = n + 16;
 	}
 	return 0;
+}
+
+/* sched_slot: tables with identical chunk schedules get the same id, so the kernel can tell
+ * whether the warps of a lock-step group may follow their own table's schedule */
+static void assign_sched_slots(QsQuantDev *q, int n) {
+	std::unordered_map<uint64_t, std::vector<int> > seen;
+	for (int i = 0; i < n; i++) {
+		uint64_t h = 1469598103934665603ull;
+		const uint8_t *b = (const uint8_t *)q[i].chunks;
+		size_t len = (size_t)q[i].nchunks * sizeof(QsChunk);
+		for (size_t k = 0; k < len; k++) h = (h ^ b[k]) * 1099511628211ull;
+		h ^= (uint64_t)q[i].nchunks << 56;
+		int slot = i;
+		for (int j : seen[h])
+			if (q[j].nchunks == q[i].nchunks && !memcmp(q[j].chunks, q[i].chunks, len)) { slot = j; break; }
+		if (slot == i) seen[h].push_back(i);
+		q[i].sched_slot = slot;
+	}
 }
 
 /* upload a job list into one of the two device slots unless it is already there */
@@ -356,8 +381,8 @@ static int upload_jobs(jpegqs_cuda_ctx *ctx, int slot, std::vector<QsJob> &jobs,
 	if (c.size() == jobs.size() && (jobs.empty() || !memcmp(c.data(), jobs.data(), jobs.size() * sizeof(QsJob))))
 		return 0;
 	if (jobs.size() > QS_MAX_JOBS) { snprintf(ctx->err, sizeof(ctx->err), "too many jobs in one launch"); return JPEGQS_ERR_ARG; }
-	/* pageable source: the runtime stages it before returning, so `jobs` may die afterwards */
-	if (!jobs.empty()) CK(cudaMemcpyAsync((void *)*dev, jobs.data(), jobs.size() * sizeof(QsJob), cudaMemcpyHostToDevice, st));
+	/* travels as kernel parameters: an H2D copy would queue behind the bulk coefficient uploads */
+	if (!jobs.empty()) CK(qs_store_jobs((QsJob *)*dev, jobs.data(), (int)jobs.size(), st));
 	c = jobs;
 	return 0;
 }
@@ -401,7 +426,14 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
 	if (key == 1) {
 		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
-		ctx->tune_maxn = value;            /* takes effect with the next quant-table upload */
+		CK(cudaSetDevice(ctx->device));
+		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaDeviceSynchronize());
+		QsChunk ch[QS_MAX_CHUNKS * 2];
+		int n = build_chunks(ch, value, NULL, 0);
+		if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
+		CK(qs_set_chunks(ch, n));                  /* the table-independent schedule */
+		ctx->tune_maxn = value;                    /* per-table schedules follow with the next upload */
 		return 0;
 	}
 	if (key == 5) { ctx->tune_uni = value ? 1 : 0; return 0; }
@@ -449,7 +481,7 @@ struct ImgState {
  * the last iteration hands its slabs to the download as they finish, so that only the first
  * slab's upload and the last slab's download are not hidden behind kernels.  Results do not
  * depend on this: a pass reads only start-of-pass neighbour pixels (quantsmooth.h:1396-1401). */
-#define QS_MAX_SLABS 8
+#define QS_MAX_SLABS 16
 struct SlabPlan { int K; int r[QS_MAX_SLABS + 1]; };
 
 static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, int flags, int niter,
@@ -536,6 +568,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			}
 		}
 	}
+	assign_sched_slots(qhost.data(), (int)qhost.size());
 	if (!qhost.empty())
 		CK(cudaMemcpyAsync(ctx->quant_dev, qhost.data(), qhost.size() * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
 	ctx->jobs_cache[0].clear(); ctx->jobs_cache[1].clear();
@@ -701,7 +734,10 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			for (CompWork *w : works) ok = ok && w->niter2 == works[0]->niter2 && w->extra == works[0]->extra && w->niter2 >= 1;
 			if (!ok) { slab_in = false; CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0)); }
 		}
-		bool slab_out = slab_in && works[0]->niter2 >= 2 && !works[0]->extra;
+		/* the download pipeline needs the slab plan but not the upload pipeline, and vice versa:
+		 * a middle group's transfers hide behind its neighbours' kernels anyway */
+		bool slab_out = slab_in && works[0]->niter2 >= 2 && !works[0]->extra && g == S[0].ngroups - 1;
+		if (slab_in && g > 0) { slab_in = false; CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0)); }
 		for (int iter = 0; iter < max_pass; iter++) {
 			if (iter == 0 && slab_in) {
 				/* ---- iteration 0 behind the upload, slab by slab ---- */
@@ -727,7 +763,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 						if (launch_smooth(jd, (int)jobs.size(), tiles, cl)) return JPEGQS_ERR_CUDA;
 					}
 				}
-				CK(cudaMemcpyAsync(ctx->flags_host, bad_dev, works.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+				CK(qs_copy_flags(bad_dev, ctx->flags_host, (int)works.size(), st));
 				CK(cudaStreamSynchronize(st));
 				bool bad = false;
 				for (size_t k = 0; k < works.size(); k++) bad = bad || ctx->flags_host[k];
@@ -765,7 +801,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				ctx->launches++;
 				if (clampv) for (CompWork *w : who) w->done_clamp = true;
 				if (iter == 0) {                                           /* bad_coef, 2602-2610 */
-					CK(cudaMemcpyAsync(ctx->flags_host, bad_dev, jobs.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+					CK(qs_copy_flags(bad_dev, ctx->flags_host, (int)jobs.size(), st));
 					CK(cudaStreamSynchronize(st));
 					for (size_t k = 0; k < who.size(); k++) {
 						CompWork *w = who[k]; ImgState &s = S[w->img];
@@ -782,6 +818,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				}
 			}
 			/* ---- smoothing pass, 2627-2640 ---- */
+			if (slab_out) for (CompWork *w : works) if (!w->iterate) slab_out = false;   /* a component stopped */
 			if (slab_out && iter == works[0]->niter2 - 1) {
 				/* last iteration: each finished slab goes straight to the download */
 				const SlabPlan &pl = plan[g];
@@ -953,6 +990,7 @@ static int stage_jobs(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jo
 		j.nblocks = j.wblk * j.hblk; j.luma = jobs[i].luma;
 		j.top_edge = jobs[i].top_edge; j.bottom_edge = jobs[i].bottom_edge;
 	}
+	assign_sched_slots(q.data(), njobs);
 	if (njobs) CK(cudaMemcpyAsync(ctx->quant_dev, q.data(), njobs * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
 	ctx->jobs_cache[slot].clear();
 	return upload_jobs(ctx, slot, v, st, jd, tiles);
@@ -971,7 +1009,7 @@ extern "C" int jpegqs_cuda_pass_idct(jpegqs_cuda_ctx *ctx, int njobs, const jpeg
 	if (bad) {
 		*bad = 0;
 		if (njobs) {
-			CK(cudaMemcpyAsync(ctx->flags_host, ctx->flags_dev, njobs * sizeof(int), cudaMemcpyDeviceToHost, st));
+			CK(qs_copy_flags(ctx->flags_dev, ctx->flags_host, njobs, st));
 			CK(cudaStreamSynchronize(st));
 			for (int i = 0; i < njobs; i++) if (ctx->flags_host[i]) *bad |= (int)(1u << (i < 31 ? i : 31));
 		}

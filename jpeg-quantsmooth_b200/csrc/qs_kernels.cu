@@ -25,6 +25,10 @@
 #include "qs_common.h"
 #include "qs_kernels.h"
 
+/* table-independent schedule: used by a lock-step group whose warps work on components with
+ * different schedules (their barrier sequences must match) */
+__constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
+__constant__ int c_nchunks;
 __constant__ QsChunk2 c_chunks2[QS_MAX_CHUNKS];
 __constant__ int c_nchunks2, c_nslots2;
 __constant__ unsigned long long c_one2;      /* {1.0f, 1.0f}, deliberately opaque to ptxas (see qs_add2) */
@@ -849,6 +853,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		int flags, int clamp_out) {
 	extern __shared__ __align__(16) uint32_t smem[];
 	__shared__ int s_tile[16];
+	__shared__ int s_sig[32];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 	const bool X2 = (SYNC & QS_SYNC_X2) != 0;
 	const int tab_words = X2 ? c_nslots2 * 2 * TS : 64 * TS;
@@ -959,6 +964,19 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		 * the plane (same coefficients, deterministic IDCT), so those 64 pixels are loaded
 		 * instead of computed - unless the JOINT_YUV predictor changed the coefficients. */
 		const bool fresh_px = job->plane2 == NULL;
+		/* Warps of a lock-step group may sit in different components (a group tile or the
+		 * balanced tail can straddle jobs).  Their barrier sequences must be identical, so a
+		 * mixed group takes the table-independent schedule and always refreshes at chunk 0. */
+		bool mixed = false;
+		if (QS_SYNC_LEVEL(SYNC)) {
+			int sig = __ldg(&qd->sched_slot) * 2 + (fresh_px ? 1 : 0);
+			if (lane == 0) s_sig[warp] = sig;
+			qs_group_sync<SYNC>(gsync);
+			int nw = (gsync >> 8) >> 5;
+			for (int k = 0; k < nw; k++) mixed = mixed || *(volatile int *)&s_sig[k * NG + grp] != sig;
+			mixed = __any_sync(0xffffffffu, mixed);
+		}
+		const bool skip0 = fresh_px && !mixed;
 		if (fresh_px) {
 			uint32_t lo[8], hi[8];
 #pragma unroll
@@ -976,16 +994,17 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			for (int ci = 0; ci < nch2; ci++) {
 				QsChunk2 ch = c_chunks2[ci];
 				qs_group_sync<SYNC>(gsync);
-				if (ch.first && !(ci == 0 && fresh_px)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+				if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 				if (ch.np == 2) qs_chunk_pairs<2, DIAG>(ch, tabs, pw, qd, cs);
 				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
 			}
 		}
-		int nch = X2 ? 0 : __ldg(&qd->nchunks);
+		int nch = X2 ? 0 : (mixed ? c_nchunks : __ldg(&qd->nchunks));
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
 			QsChunk ch;
-			{
+			if (mixed) ch = c_chunks[ci];
+			else {
 				const uint32_t *cp = (const uint32_t *)&qd->chunks[ci];     /* 12 bytes, warp-uniform */
 				uint32_t c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
 				ch.type = c0 & 255; ch.n = (c0 >> 8) & 255; ch.first = (c0 >> 16) & 255; ch.pad = 0;
@@ -995,7 +1014,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			qs_group_sync<SYNC>(gsync);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
-			if (ch.first && !(ci == 0 && fresh_px)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
+			if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
 			else if (ch.type == 2) {
 				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
@@ -1229,8 +1248,30 @@ __global__ void qs_fdct_plane_kernel(const uint8_t *__restrict__ px, int pstride
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Control-data movers.  Job lists and the "coefficient out of range" flags are a few hundred
+ * bytes, but as cudaMemcpyAsync they queue on the copy engines BEHIND the bulk coefficient
+ * transfers of the host entry points (measured: a 4-byte flag read waited 1.2 ms for a 66 MB
+ * download).  Kernel parameters and stores to mapped pinned memory do not touch the copy engines.
+ * ------------------------------------------------------------------------------------------ */
+struct QsJobPack { QsJob j[QS_JOB_PACK]; };
+__global__ void qs_store_jobs_kernel(const __grid_constant__ QsJobPack pack, QsJob *__restrict__ dst, int n) {
+	int i = threadIdx.x;
+	if (i < n) dst[i] = pack.j[i];
+}
+__global__ void qs_copy_flags_kernel(const int *__restrict__ src, volatile int *dst, int n) {
+	for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+	__threadfence_system();
+}
+
+/* ------------------------------------------------------------------------------------------
  * launch wrappers
  * ------------------------------------------------------------------------------------------ */
+cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
+	cudaError_t e = cudaMemcpyToSymbol(c_chunks, chunks, sizeof(QsChunk) * n);
+	if (e != cudaSuccess) return e;
+	return cudaMemcpyToSymbol(c_nchunks, &n, sizeof(int));
+}
+
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
 static qs_smooth_fn qs_smooth_variant_x2(int diag, int sync) {
@@ -1432,5 +1473,23 @@ cudaError_t qs_launch_render_rgb(const uint8_t *const *planes, const int *stride
 	a.ncomp = ncomp; a.width = width; a.height = height; a.ycc = ycc;
 	dim3 blk(32, 8), grd((width + 31) / 32, (height + 7) / 8);
 	qs_render_rgb_kernel<<<grd, blk, 0, st>>>(a, rgb);
+	return cudaGetLastError();
+}
+
+cudaError_t qs_store_jobs(QsJob *dst, const QsJob *jobs_host, int n, cudaStream_t st) {
+	for (int off = 0; off < n; off += QS_JOB_PACK) {
+		QsJobPack pack;
+		int cnt = n - off < QS_JOB_PACK ? n - off : QS_JOB_PACK;
+		memcpy(pack.j, jobs_host + off, (size_t)cnt * sizeof(QsJob));
+		if (cnt < QS_JOB_PACK) memset(pack.j + cnt, 0, (size_t)(QS_JOB_PACK - cnt) * sizeof(QsJob));
+		qs_store_jobs_kernel<<<1, QS_JOB_PACK, 0, st>>>(pack, dst + off, cnt);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return e;
+	}
+	return cudaSuccess;
+}
+
+cudaError_t qs_copy_flags(const int *src_dev, int *dst_mapped, int n, cudaStream_t st) {
+	qs_copy_flags_kernel<<<1, 128, 0, st>>>(src_dev, dst_mapped, n);
 	return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 
 size_t qs_smooth_smem_bytes(int diag, int wpg);
 cudaError_t qs_smooth_configure(void);
+cudaError_t qs_set_chunks(const QsChunk *chunks, int n);
 cudaError_t qs_set_chunks2(const QsChunk2 *chunks, int n, int nslots);
 size_t qs_smooth_smem_bytes_x2(int diag, int nslots);
 cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
@@ -27,4 +28,9 @@ cudaError_t qs_launch_fdct_plane(const uint8_t *px, int pstride, int16_t *coef, 
 cudaError_t qs_launch_render_rgb(const uint8_t *const *planes, const int *strides, const int *cw, const int *ch,
 		const int *hs, const int *vs, int ncomp, int width, int height, int ycc, uint8_t *rgb, cudaStream_t st);
 extern "C" int qs_host_orig_coef(int c, int q);
+/* control data without the copy engines (see qs_kernels.cu) */
+#define QS_JOB_PACK 48
+cudaError_t qs_store_jobs(QsJob *dst, const QsJob *jobs_host, int n, cudaStream_t st);
+cudaError_t qs_copy_flags(const int *src_dev, int *dst_mapped, int n, cudaStream_t st);
+
 #endif
