@@ -169,6 +169,13 @@ int jpegqs_cuda_render_rgb(jpegqs_cuda_ctx *ctx, const jpegqs_cuda_image *img, i
 int jpegqs_cuda_tables(int flags, float *out);
 /* host evaluation of the device's exact-division helper (GET_ORIG_COEF, 324-341) */
 int jpegqs_cuda_orig_coef(int coef, int q);
+/* the smoothing kernel's chunk schedule for one quant table (host-only): the 63
+ * AC coefficients in the reference's anti-diagonal visiting order (quantsmooth.h:313-322,
+ * 1403-1409), grouped into chunks.  out: 12 bytes per chunk = {type, n, first, 0, idx[8]} with
+ * type 0 = plain, 1 = the diagonal's two edge coefficients, 2 = equal quant values (shared
+ * threshold work); idx = natural-order coefficient indices.  quant == NULL or uniform == 0
+ * gives the table-independent schedule.  Returns the chunk count (<= 64), or JPEGQS_ERR_ARG. */
+int jpegqs_cuda_chunk_schedule(const uint16_t *quant, int max_coefs, int uniform, uint8_t *out);
 
 #ifdef __cplusplus
 }

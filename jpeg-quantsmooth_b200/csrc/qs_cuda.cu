@@ -333,7 +333,14 @@ static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int 
 		q->Rs[i] = (float)(2 * qq) * (1.0f / (float)(1 << QS_SCALE_BITS));
 		q->m31[i] = (uint32_t)(((1ull << 31) + (uint32_t)qq - 1) / (uint32_t)qq);
 	}
-	q->nchunks = build_chunks(q->chunks, maxn, q->q, uniform);
+	{
+		QsChunk tmp[QS_MAX_CHUNKS * 2];
+		int n = build_chunks(tmp, maxn, q->q, uniform);
+		if (n > QS_MAX_CHUNKS) n = build_chunks(tmp, maxn, NULL, 0);   /* cannot happen for maxn 1..4 */
+		memset(q->chunks, 0, sizeof(q->chunks));
+		memcpy(q->chunks, tmp, (size_t)n * sizeof(QsChunk));
+		q->nchunks = n;
+	}
 	q->sched_slot = 0;      /* callers that smooth run assign_sched_slots over the upload */
 	*val_out = val;
 }
@@ -440,6 +447,16 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 	if (key == 6) { ctx->tune_slabs = value ? 1 : 0; return 0; }
 	if (key == 7) { if (value < 0) return JPEGQS_ERR_ARG; ctx->tune_wave = value; return 0; }
 	return JPEGQS_ERR_ARG;
+}
+extern "C" int jpegqs_cuda_chunk_schedule(const uint16_t *quant, int max_coefs, int uniform, uint8_t *out) {
+	if (max_coefs < 1 || max_coefs > 4 || !out) return JPEGQS_ERR_ARG;
+	uint16_t q[64];
+	if (quant) for (int i = 0; i < 64; i++) q[i] = quant[i] ? quant[i] : 1;       /* as quant_prepare */
+	QsChunk tmp[QS_MAX_CHUNKS * 2];
+	int n = build_chunks(tmp, max_coefs, quant ? q : NULL, quant ? uniform : 0);
+	if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
+	memcpy(out, tmp, (size_t)n * sizeof(QsChunk));
+	return n;
 }
 extern "C" void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
 		float *smooth_ms, int *smooth_launches) {

@@ -116,6 +116,22 @@ def orig_coef(coef: int, q: int) -> int:
     return load().jpegqs_cuda_orig_coef(coef, q)
 
 
+def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True):
+    """The smoothing kernel's chunk schedule for a quant table (or the table-independent one
+    for quant=None): list of (type, first, [natural-order coefficient indices]).  Host-only."""
+    lib = load()
+    lib.jpegqs_cuda_chunk_schedule.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    out = np.zeros((64, 12), dtype=np.uint8)
+    qp = None
+    if quant is not None:
+        qa = np.ascontiguousarray(quant, dtype=np.uint16).reshape(64)
+        qp = qa.ctypes.data
+    n = lib.jpegqs_cuda_chunk_schedule(qp, max_coefs, int(uniform), out.ctypes.data)
+    if n < 0:
+        raise QsError(f"jpegqs_cuda_chunk_schedule: {n}")
+    return [(int(r[0]), int(r[2]), [int(x) for x in r[4:4 + r[1]]]) for r in out[:n]]
+
+
 class PinnedArray:
     """int16 numpy view over pinned host memory from jpegqs_cuda_host_alloc."""
 

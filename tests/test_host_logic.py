@@ -57,3 +57,49 @@ def test_torch_generator_matches_numpy():
         for ca, cb in zip(a.comps, b.comps):
             assert np.array_equal(ca.coef, cb.coef.numpy())
             assert np.array_equal(ca.quant, cb.quant)
+
+
+# ---- chunk schedule of the smoothing kernel (host side of DESIGN.md 3.3) ---------------------
+def _check_schedule(sched, quant, max_coefs):
+    seen = []
+    diag_order = []
+    for typ, first, idx in sched:
+        assert 1 <= len(idx) <= (2 if typ == 1 else max_coefs)
+        s = {(i >> 3) + (i & 7) for i in idx}
+        assert len(s) == 1, "a chunk never crosses an anti-diagonal (refresh points, quantsmooth.h:313-322)"
+        s = s.pop()
+        if first:
+            diag_order.append(s)
+        else:
+            assert diag_order and diag_order[-1] == s
+        if typ == 1:                                  # row-0 and column-0 coefficient of the diagonal
+            assert idx == [s, s * 8] and s <= 7
+        else:
+            assert all((i >> 3) and (i & 7) for i in idx)
+        if typ == 2:
+            assert quant is not None and len(idx) >= 2
+            q = [int(quant[i]) or 1 for i in idx]
+            assert len(set(q)) == 1, "uniform chunks share one quant value"
+        seen += idx
+    assert diag_order == list(range(14, 0, -1)), "reverse zig-zag visiting order (quantsmooth.h:1403)"
+    assert sorted(seen) == list(range(1, 64)), "every AC coefficient exactly once"
+    assert len(sched) <= 64
+
+
+def test_chunk_schedule_covers_every_coefficient_once():
+    from jpegqs_b200 import cuda
+    rng = np.random.default_rng(7)
+    im = qs.synth.make_image(16, 16, "420")
+    tables = [None, im.comps[0].quant, im.comps[1].quant, np.full(64, 255, np.uint16), np.ones(64, np.uint16)]
+    for _ in range(40):
+        tables.append(rng.integers(0, 6, 64).astype(np.uint16))       # many ties, some zeros (-> 1)
+        tables.append(rng.integers(1, 2047, 64).astype(np.uint16))    # hardly any ties
+    for quant in tables:
+        for max_coefs in (1, 2, 3, 4):
+            for uniform in (False, True):
+                _check_schedule(cuda.chunk_schedule(quant, max_coefs, uniform), quant, max_coefs)
+    # the Annex-K chroma table: 46 of the 49 inner coefficients sit in shared-threshold chunks
+    shared = sum(len(idx) for typ, _, idx in cuda.chunk_schedule(im.comps[1].quant) if typ == 2)
+    assert shared == 46
+    assert all(typ != 2 for typ, _, _ in cuda.chunk_schedule(im.comps[1].quant, 4, False))
+    assert len(cuda.chunk_schedule(None)) == 25
