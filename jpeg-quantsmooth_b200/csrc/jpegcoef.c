@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <pthread.h>
+#include <unistd.h>
 #include "jpegcoef.h"
 
 /* zig-zag index -> natural (row-major) index, T.81 figure A.6 */
@@ -507,49 +509,187 @@ static void ehuff_optimal(jq_ehuff *h) {
 	h->nval = k;
 }
 
-static int bit_size(int v) { int n = 0; if (v < 0) v = -v; while (v) { n++; v >>= 1; } return n; }
+/* ---------------------------------------------------------------- entropy coding of the scan
+ * The one interleaved scan is cut into segments of MCU rows that worker threads code
+ * independently: a segment's DC predictors are the DC values of the last real blocks of the MCU
+ * row above it (padding blocks repeat the predictor, so they never change it), and its bits go
+ * to a private buffer WITHOUT byte stuffing.  The segments are then appended in order to the
+ * output, shifted to the running bit position and stuffed there.  The result is byte for byte
+ * what a sequential coder writes, whatever the number of threads. */
+static int jq_threads_wanted = 0;
+void jq_set_threads(int n) { jq_threads_wanted = n; }
 
-/* one block: either counts symbols (o == NULL) or emits them */
-static int enc_block(jq_out *o, const JCOEF *blk, int *pred, jq_ehuff *dc, jq_ehuff *ac) {
+static inline int bit_size(int v) { unsigned a = (unsigned)(v < 0 ? -v : v); return a ? 32 - __builtin_clz(a) : 0; }
+
+typedef struct {
+	unsigned char *p; size_t n, cap;     /* whole bytes, unstuffed */
+	uint64_t acc; int nacc;              /* pending bits (< 8 after a block) */
+	int fail;
+	char pad[128];                       /* workers write neighbouring entries: keep them on separate cache lines */
+} jq_seg;
+
+typedef struct {
+	jq_image *im; jvirt_barray_ptr *arrays;
+	const jq_ehuff *dc, *ac;             /* NULL: count symbols only */
+	JDIMENSION mcux, mcuy;
+	int nseg; volatile int next;         /* dynamic segment queue */
+	jq_seg *seg;                         /* [nseg] code bits */
+	long (*freq)[4][257];                /* [nseg] dc0, ac0, dc1, ac1 symbol counts */
+	volatile int range_error;
+} jq_enc;
+
+#define SEG_PUT(code, size) do { acc = (acc << (size)) | (uint64_t)(code); nacc += (size); } while (0)
+#define SEG_DRAIN() do { while (nacc >= 8) { nacc -= 8; *w++ = (unsigned char)(acc >> nacc); } } while (0)
+
+/* one block: counts symbols (sg == NULL) or appends its code bits to the segment */
+static inline int enc_block(jq_seg *sg, const JCOEF *blk, int *pred, const jq_ehuff *dc, const jq_ehuff *ac,
+		long *fdc, long *fac) {
 	int diff = blk[0] - *pred, s = bit_size(diff), i, run = 0;
 	*pred = blk[0];
 	if (s > 11) return -1;
-	if (!o) dc->freq[s]++;
-	else { out_bits(o, dc->code[s], dc->size[s]); if (s) out_bits(o, (unsigned)(diff < 0 ? diff - 1 : diff), s); }
-	for (i = 1; i < 64; i++) {
-		int v = blk[zz_nat[i]];
-		if (!v) { run++; continue; }
-		for (; run > 15; run -= 16) { if (!o) ac->freq[0xF0]++; else out_bits(o, ac->code[0xF0], ac->size[0xF0]); }
-		s = bit_size(v);
-		if (s > 10) return -1;
-		if (!o) ac->freq[run << 4 | s]++;
-		else { out_bits(o, ac->code[run << 4 | s], ac->size[run << 4 | s]); out_bits(o, (unsigned)(v < 0 ? v - 1 : v), s); }
-		run = 0;
+	if (!sg) {
+		fdc[s]++;
+		for (i = 1; i < 64; i++) {
+			int v = blk[zz_nat[i]];
+			if (!v) { run++; continue; }
+			for (; run > 15; run -= 16) fac[0xF0]++;
+			s = bit_size(v);
+			if (s > 10) return -1;
+			fac[run << 4 | s]++;
+			run = 0;
+		}
+		if (run) fac[0]++;
+		return 0;
 	}
-	if (run) { if (!o) ac->freq[0]++; else out_bits(o, ac->code[0], ac->size[0]); }
+	{
+		uint64_t acc = sg->acc; int nacc = sg->nacc;
+		unsigned char *w = sg->p + sg->n;            /* the caller reserved room for a whole block */
+		SEG_PUT(dc->code[s], dc->size[s]);
+		if (s) SEG_PUT((unsigned)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1), s);
+		SEG_DRAIN();
+		for (i = 1; i < 64; i++) {
+			int v = blk[zz_nat[i]], rs;
+			if (!v) { run++; continue; }
+			for (; run > 15; run -= 16) { SEG_PUT(ac->code[0xF0], ac->size[0xF0]); SEG_DRAIN(); }
+			s = bit_size(v);
+			if (s > 10) return -1;
+			rs = run << 4 | s;
+			SEG_PUT(ac->code[rs], ac->size[rs]);
+			SEG_PUT((unsigned)(v < 0 ? v - 1 : v) & ((1u << s) - 1), s);
+			SEG_DRAIN();
+			run = 0;
+		}
+		if (run) { SEG_PUT(ac->code[0], ac->size[0]); SEG_DRAIN(); }
+		sg->acc = acc & 0xFF; sg->nacc = nacc; sg->n = (size_t)(w - sg->p);
+	}
 	return 0;
 }
 
-static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff *dc, jq_ehuff *ac) {
-	struct jpeg_decompress_struct *ci = &im->cinfo;
-	int maxh = ci->max_h_samp_factor, maxv = ci->max_v_samp_factor, k, pred[MAX_COMPONENTS] = { 0 };
-	JDIMENSION mcux = (ci->image_width + 8 * maxh - 1) / (8 * maxh), mcuy = (ci->image_height + 8 * maxv - 1) / (8 * maxv), x, y;
+/* MCU rows [y0, y1): walk = 1 only tracks the DC predictors (used for the row above a segment) */
+static int enc_rows(jq_enc *e, JDIMENSION y0, JDIMENSION y1, int *pred, jq_seg *sg, long (*fr)[257], int walk) {
+	struct jpeg_decompress_struct *ci = &e->im->cinfo;
+	JDIMENSION x, y; int k;
 	static const JCOEF zero[64] = { 0 };
-	for (y = 0; y < mcuy; y++) for (x = 0; x < mcux; x++) for (k = 0; k < ci->num_components; k++) {
-		jpeg_component_info *c = &ci->comp_info[k]; int h, v, t = k ? 1 : 0;
-		for (v = 0; v < c->v_samp_factor; v++) for (h = 0; h < c->h_samp_factor; h++) {
-			JDIMENSION bx = x * c->h_samp_factor + h, by = y * c->v_samp_factor + v;
-			JCOEF dummy[64];
-			const JCOEF *blk;
-			if (bx < c->width_in_blocks && by < c->height_in_blocks)
-				blk = (*ci->mem->access_virt_barray)((j_common_ptr)ci, arrays[k], by, 1, FALSE)[0][bx];
-			else {                                       /* padding block: DC repeats, AC zero (like jctrans.c) */
-				memcpy(dummy, zero, sizeof(dummy)); dummy[0] = (JCOEF)pred[k]; blk = dummy;
+	for (y = y0; y < y1; y++) {
+		JBLOCKROW rows[MAX_COMPONENTS][4];
+		for (k = 0; k < ci->num_components; k++) {
+			jpeg_component_info *c = &ci->comp_info[k]; int v;
+			for (v = 0; v < c->v_samp_factor && v < 4; v++) {
+				JDIMENSION by = y * c->v_samp_factor + v;
+				rows[k][v] = by < c->height_in_blocks ?
+						(*ci->mem->access_virt_barray)((j_common_ptr)ci, e->arrays[k], by, 1, FALSE)[0] : NULL;
 			}
-			if (enc_block(o, blk, &pred[k], &dc[t], &ac[t])) return -1;
+		}
+		for (x = 0; x < e->mcux; x++) for (k = 0; k < ci->num_components; k++) {
+			jpeg_component_info *c = &ci->comp_info[k]; int h, v, t = k ? 1 : 0;
+			for (v = 0; v < c->v_samp_factor; v++) for (h = 0; h < c->h_samp_factor; h++) {
+				JDIMENSION bx = x * c->h_samp_factor + h;
+				JCOEF dummy[64];
+				const JCOEF *blk;
+				if (bx < c->width_in_blocks && rows[k][v]) blk = rows[k][v][bx];
+				else if (walk) continue;                     /* padding keeps the predictor */
+				else {                                       /* padding block: DC repeats, AC zero (like jctrans.c) */
+					memcpy(dummy, zero, sizeof(dummy)); dummy[0] = (JCOEF)pred[k]; blk = dummy;
+				}
+				if (walk) { pred[k] = blk[0]; continue; }
+				if (sg && sg->cap - sg->n < 512) {           /* a block is at most 1665 bits */
+					size_t nc = sg->cap ? sg->cap * 2 : 1 << 16; unsigned char *q = (unsigned char*)realloc(sg->p, nc);
+					if (!q) { sg->fail = 1; return -1; }
+					sg->p = q; sg->cap = nc;
+				}
+				if (enc_block(sg, blk, &pred[k], e->dc ? &e->dc[t] : NULL, e->ac ? &e->ac[t] : NULL,
+						fr ? fr[2 * t] : NULL, fr ? fr[2 * t + 1] : NULL)) return -1;
+			}
 		}
 	}
 	return 0;
+}
+
+static void *enc_worker(void *arg) {
+	jq_enc *e = (jq_enc*)arg;
+	for (;;) {
+		int i = __sync_fetch_and_add(&e->next, 1), pred[MAX_COMPONENTS] = { 0 };
+		JDIMENSION y0, y1;
+		if (i >= e->nseg) break;
+		y0 = (JDIMENSION)((uint64_t)e->mcuy * (unsigned)i / (unsigned)e->nseg);
+		y1 = (JDIMENSION)((uint64_t)e->mcuy * (unsigned)(i + 1) / (unsigned)e->nseg);
+		if (y0 > 0) enc_rows(e, y0 - 1, y0, pred, NULL, NULL, 1);
+		if (enc_rows(e, y0, y1, pred, e->dc ? &e->seg[i] : NULL, e->dc ? NULL : e->freq[i], 0) &&
+				!(e->dc && e->seg[i].fail)) e->range_error = 1;
+	}
+	return NULL;
+}
+
+static int enc_thread_count(JDIMENSION mcuy) {
+	int n = jq_threads_wanted;
+	const char *env = getenv("JPEGQS_CODEC_THREADS");
+	if (env && atoi(env) > 0) n = atoi(env);
+	if (n <= 0) { long c = sysconf(_SC_NPROCESSORS_ONLN); n = c > 0 ? (int)c : 1; if (n > 16) n = 16; }
+	if (n > 64) n = 64;
+	if ((JDIMENSION)n > mcuy) n = (int)mcuy;
+	return n < 1 ? 1 : n;
+}
+
+/* appends a segment's bits at the output's current bit position, stuffing FF bytes */
+static void out_segment(jq_out *o, const jq_seg *sg) {
+	size_t i = 0;
+	if (o->nacc == 0) {
+		for (; i < sg->n; i++) { unsigned b = sg->p[i]; out_byte(o, b); if (b == 0xFF) out_byte(o, 0); }
+	} else for (; i < sg->n; i++) out_bits(o, sg->p[i], 8);
+	if (sg->nacc) out_bits(o, (unsigned)sg->acc & ((1u << sg->nacc) - 1), sg->nacc);
+}
+
+/* counts symbols into dc/ac[].freq (o == NULL) or writes the entropy-coded segment to o */
+static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff *dc, jq_ehuff *ac) {
+	struct jpeg_decompress_struct *ci = &im->cinfo;
+	int maxh = ci->max_h_samp_factor, maxv = ci->max_v_samp_factor, nthr, i, j, k, rc = -1;
+	jq_enc e; pthread_t tid[64];
+	memset(&e, 0, sizeof(e));
+	e.im = im; e.arrays = arrays;
+	e.mcux = (ci->image_width + 8 * maxh - 1) / (8 * maxh); e.mcuy = (ci->image_height + 8 * maxv - 1) / (8 * maxv);
+	if (!e.mcuy || !e.mcux) return 0;
+	for (k = 0; k < ci->num_components; k++) if (ci->comp_info[k].v_samp_factor > 4) return -1;
+	nthr = enc_thread_count(e.mcuy);
+	e.nseg = nthr == 1 ? 1 : nthr * 4;
+	if ((JDIMENSION)e.nseg > e.mcuy) e.nseg = (int)e.mcuy;
+	if (o) { e.dc = dc; e.ac = ac; e.seg = (jq_seg*)calloc((size_t)e.nseg, sizeof(jq_seg)); if (!e.seg) return -1; }
+	else { e.freq = (long (*)[4][257])calloc((size_t)e.nseg, sizeof(*e.freq)); if (!e.freq) return -1; }
+	for (i = 1; i < nthr; i++) if (pthread_create(&tid[i], NULL, enc_worker, &e)) break;
+	nthr = i;                                            /* threads that really started (+ this one) */
+	enc_worker(&e);
+	for (i = 1; i < nthr; i++) pthread_join(tid[i], NULL);
+	if (!e.range_error) {
+		rc = 0;
+		if (o) {
+			for (i = 0; i < e.nseg; i++) { if (e.seg[i].fail) { o->fail = 1; break; } out_segment(o, &e.seg[i]); }
+		} else for (i = 0; i < e.nseg; i++) for (j = 0; j < 257; j++) {
+			dc[0].freq[j] += e.freq[i][0][j]; ac[0].freq[j] += e.freq[i][1][j];
+			dc[1].freq[j] += e.freq[i][2][j]; ac[1].freq[j] += e.freq[i][3][j];
+		}
+	}
+	if (e.seg) { for (i = 0; i < e.nseg; i++) free(e.seg[i].p); free(e.seg); }
+	free(e.freq);
+	return rc;
 }
 
 static void out_dht(jq_out *o, int tc_th, const jq_ehuff *h) {

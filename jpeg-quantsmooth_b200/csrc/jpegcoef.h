@@ -48,6 +48,10 @@ int jq_write(jq_image *im, jvirt_barray_ptr *arrays, int optimize, unsigned char
 
 void jq_free(jq_image *im);
 
+/* worker threads of the writer's entropy coder: 0 = one per processor (at most 16).  The output
+ * bytes do not depend on it.  The environment variable JPEGQS_CODEC_THREADS overrides. */
+void jq_set_threads(int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,28 @@ def test_codec_is_a_lossless_transcoder(jpegs, tmp_path, name, optimize):
     assert np.array_equal(_pixels(out), _pixels(out2))
 
 
+def test_writer_bytes_do_not_depend_on_the_thread_count(jpegs, tmp_path):
+    """The writer codes segments of MCU rows on worker threads and splices their bits: the file
+    must be byte for byte the sequential coder's (1 thread), also with -o and odd thread counts."""
+    for name in ("base420", "prog420", "gray", "rst", "base444"):
+        if name not in jpegs:
+            continue
+        for optimize in ([], ["-o"]):
+            want = None
+            for threads in ("1", "2", "3", "7", "64"):
+                out = str(tmp_path / f"t{threads}.jpg")
+                env = dict(os.environ, JPEGQS_CODEC_THREADS=threads)
+                assert subprocess.run([EXE, "-n", "0", "-i", "0"] + optimize + [jpegs[name], out], env=env).returncode == 0
+                got = open(out, "rb").read()
+                if want is None:
+                    want = got
+                assert got == want, (name, optimize, threads)
+            out = str(tmp_path / "tflag.jpg")             # the -t option, environment unset
+            env = {k: v for k, v in os.environ.items() if k != "JPEGQS_CODEC_THREADS"}
+            assert subprocess.run([EXE, "-n", "0", "-i", "0", "-t", "5"] + optimize + [jpegs[name], out], env=env).returncode == 0
+            assert open(out, "rb").read() == want
+
+
 def test_marker_copy_levels(jpegs, tmp_path):
     src = jpegs["base420"]
     for level, want_com, want_app in ((2, True, True), (1, True, False), (0, False, False)):
@@ -175,7 +197,7 @@ def test_codec_survives_corrupt_input(jpegs, tmp_path):
     csrc = os.path.join(ROOT, "jpeg-quantsmooth_b200", "csrc")
     r = subprocess.run(["/usr/bin/gcc", "-O1", "-g", "-fsanitize=address,undefined", "-DJPEGQS_NO_CUDA_RENDER",
                         "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"), "-I", csrc,
-                        "-o", exe, os.path.join(csrc, "jpegqs.c"), os.path.join(csrc, "jpegcoef.c"), str(stub)],
+                        "-o", exe, os.path.join(csrc, "jpegqs.c"), os.path.join(csrc, "jpegcoef.c"), str(stub), "-lpthread"],
                        capture_output=True, text=True)
     if r.returncode:
         pytest.skip("sanitizer build unavailable: " + r.stderr[-200:])
