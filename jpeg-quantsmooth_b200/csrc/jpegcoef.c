@@ -110,6 +110,18 @@ typedef struct {
 } jq_bits;
 
 static void bits_fill(jq_bits *b) {
+	/* fast path: eight bytes ahead without an FF (no stuffing, no marker) are taken at once */
+	if (!b->hit_marker && b->nbits <= 48 && b->end - b->p >= 8) {
+		uint64_t x, nx; int k = (64 - b->nbits) >> 3;
+		memcpy(&x, b->p, 8);
+		nx = ~x;
+		if (!((nx - 0x0101010101010101ULL) & ~nx & 0x8080808080808080ULL)) {
+			uint64_t be = __builtin_bswap64(x);          /* little-endian hosts only (x86-64, aarch64) */
+			b->buf = k == 8 ? be : (b->buf << (8 * k)) | (be >> (64 - 8 * k));
+			b->p += k; b->nbits += 8 * k;
+			return;
+		}
+	}
 	while (b->nbits <= 48) {
 		unsigned c = 0;
 		if (!b->hit_marker && b->p < b->end) {
@@ -161,12 +173,23 @@ static void dec_block_seq(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFP
 	t = huff_decode(b, &d->dc[s->td[k]]);
 	d->pred[c] += extend(bits_get(b, t & 15), t & 15);
 	blk[0] = (JCOEF)d->pred[c];
-	for (i = 1; i < 64; ) {
-		int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15;
-		if (!sz) { if (r != 15) break; i += 16; continue; }
-		i += r;
-		blk[zz_nat[i]] = (JCOEF)extend(bits_get(b, sz), sz);
-		i++;
+	{
+		const jq_dhuff *h = &d->ac[s->ta[k]];
+		for (i = 1; i < 64; ) {
+			/* one refill check per symbol: a code (<= 16 bits) and its value bits (<= 15) fit in 32 */
+			unsigned look, e, v; int rs, r, sz;
+			if (b->nbits < 32) bits_fill(b);
+			look = (unsigned)(b->buf >> (b->nbits - 16)) & 0xFFFF;
+			e = h->look[look >> 7];
+			if (e) { b->nbits -= (int)(e >> 8); rs = (int)(e & 255); }
+			else rs = huff_decode(b, h);
+			r = rs >> 4; sz = rs & 15;
+			if (!sz) { if (r != 15) break; i += 16; continue; }
+			i += r;
+			v = (unsigned)(b->buf >> (b->nbits - sz)) & ((1u << sz) - 1); b->nbits -= sz;
+			blk[zz_nat[i]] = (JCOEF)extend(v, sz);
+			i++;
+		}
 	}
 }
 
