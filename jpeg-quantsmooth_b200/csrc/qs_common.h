@@ -77,6 +77,7 @@ typedef struct {
 #define QS_IDCT_CLAMP 2       /* write coefficients back clamped to +-1023 (2670-2689) */
 #define QS_IDCT_NOPLANE 4     /* do not render pixels (dequantize/clamp only) */
 
+#ifdef QS_EXPERIMENTS
 /* Pair schedule (packed FP32x2 path): every coefficient of an anti-diagonal belongs to one
  * pair slot (two coefficients that advance through the same terms in the two lanes of
  * FMUL2/FADD2; a coefficient without partner gets an all-zero dummy lane).  Each slot owns an
@@ -88,5 +89,7 @@ typedef struct {
 	uint8_t idx[4];                 /* natural coefficient index per lane, 0xFF = dummy lane */
 } QsChunk2;
 #define QS_MAX_SLOTS 40
+
+#endif
 
 #endif

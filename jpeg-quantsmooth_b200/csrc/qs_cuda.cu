@@ -128,6 +128,7 @@ static int build_chunks(QsChunk *ch, int maxn, const uint16_t *q, int uniform) {
 	return n;
 }
 
+#ifdef QS_EXPERIMENTS
 /* pair schedule + interleaved pair tables of the packed FP32x2 path (qs_common.h QsChunk2):
  * per anti-diagonal the two edge coefficients form one pair, the others pair up in order, a
  * left-over coefficient gets a dummy lane.  out_tab: [nslots][size][2] floats. */
@@ -170,6 +171,8 @@ static void build_pair_tables(int flags, const uint8_t lanes[][2], int nslots, f
 		}
 	}
 }
+
+#endif
 
 /* ------------------------------------------------------------------------------------------ */
 struct jpegqs_cuda_ctx {
@@ -281,6 +284,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 			int n = build_chunks(ch, ctx->tune_maxn, NULL, 0);
 			CK(qs_set_chunks(ch, n));
 		}
+#ifdef QS_EXPERIMENTS
 		{
 			QsChunk2 ch2[QS_MAX_CHUNKS]; uint8_t lanes[QS_MAX_SLOTS][2]; int ns = 0;
 			int n2 = build_pairs(ch2, &ns, 2, lanes);
@@ -294,6 +298,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 			CK(cudaMalloc(&ctx->tab2_diag, (size_t)ns * QS_TAB_DIAG * 2 * sizeof(float)));
 			CK(cudaMemcpy(ctx->tab2_diag, t2.data(), (size_t)ns * QS_TAB_DIAG * 2 * sizeof(float), cudaMemcpyHostToDevice));
 		}
+#endif
 		CK(qs_smooth_configure());
 		CK(cudaMalloc(&ctx->jobs_dev, 2 * QS_MAX_JOBS * sizeof(QsJob)));
 		CK(cudaMalloc(&ctx->flags_dev, (QS_MAX_JOBS + 1) * sizeof(int)));
@@ -427,10 +432,18 @@ extern "C" void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on) { ctx->p
  * setting.  key 0: lock-step sub-partition groups (0/1); key 1: max coefficients per chunk (1..4) */
 extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) {
 	if (!ctx) return JPEGQS_ERR_ARG;
-	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 1 : value; return 0; }
+#ifdef QS_EXPERIMENTS
+	if (key == 0) { ctx->tune_sync = value < 0 || value > 2 ? 2 : value; return 0; }
+#else
+	if (key == 0) return value == 2 ? 0 : JPEGQS_ERR_UNSUPPORTED;                              /* experiments build only */
+#endif
+#ifdef QS_EXPERIMENTS
 	if (key == 4) { ctx->tune_x2 = value ? 1 : 0; return 0; }
-	if (key == 3) { ctx->tune_gs = value < 1 || value > 3 ? 1 : value; return 0; }
 	if (key == 2) { ctx->tune_wpg = value == 6 ? 6 : 4; return 0; }
+#else
+	if (key == 4 || key == 2) return value == (key == 4 ? 0 : 4) ? 0 : JPEGQS_ERR_UNSUPPORTED;   /* experiments build only */
+#endif
+	if (key == 3) return 0;                            /* retired */
 	if (key == 1) {
 		if (value < 1 || value > 4) return JPEGQS_ERR_ARG;
 		CK(cudaSetDevice(ctx->device));
@@ -701,10 +714,12 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	auto launch_smooth = [&](const QsJob *jd, int nj, int tiles, int clampv) -> int {
 		if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
 		if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, nj, tiles, flags, clampv, st));
+#ifdef QS_EXPERIMENTS
 		else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, nj, tiles,
 				(flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain, ctx->nslots2, tile_counter, flags, clampv,
 				ctx->num_sms, ctx->tune_sync, st));
-		else CK(qs_launch_smooth(jd, nj, tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+#endif
+		else CK(qs_launch_smooth(jd, nj, tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
 		if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 		ctx->launches++;
 		return 0;
@@ -1043,9 +1058,11 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, st));
+#ifdef QS_EXPERIMENTS
 	else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, njobs, tiles, (flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain,
 			ctx->nslots2, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, st));
-	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, ctx->tune_gs, st));
+#endif
+	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
 	return 0;
 }
 

@@ -25,13 +25,28 @@
 #include "qs_common.h"
 #include "qs_kernels.h"
 
+/* Phase clocks (measurement builds only, -DQS_PHASE_CLOCKS): every warp accumulates the SM
+ * clock cycles it spends in each phase of the smoothing kernel into shared memory and adds them
+ * to qs_phase_acc at the end; read back with qs_read_phase_clocks.  In lock step the four warps
+ * of a sub-partition are in the same phase, so cycles/4 per phase is sub-partition time. */
+#ifdef QS_PHASE_CLOCKS
+#define QS_NPHASE 16
+__device__ unsigned long long qs_phase_acc[QS_NPHASE];
+struct QsPh {
+	uint32_t t; uint32_t *acc;
+	__device__ __forceinline__ void start(uint32_t *a) { acc = a; t = (uint32_t)clock(); }
+	__device__ __forceinline__ void mark(int k) { uint32_t n = (uint32_t)clock(); acc[k] += n - t; t = n; }
+};
+#define QS_PH_MARK(ph, k) (ph).mark(k)
+#else
+struct QsPh {};
+#define QS_PH_MARK(ph, k) ((void)0)
+#endif
+
 /* table-independent schedule: used by a lock-step group whose warps work on components with
  * different schedules (their barrier sequences must match) */
 __constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
 __constant__ int c_nchunks;
-__constant__ QsChunk2 c_chunks2[QS_MAX_CHUNKS];
-__constant__ int c_nchunks2, c_nslots2;
-__constant__ unsigned long long c_one2;      /* {1.0f, 1.0f}, deliberately opaque to ptxas (see qs_add2) */
 
 /* ------------------------------------------------------------------------------------------
  * small helpers
@@ -547,7 +562,7 @@ __device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const
 
 template <int N, bool DIAG, int SYNC, bool UNI>
 __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph) {
 	const float *tab[N]; float Rs[N], a2[N], a3[N];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -555,22 +570,28 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 		int i = ch.idx[c];
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
+	QS_PH_MARK(ph, 4);
 	qs_sec_h<N, UNI>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 5);
 	qs_sec_border<N, UNI>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 6);
 	qs_sec_v<N, UNI>(pw, tab, Rs, a2, a3);
+	QS_PH_MARK(ph, 7);
 	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<N, UNI>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 8);
 #pragma unroll
 	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+	QS_PH_MARK(ph, 9);
 }
 
 /* the two edge coefficients of an anti-diagonal: idx[0] lies in row 0 (i <= 7: no vertical
  * terms), idx[1] in column 0 (i & 7 == 0: no horizontal terms) */
 template <bool DIAG, int SYNC>
 __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph) {
 	const float *tab[2]; float Rs[2], a2[2], a3[2];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -578,185 +599,26 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 		int i = ch.idx[c];
 		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
 	}
+	QS_PH_MARK(ph, 4);
 	qs_sec_h<1, false>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 5);
 	qs_sec_border<2, false>(pw, tab, Rs, a2, a3);
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 6);
 	qs_sec_v<1, false>(pw, tab + 1, Rs + 1, a2 + 1, a3 + 1);
+	QS_PH_MARK(ph, 7);
 	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<2, false>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 8);
 #pragma unroll
 	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+	QS_PH_MARK(ph, 9);
 }
 
-/* ------------------------------------------------------------------------------------------
- * Packed FP32x2 path.  Blackwell's FMUL2 / FADD2 (PTX mul/add.rn.f32x2) perform two IEEE-RN
- * FP32 operations per lane per issue slot at full rate (tools/ubench_f32x2.cu: 253 FP32
- * ops/clk/SM vs 114 scalar).  Two coefficients of an anti-diagonal advance through the same
- * pixel-difference terms in the two halves of 64-bit register pairs: per (term, pair)
- * 2 FADD.SAT + 5 FMUL2 + 2 FADD2 = 9 issue slots instead of 16, each lane still being the
- * reference's sequential, separately rounded sum (.rn forbids contraction into FFMA2).
- * ------------------------------------------------------------------------------------------ */
-typedef unsigned long long qs_u64;
-__device__ __forceinline__ qs_u64 qs_pk(float lo, float hi) {
-	qs_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void qs_unpk(qs_u64 v, float &lo, float &hi) {
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ qs_u64 qs_mul2(qs_u64 a, qs_u64 b) {
-	qs_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
-}
-/* a + b, per lane, IEEE RN.  NOT written as add.rn.f32x2: ptxas 12.9 contracts a mul.rn.f32x2
- * feeding an add.rn.f32x2 into one FFMA2 even with -fmad=false (it keeps the scalar mul.rn/add.rn
- * pair apart), which would drop the rounding of the product.  fma(b, 1.0, a) with the 1.0 pair
- * in a register ptxas cannot see through is exact (b*1 is exact, one rounding of the sum) and
- * cannot be merged with the producer of b. */
-__device__ __forceinline__ qs_u64 qs_add2(qs_u64 a, qs_u64 b, qs_u64 one) {
-	qs_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(b), "l"(one), "l"(a)); return r;
-}
-
-/* CORE (quantsmooth.h:1519-1520) for the two lanes of a pair; dd = {ds, ds}, w = {w_a, w_b} */
-__device__ __forceinline__ void qs_term2(qs_u64 dd, float nad, qs_u64 w, float Rsa, float Rsb,
-		qs_u64 &a2, qs_u64 &a3, qs_u64 one) {
-	float ta, tb;
-	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(ta) : "f"(Rsa), "f"(nad));
-	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(tb) : "f"(Rsb), "f"(nad));
-	qs_u64 t = qs_pk(ta, tb);
-	t = qs_mul2(t, t);
-	qs_u64 a0 = qs_mul2(dd, t), a1 = qs_mul2(w, t);
-	a2 = qs_add2(a2, qs_mul2(a0, a1), one);
-	a3 = qs_add2(a3, qs_mul2(a1, a1), one);
-}
-
-/* all terms of one row step for NP pairs; tab[c] = pair table (float2 per term) */
-template <int NP, int NT, class Prep>
-__device__ __forceinline__ void qs_terms_row2(const float *d, const float *const *tab, int off,
-		const float *Rs, qs_u64 *a2, qs_u64 *a3, qs_u64 one, Prep prep) {
-	qs_u64 dd[8]; float nad[8];
-#pragma unroll
-	for (int x = 0; x < NT; x++) { dd[x] = qs_pk(d[x], d[x]); nad[x] = -fabsf(d[x]); }
-#pragma unroll
-	for (int c = 0; c < NP; c++) {
-		const ulonglong2 *t = (const ulonglong2 *)(tab[c] + off * 2);
-		qs_u64 w[8];
-#pragma unroll
-		for (int k = 0; k < 4; k++) { ulonglong2 v = t[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
-#pragma unroll
-		for (int x = 0; x < NT; x++) qs_term2(dd[x], nad[x], w[x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
-		prep(c);
-	}
-}
-
-template <int NP>
-__device__ __forceinline__ void qs_prep_slice2(uint2 w, float *f, int c) {
-#pragma unroll
-	for (int j = 0; j < 8; j++) if (j * NP / 8 == c) f[j] = qs_px8(w, j);
-}
-
-template <int NP, bool DIAG>
-__device__ __forceinline__ void qs_pair_sections(const uint2 *pw, const float *const *tab, const float *Rs,
-		qs_u64 *a2, qs_u64 *a3) {
-	float d[8];
-	const qs_u64 one = c_one2;
-	{                                                   /* horizontal, quantsmooth.h:1527 */
-		float f[8];
-		qs_unpack8(pw[0], f);
-#pragma unroll
-		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
-#pragma unroll 1
-		for (int y = 0; y < 8; y++) {
-			uint2 wn = pw[((y + 1) & 7) * 32];
-			qs_terms_row2<NP, 7>(d, tab, y * 8, Rs, a2, a3, one, [&](int c) { qs_prep_slice2<NP>(wn, f, c); });
-#pragma unroll
-			for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
-		}
-	}
-	{                                                   /* border, quantsmooth.h:1529-1530 */
-		float fa[8], fb[8];
-		qs_unpack8(pw[0], fa); qs_unpack8(pw[10 * 32], fb);
-#pragma unroll
-		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
-#pragma unroll 1
-		for (int s = 0; s < 4; s++) {
-			int sn = (s + 1) & 3;
-			int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;
-			uint2 wa = pw[wi * 32], wb = pw[(10 + sn) * 32];
-			qs_terms_row2<NP, 8>(d, tab, 64 + s * 8, Rs, a2, a3, one,
-					[&](int c) { qs_prep_slice2<NP>(wa, fa, c); qs_prep_slice2<NP>(wb, fb, c); });
-#pragma unroll
-			for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
-		}
-	}
-	{                                                   /* vertical, quantsmooth.h:1531 */
-		float fp[8], fn[8];
-		qs_unpack8(pw[0], fn); qs_unpack8(pw[32], fp);
-#pragma unroll
-		for (int x = 0; x < 8; x++) d[x] = FS(fn[x], fp[x]);
-#pragma unroll 1
-		for (int y = 0; y < 7; y++) {
-			uint2 wn = pw[min(y + 2, 7) * 32];
-			qs_terms_row2<NP, 8>(d, tab, 96 + y * 8, Rs, a2, a3, one, [&](int c) { qs_prep_slice2<NP>(wn, fn, c); });
-#pragma unroll
-			for (int x = 0; x < 8; x++) { d[x] = FS(fp[x], fn[x]); fp[x] = fn[x]; }
-		}
-	}
-	if (DIAG) {                                         /* diagonals, quantsmooth.h:1533-1540 */
-		float fp[8], fn[8], d1[8], d2[8];
-		qs_unpack8(pw[0], fn); qs_unpack8(pw[32], fp);
-#pragma unroll
-		for (int x = 0; x < 7; x++) { d1[x] = FS(fn[x], fp[x + 1]); d2[x] = FS(fn[x + 1], fp[x]); }
-#pragma unroll 1
-		for (int y = 0; y < 7; y++) {
-			uint2 wn = pw[min(y + 2, 7) * 32];
-			qs_u64 e1[8], e2[8];
-#pragma unroll
-			for (int x = 0; x < 7; x++) { e1[x] = qs_pk(d1[x], d1[x]); e2[x] = qs_pk(d2[x], d2[x]); }
-#pragma unroll
-			for (int c = 0; c < NP; c++) {
-				const ulonglong2 *t = (const ulonglong2 *)(tab[c] + (160 + y * 16) * 2);
-				qs_u64 w[16];
-#pragma unroll
-				for (int k = 0; k < 8; k++) { ulonglong2 v = t[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
-#pragma unroll
-				for (int x = 0; x < 7; x++) {
-					qs_term2(e1[x], -fabsf(d1[x]), w[x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
-					qs_term2(e2[x], -fabsf(d2[x]), w[8 + x], Rs[2 * c], Rs[2 * c + 1], a2[c], a3[c], one);
-				}
-				qs_prep_slice2<NP>(wn, fn, c);
-			}
-#pragma unroll
-			for (int x = 0; x < 7; x++) { d1[x] = FS(fp[x], fn[x + 1]); d2[x] = FS(fp[x + 1], fn[x]); }
-#pragma unroll
-			for (int x = 0; x < 8; x++) fp[x] = fn[x];
-		}
-	}
-}
-
-template <int NP, bool DIAG>
-__device__ __forceinline__ void qs_chunk_pairs(const QsChunk2 &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
-	const float *tab[NP]; float Rs[2 * NP]; qs_u64 a2[NP], a3[NP];
-	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
-#pragma unroll
-	for (int c = 0; c < NP; c++) {
-		tab[c] = tabs + (int)ch.slot[c] * TS * 2;
-		a2[c] = 0ull; a3[c] = 0ull;
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			int i = ch.idx[2 * c + h];
-			Rs[2 * c + h] = i < 64 ? __ldg(&qd->Rs[i]) : 0.0f;
-		}
-	}
-	qs_pair_sections<NP, DIAG>(pw, tab, Rs, a2, a3);
-#pragma unroll
-	for (int c = 0; c < NP; c++) {
-		float x2a, x2b, x3a, x3b;
-		qs_unpk(a2[c], x2a, x2b); qs_unpk(a3[c], x3a, x3b);
-		if (ch.idx[2 * c] < 64) qs_coef_update(x2a, x3a, ch.idx[2 * c], qd, cs);
-		if (ch.idx[2 * c + 1] < 64) qs_coef_update(x2b, x3b, ch.idx[2 * c + 1], qd, cs);
-	}
-}
+#ifdef QS_EXPERIMENTS
+#include "qs_experiments.cuh"
+#endif
 
 /* IDCT of the lane's block from shared coefficients into the shared pixel words */
 __device__ __forceinline__ void qs_refresh(const uint32_t *cw, uint2 *pw) {
@@ -855,8 +717,13 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	__shared__ int s_tile[16];
 	__shared__ int s_sig[32];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+#ifdef QS_EXPERIMENTS
 	const bool X2 = (SYNC & QS_SYNC_X2) != 0;
 	const int tab_words = X2 ? c_nslots2 * 2 * TS : 64 * TS;
+#else
+	const bool X2 = false;
+	const int tab_words = 64 * TS;
+#endif
 	float *tabs = (float *)smem;
 	{
 		/* Stage the weight tables (40-80 KB) with one TMA bulk copy (cp.async.bulk, UBLKCP in
@@ -897,6 +764,13 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	const int left = total_tiles - a_tiles * WPG, lbase = left / G, lextra = left - lbase * G;
 	int gbar = (1 + grp) | ((WPG * 32) << 8);           /* barrier id | participating threads */
 	bool last = false;
+	QsPh ph;
+#ifdef QS_PHASE_CLOCKS
+	__shared__ uint32_t s_ph[32][QS_NPHASE];
+	for (int k = lane; k < QS_NPHASE; k += 32) s_ph[warp][k] = 0;
+	__syncwarp();
+	ph.start(s_ph[warp]);
+#endif
 
 	for (;;) {
 		int tile = 0;
@@ -922,6 +796,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		}
 		const int gsync = gbar;
 		const bool active = true;
+		QS_PH_MARK(ph, 0);
 		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 		int nblocks = job->nblocks;
 		int b = (tile - job->tile_begin) * 32 + lane;
@@ -987,7 +862,9 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			pw[8 * 32] = qs_gather_col(lo, 0);
 			pw[9 * 32] = qs_gather_col(hi, 3);
 		}
+		QS_PH_MARK(ph, 1);
 
+#ifdef QS_EXPERIMENTS
 		if (X2) {
 			int nch2 = c_nchunks2;
 #pragma unroll 1
@@ -999,6 +876,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
 			}
 		}
+#endif
 		int nch = X2 ? 0 : (mixed ? c_nchunks : __ldg(&qd->nchunks));
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
@@ -1012,23 +890,27 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 				ch.idx[4] = c2 & 255; ch.idx[5] = (c2 >> 8) & 255; ch.idx[6] = (c2 >> 16) & 255; ch.idx[7] = c2 >> 24;
 			}
 			qs_group_sync<SYNC>(gsync);
+			QS_PH_MARK(ph, 2);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
-			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync);
+			QS_PH_MARK(ph, 3);
+			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph);
 			else if (ch.type == 2) {
-				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
-				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
-				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync);
+				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
+				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
+				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
 			}
-			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
-			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
+			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
 		}
+		QS_PH_MARK(ph, 10);
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
 			qs_rebalance(qd, cs);
+		QS_PH_MARK(ph, 11);
 
 		if (valid) {
 			int4 *p = (int4 *)cptr;
@@ -1048,8 +930,22 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			}
 		}
 		__syncwarp();
+		QS_PH_MARK(ph, 12);
 	}
+#ifdef QS_PHASE_CLOCKS
+	__syncwarp();
+	if (lane < QS_NPHASE) atomicAdd(&qs_phase_acc[lane], (unsigned long long)s_ph[warp][lane]);
+#endif
 }
+
+#ifdef QS_PHASE_CLOCKS
+extern "C" int qs_read_phase_clocks(unsigned long long *out, int reset) {
+	unsigned long long z[QS_NPHASE] = { 0 };
+	if (cudaMemcpyFromSymbol(out, qs_phase_acc, sizeof(z)) != cudaSuccess) return -1;
+	if (reset && cudaMemcpyToSymbol(qs_phase_acc, z, sizeof(z)) != cudaSuccess) return -1;
+	return QS_NPHASE;
+}
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * LOW_QUALITY (q0-2) block function, quantsmooth.h:924-938 + 1162-1178 (scalar branch, which
@@ -1274,12 +1170,12 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
+#ifdef QS_EXPERIMENTS
 static qs_smooth_fn qs_smooth_variant_x2(int diag, int sync) {
 	if (diag) return sync == 1 ? qs_smooth_kernel<true, QS_SYNC(1, 4, 1) + QS_SYNC_X2> : qs_smooth_kernel<true, QS_SYNC(2, 4, 1) + QS_SYNC_X2>;
 	return sync == 1 ? qs_smooth_kernel<false, QS_SYNC(1, 4, 1) + QS_SYNC_X2> : qs_smooth_kernel<false, QS_SYNC(2, 4, 1) + QS_SYNC_X2>;
 }
-static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
-	(void)gs;    /* 2-3 independent groups per sub-partition were tried and rejected (profiles/README.md) */
+static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps) {
 	if (wps == 6) {
 		if (diag) return sync == 2 ? QS_V(true, 2, 6, 1) : QS_V(true, 1, 6, 1);
 		return sync == 2 ? QS_V(false, 2, 6, 1) : QS_V(false, 1, 6, 1);
@@ -1287,10 +1183,44 @@ static qs_smooth_fn qs_smooth_variant(int diag, int sync, int wps, int gs) {
 	if (diag) return sync == 2 ? QS_V(true, 2, 4, 1) : sync ? QS_V(true, 1, 4, 1) : QS_V(true, 0, 4, 1);
 	return sync == 2 ? QS_V(false, 2, 4, 1) : sync ? QS_V(false, 1, 4, 1) : QS_V(false, 0, 4, 1);
 }
+#else
+/* the shipped configuration: lock step with one barrier per chunk, 4 warps per sub-partition
+ * (everything else was measured slower, profiles/README.md; the variants live behind
+ * -DQS_EXPERIMENTS) */
+static qs_smooth_fn qs_smooth_variant(int diag, int, int) {
+	return diag ? QS_V(true, 2, 4, 1) : QS_V(false, 2, 4, 1);
+}
+#endif
 
 size_t qs_smooth_smem_bytes(int diag, int wpg) {
 	return (size_t)64 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 + (size_t)(wpg * 4) * QS_WARP_WORDS * 4;
 }
+
+cudaError_t qs_smooth_configure(void) {
+#ifdef QS_EXPERIMENTS
+	for (int d = 0; d < 2; d++) for (int wps = 4; wps <= 6; wps += 2)
+		for (int sy = 0; sy < 3; sy++) {
+			if (qs_smooth_smem_bytes(d, wps) > 227 * 1024) continue;
+			cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wps),
+					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wps));
+			if (e != cudaSuccess) return e;
+		}
+	for (int d = 0; d < 2; d++) for (int sy = 1; sy <= 2; sy++) {
+		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant_x2(d, sy),
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes_x2(d, QS_MAX_SLOTS));
+		if (e != cudaSuccess) return e;
+	}
+#else
+	for (int d = 0; d < 2; d++) {
+		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, 2, 4),
+				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, 4));
+		if (e != cudaSuccess) return e;
+	}
+#endif
+	return cudaSuccess;
+}
+
+#ifdef QS_EXPERIMENTS
 size_t qs_smooth_smem_bytes_x2(int diag, int nslots) {
 	return (size_t)nslots * 2 * (diag ? QS_TAB_DIAG : QS_TAB_PLAIN) * 4 + (size_t)16 * QS_WARP_WORDS * 4;
 }
@@ -1304,23 +1234,6 @@ cudaError_t qs_set_chunks2(const QsChunk2 *chunks, int n, int nslots) {
 	const unsigned long long one = 0x3f8000003f800000ull;
 	return cudaMemcpyToSymbol(c_one2, &one, sizeof(one));
 }
-
-cudaError_t qs_smooth_configure(void) {
-	for (int d = 0; d < 2; d++) for (int wps = 4; wps <= 6; wps += 2) for (int gs = 1; gs <= 3; gs++)
-		for (int sy = 0; sy < 3; sy++) {
-			if (qs_smooth_smem_bytes(d, wps) > 227 * 1024) continue;
-			cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant(d, sy, wps, gs),
-					cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes(d, wps));
-			if (e != cudaSuccess) return e;
-		}
-	for (int d = 0; d < 2; d++) for (int sy = 1; sy <= 2; sy++) {
-		cudaError_t e = cudaFuncSetAttribute(qs_smooth_variant_x2(d, sy),
-				cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qs_smooth_smem_bytes_x2(d, QS_MAX_SLOTS));
-		if (e != cudaSuccess) return e;
-	}
-	return cudaSuccess;
-}
-
 cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
 		int nslots, int *tile_counter, int flags, int clamp_out, int num_sms, int sync, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
@@ -1333,6 +1246,7 @@ cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tile
 			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
 	return cudaGetLastError();
 }
+#endif
 
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
 		int *bad_flags, cudaStream_t st) {
@@ -1343,18 +1257,21 @@ cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tile
 }
 
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, int gs, cudaStream_t st) {
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
 	int diag = (flags & QS_DIAGONALS) ? 1 : 0;
+#ifdef QS_EXPERIMENTS
 	if ((wpg != 4 && wpg != 6) || qs_smooth_smem_bytes(diag, wpg) > 227 * 1024) wpg = 4;
-	if (sync < 0 || sync > 2) sync = 1;
+	if (sync < 0 || sync > 2) sync = 2;
+#else
+	wpg = 4; sync = 2;
+#endif
 	int warps = wpg * 4;
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
-	if (gs < 1 || gs > 3 || (wpg == 4 && gs == 3)) gs = 1;
-	qs_smooth_variant(diag, sync, wpg, gs)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
+	qs_smooth_variant(diag, sync, wpg)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
 			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
 	return cudaGetLastError();
 }

@@ -25,7 +25,9 @@ class QsError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "csrc", "libjpegqs_b200.so")
+    # JPEGQS_B200_LIB: measurement builds of the same library (csrc/Makefile `experiments`,
+    # `phase`) for tools/; never another implementation - there is no fallback of any kind
+    return os.environ.get("JPEGQS_B200_LIB") or os.path.join(_HERE, "csrc", "libjpegqs_b200.so")
 
 
 class _Comp(C.Structure):

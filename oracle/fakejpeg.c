@@ -69,69 +69,105 @@ typedef struct {
 
 typedef int (*qs_fn)(j_decompress_ptr, jvirt_barray_ptr*, jpegqs_control_t*);
 
-int fakejpeg_call(qs_fn fn, fake_image *im, jpegqs_control_t *opts) {
+/* A session keeps the fake decompress object alive between calls, so that a benchmark can time
+ * fn(&ci, arrays, opts) alone - exactly what a libjpeg application spends inside do_quantsmooth
+ * (reference quantsmooth.c:550) - with the set-up (libjpeg's own decoding work in real life)
+ * outside the timed region:
+ *   s = fakejpeg_open(im); { fakejpeg_load(s, im); ret = fakejpeg_run(s, fn, opts); } ...
+ *   fakejpeg_store(s, im); fakejpeg_close(s);                                              */
+typedef struct {
 	struct jpeg_decompress_struct ci; fake_mem mem;
 	JQUANT_TBL tbl[4]; jpeg_component_info comp[4]; jvirt_barray_ptr arrays[4];
-	int i, c, ret; JDIMENSION y;
-	memset(&ci, 0, sizeof(ci)); memset(&mem, 0, sizeof(mem));
-	memset(tbl, 0, sizeof(tbl)); memset(comp, 0, sizeof(comp));
-	mem.pub.request_virt_barray = fake_request;
-	mem.pub.realize_virt_arrays = fake_realize;
-	mem.pub.access_virt_barray = fake_access;
-	mem.scatter = im->scatter_rows;
-	ci.mem = &mem.pub;
-	ci.image_width = im->image_width; ci.image_height = im->image_height;
-	ci.num_components = im->num_components;
-	ci.jpeg_color_space = (J_COLOR_SPACE)im->color_space;
-	ci.comp_info = comp;
+} fake_session;
+
+static void fake_setup(fake_session *s, const fake_image *im, int reuse_arrays) {
+	int i, c; JDIMENSION y;
+	jvirt_barray_ptr keep[4]; struct jvirt_barray_control *head = NULL;
+	if (reuse_arrays) { memcpy(keep, s->arrays, sizeof(keep)); head = s->mem.head; }
+	memset(s, 0, sizeof(*s));
+	if (reuse_arrays) { memcpy(s->arrays, keep, sizeof(keep)); s->mem.head = head; }
+	s->mem.pub.request_virt_barray = fake_request;
+	s->mem.pub.realize_virt_arrays = fake_realize;
+	s->mem.pub.access_virt_barray = fake_access;
+	s->mem.scatter = im->scatter_rows;
+	s->ci.mem = &s->mem.pub;
+	s->ci.image_width = im->image_width; s->ci.image_height = im->image_height;
+	s->ci.num_components = im->num_components;
+	s->ci.jpeg_color_space = (J_COLOR_SPACE)im->color_space;
+	s->ci.comp_info = s->comp;
 	for (i = 0; i < 4; i++) {
-		memcpy(tbl[i].quantval, im->quant[i], sizeof(tbl[i].quantval));
-		ci.quant_tbl_ptrs[i] = (im->slot_present >> i) & 1 ? &tbl[i] : NULL;
+		memcpy(s->tbl[i].quantval, im->quant[i], sizeof(s->tbl[i].quantval));
+		s->ci.quant_tbl_ptrs[i] = (im->slot_present >> i) & 1 ? &s->tbl[i] : NULL;
 	}
 	for (c = 0; c < im->num_components; c++) {
 		size_t rowb = (size_t)im->width_in_blocks[c] * sizeof(JBLOCK);
-		comp[c].component_index = c; comp[c].component_id = c + 1;
-		comp[c].h_samp_factor = im->h_samp[c]; comp[c].v_samp_factor = im->v_samp[c];
-		comp[c].quant_tbl_no = im->quant_tbl_no[c];
-		comp[c].width_in_blocks = im->width_in_blocks[c];
-		comp[c].height_in_blocks = im->height_in_blocks[c];
-		comp[c].quant_table = ci.quant_tbl_ptrs[im->quant_tbl_no[c] & 3];
-		if (comp[c].h_samp_factor > ci.max_h_samp_factor) ci.max_h_samp_factor = comp[c].h_samp_factor;
-		if (comp[c].v_samp_factor > ci.max_v_samp_factor) ci.max_v_samp_factor = comp[c].v_samp_factor;
-		arrays[c] = fake_request((j_common_ptr)&ci, JPOOL_IMAGE, FALSE,
+		jpeg_component_info *cp = &s->comp[c];
+		cp->component_index = c; cp->component_id = c + 1;
+		cp->h_samp_factor = im->h_samp[c]; cp->v_samp_factor = im->v_samp[c];
+		cp->quant_tbl_no = im->quant_tbl_no[c];
+		cp->width_in_blocks = im->width_in_blocks[c];
+		cp->height_in_blocks = im->height_in_blocks[c];
+		cp->quant_table = s->ci.quant_tbl_ptrs[im->quant_tbl_no[c] & 3];
+		if (cp->h_samp_factor > s->ci.max_h_samp_factor) s->ci.max_h_samp_factor = cp->h_samp_factor;
+		if (cp->v_samp_factor > s->ci.max_v_samp_factor) s->ci.max_v_samp_factor = cp->v_samp_factor;
+		if (!s->arrays[c]) s->arrays[c] = fake_request((j_common_ptr)&s->ci, JPOOL_IMAGE, FALSE,
 				im->width_in_blocks[c], im->height_in_blocks[c], 1);
 		for (y = 0; y < im->height_in_blocks[c]; y++)
-			memcpy(arrays[c]->rows[y], (char*)im->coef[c] + y * rowb, rowb);
+			memcpy(s->arrays[c]->rows[y], (char*)im->coef[c] + y * rowb, rowb);
 	}
+}
 
-	ret = fn(&ci, arrays, opts);
-
+static void fake_store(fake_session *s, fake_image *im) {
+	int i, c; JDIMENSION y;
 	im->upsampled = 0;
 	for (c = 0; c < im->num_components; c++) {
-		int replaced = arrays[c]->w != im->width_in_blocks[c] ||
-				arrays[c]->h != im->height_in_blocks[c] ||
-				comp[c].width_in_blocks != im->width_in_blocks[c] ||
-				comp[c].height_in_blocks != im->height_in_blocks[c];
+		jvirt_barray_ptr a = s->arrays[c];
+		int replaced = a->w != im->width_in_blocks[c] || a->h != im->height_in_blocks[c] ||
+				s->comp[c].width_in_blocks != im->width_in_blocks[c] ||
+				s->comp[c].height_in_blocks != im->height_in_blocks[c];
 		int16_t *dst = im->coef[c]; size_t rowb;
 		if (replaced) {
 			im->upsampled = 1;
 			dst = (c >= 1 && c <= 2) ? im->coef_up[c - 1] : NULL;
 		}
-		im->width_in_blocks[c] = comp[c].width_in_blocks;
-		im->height_in_blocks[c] = comp[c].height_in_blocks;
-		im->h_samp[c] = comp[c].h_samp_factor; im->v_samp[c] = comp[c].v_samp_factor;
-		rowb = (size_t)arrays[c]->w * sizeof(JBLOCK);
-		if (dst) for (y = 0; y < arrays[c]->h; y++)
-			memcpy((char*)dst + y * rowb, arrays[c]->rows[y], rowb);
+		im->width_in_blocks[c] = s->comp[c].width_in_blocks;
+		im->height_in_blocks[c] = s->comp[c].height_in_blocks;
+		im->h_samp[c] = s->comp[c].h_samp_factor; im->v_samp[c] = s->comp[c].v_samp_factor;
+		rowb = (size_t)a->w * sizeof(JBLOCK);
+		if (dst) for (y = 0; y < a->h; y++)
+			memcpy((char*)dst + y * rowb, a->rows[y], rowb);
 	}
-	im->max_h_samp = ci.max_h_samp_factor; im->max_v_samp = ci.max_v_samp_factor;
-	for (i = 0; i < 4; i++) memcpy(im->quant[i], tbl[i].quantval, sizeof(tbl[i].quantval));
+	im->max_h_samp = s->ci.max_h_samp_factor; im->max_v_samp = s->ci.max_v_samp_factor;
+	for (i = 0; i < 4; i++) memcpy(im->quant[i], s->tbl[i].quantval, sizeof(s->tbl[i].quantval));
+}
 
-	while (mem.head) {
-		struct jvirt_barray_control *a = mem.head; mem.head = a->next;
+static void fake_free(fake_session *s) {
+	JDIMENSION y;
+	while (s->mem.head) {
+		struct jvirt_barray_control *a = s->mem.head; s->mem.head = a->next;
 		if (a->data) free(a->data);
 		else for (y = 0; y < a->h; y++) free(a->rows[y]);
 		free(a->rows); free(a);
 	}
+}
+
+fake_session *fakejpeg_open(const fake_image *im) {
+	fake_session *s = calloc(1, sizeof(*s));
+	if (s) fake_setup(s, im, 0);
+	return s;
+}
+/* (re)load the input coefficients and tables of `im` into the session's arrays; only valid
+ * while the geometry is the original one (i.e. not after an UPSAMPLE_UV run) */
+void fakejpeg_load(fake_session *s, const fake_image *im) { fake_setup(s, im, 1); }
+int fakejpeg_run(fake_session *s, qs_fn fn, jpegqs_control_t *opts) { return fn(&s->ci, s->arrays, opts); }
+void fakejpeg_store(fake_session *s, fake_image *im) { fake_store(s, im); }
+void fakejpeg_close(fake_session *s) { if (s) { fake_free(s); free(s); } }
+
+int fakejpeg_call(qs_fn fn, fake_image *im, jpegqs_control_t *opts) {
+	fake_session s; int ret;
+	fake_setup(&s, im, 0);
+	ret = fn(&s.ci, s.arrays, opts);
+	fake_store(&s, im);
+	fake_free(&s);
 	return ret;
 }

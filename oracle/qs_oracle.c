@@ -248,10 +248,17 @@ static float regress_scale(const uint8_t *A, const uint8_t *B, int stride, int32
  *      image  -> top-left pixel of this block in the component's sample plane
  *      image2 -> same position in the down-sampled luma plane, or NULL
  *      tables -> qso_tables() output (unused with LOW_QUALITY, quantsmooth.h:924-938, 1162-1178). */
+/* measurement probe (tools/refresh_stats.py): per block, bit s-1 = "a coefficient of
+ * anti-diagonal s changed in the last pass", i.e. the reference's need_refresh at the start of
+ * the next diagonal.  Off unless qso_set_change_probe was called. */
+static const int16_t *probe_base; static uint16_t *probe_out;
+void qso_set_change_probe(const int16_t *coef_base, uint16_t *out) { probe_base = coef_base; probe_out = out; }
+
 void qso_smooth_block(int16_t *coef, const uint16_t *q, const uint8_t *image,
 		const uint8_t *image2, int stride, int flags, const float *tables, int luma) {
 	uint8_t buf[64], border[32]; int k, x, y, need_refresh = 1;
 	int tsize = qso_table_size(flags);
+	unsigned probe_mask = 0;
 
 	if (image2) {                                             /* 577-579, 894-921 */
 		float fbuf[64];
@@ -331,8 +338,10 @@ void qso_smooth_block(int16_t *coef, const uint16_t *q, const uint8_t *image,
 			if (add < dl) add = dl;
 			coef[i] = (int16_t)add;
 			need_refresh |= add ^ c;
+			if (add != c) probe_mask |= 1u << ((i >> 3) + (i & 7) - 1);
 		}
 	}
+	if (probe_out) probe_out[(coef - probe_base) / 64] = (uint16_t)probe_mask;
 
 rebalance:
 	if (flags & QSO_NO_REBALANCE) return;                                     /* 1566-1568 */

@@ -125,6 +125,82 @@ def run_libjpeg_boundary(fn_ptr, image, flags, niter, threads=0, progprec=0, pro
     return ret, out
 
 
+class BoundarySession:
+    """A live fake `j_decompress_ptr` + coefficient arrays (oracle/fakejpeg.c session API):
+    `run(fn_ptr, flags, niter)` calls fn(&cinfo, coef_arrays, &opts) and nothing else, so a
+    benchmark can time exactly the drop-in call; `load()` restores the input, `result()` copies
+    the arrays out.  scatter_rows: every block row separately malloc'd (pageable, non-adjacent),
+    which is how libjpeg's memory manager hands rows over."""
+
+    def __init__(self, image, scatter_rows=True):
+        self.image = image.clone()
+        self.fi = fi = FakeImage()
+        out = self.image
+        fi.num_components = len(out.comps)
+        fi.color_space = out.colorspace
+        fi.image_width, fi.image_height = out.width, out.height
+        fi.scatter_rows = int(scatter_rows)
+        slots = 0
+        for i, c in enumerate(out.comps):
+            fi.h_samp[i], fi.v_samp[i], fi.quant_tbl_no[i] = c.h_samp, c.v_samp, c.quant_tbl_no
+            fi.width_in_blocks[i], fi.height_in_blocks[i] = c.wblk, c.hblk
+            c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+            fi.coef[i] = c.coef.ctypes.data
+            if c.quant is not None:
+                slots |= 1 << c.quant_tbl_no
+                for k in range(64):
+                    fi.quant[c.quant_tbl_no][k] = int(c.quant[k])
+        fi.slot_present = slots
+        self.ups = []
+        if len(out.comps) >= 3:
+            y = out.comps[0]
+            for j in range(2):
+                a = np.zeros((y.hblk, y.wblk, 64), dtype=np.int16)
+                self.ups.append(a)
+                fi.coef_up[j] = a.ctypes.data
+        lib = fakejpeg()
+        lib.fakejpeg_open.restype = C.c_void_p
+        lib.fakejpeg_open.argtypes = [C.POINTER(FakeImage)]
+        lib.fakejpeg_load.argtypes = [C.c_void_p, C.POINTER(FakeImage)]
+        lib.fakejpeg_run.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Control)]
+        lib.fakejpeg_run.restype = C.c_int
+        lib.fakejpeg_store.argtypes = [C.c_void_p, C.POINTER(FakeImage)]
+        lib.fakejpeg_close.argtypes = [C.c_void_p]
+        self.lib = lib
+        self.h = lib.fakejpeg_open(C.byref(fi))
+
+    def load(self):
+        self.lib.fakejpeg_load(self.h, C.byref(self.fi))
+
+    def run(self, fn_ptr, flags, niter, threads=0):
+        ctl = Control(flags=flags, niter=niter, threads=threads, progprec=0)
+        return self.lib.fakejpeg_run(self.h, C.cast(fn_ptr, C.c_void_p), C.byref(ctl))
+
+    def result(self):
+        """Copies the arrays out (into a clone of the input image)."""
+        out = self.image.clone()
+        fi = FakeImage.from_buffer_copy(self.fi)
+        keep, ups = [], []
+        for i, c in enumerate(out.comps):
+            c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+            fi.coef[i] = c.coef.ctypes.data
+        for j in range(len(self.ups)):
+            a = np.zeros_like(self.ups[j]); ups.append(a); fi.coef_up[j] = a.ctypes.data
+        self.lib.fakejpeg_store(self.h, C.byref(fi))
+        for i, c in enumerate(out.comps):
+            if fi.upsampled and i in (1, 2):
+                c.coef = ups[i - 1]
+            c.h_samp, c.v_samp = fi.h_samp[i], fi.v_samp[i]
+            if c.quant is not None:
+                c.quant = np.array(list(fi.quant[c.quant_tbl_no]), dtype=np.uint16)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.fakejpeg_close(self.h)
+            self.h = None
+
+
 def run_reference(image, flags, niter, variant="scalar", threads=0, **kw):
     lib = reflib(variant)
     return run_libjpeg_boundary(lib.qsref_do_quantsmooth, image, flags | 64, niter, threads=threads, **kw)

@@ -185,20 +185,22 @@ def test_run_slab_pass_level_luma_chroma_handover(ctx, flags, ss, w, h):
 
 
 def test_tuning_variants_are_bit_identical(ctx):
+    """The shipped library carries one lock-step configuration (the others live behind
+    -DQS_EXPERIMENTS); what can still vary is the chunk schedule: 1..4 coefficients per chunk,
+    with and without uniform-quant chunks.  Every schedule gives the oracle's bytes."""
     im = qs.synth.make_image(320, 240, "420")
-    _, want = ol.run_oracle(im, 1, 2)
-    _, want0 = ol.run_oracle(im, 0, 2)
+    want = {f: ol.run_oracle(im, f, 2)[1] for f in (0, 1)}
     try:
-        for wpg in (4, 6):
-            for sync in (0, 1, 2):
-                for maxn in (1, 2, 3, 4):
-                    ctx.set_tuning(0, sync); ctx.set_tuning(1, maxn); ctx.set_tuning(2, wpg)
-                    ctx.set_tuning(4, maxn & 1)        # alternate scalar / packed FP32x2 path
-                    _, out = ctx.do_quantsmooth(im, 1 if wpg == 4 else 0, 2)
-                    ref = want if wpg == 4 else want0
-                    assert ol.images_equal(out, ref), (sync, maxn, wpg)
+        for uni in (0, 1):
+            for maxn in (1, 2, 3, 4):
+                ctx.set_tuning(1, maxn); ctx.set_tuning(5, uni)
+                for f in (0, 1):
+                    _, out = ctx.do_quantsmooth(im, f, 2)
+                    assert ol.images_equal(out, want[f]), (uni, maxn, f)
+        with pytest.raises(qs.cuda.QsError):
+            ctx.set_tuning(0, 0)                      # free-running warps: experiments build only
     finally:
-        ctx.set_tuning(0, 2); ctx.set_tuning(1, 4); ctx.set_tuning(2, 4); ctx.set_tuning(4, 0)
+        ctx.set_tuning(1, 4); ctx.set_tuning(5, 1)
 
 
 # ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----
