@@ -328,37 +328,49 @@ def main():
     ms_per_step = ms_total / K
     value = mpix_job / (ms_per_step / 1e3)
 
-    # ---- e2e: the public host-buffer call (pinned host in, pinned host out) -------------
+    # ---- e2e: the drop-in call itself --------------------------------------------------------
+    # N=1: the library's exported do_quantsmooth(j_decompress_ptr, jvirt_barray_ptr*, jpegqs_control_t*)
+    # (include/libjpegqs.h, reference libjpegqs.h:47-48) driven by a fake libjpeg front end whose
+    # coefficient arrays are separately malloc'd, pageable block rows - what libjpeg's memory
+    # manager hands over.  Only the call is timed (a libjpeg application has the arrays already,
+    # reference quantsmooth.c:548-550); inside it: gather into pinned staging, H2D, kernels, D2H,
+    # scatter back into the rows.
     e2e = None
     if not args.no_e2e:
-        pinned = []
-        for _ in range(nbuf):
-            row = []
-            for c in im.comps:
-                p = qs.cuda.PinnedArray(c.coef.shape)
-                p.array[...] = c.coef
-                row.append(p)
-            pinned.append(row)
         h2d = sum(c.coef.nbytes for c in im.comps)
         d2h = h2d
+        if world == 1:
+            import ctypes as C
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib as ol                   # only its fake libjpeg front end (no smoothing code)
+            ol.ensure_built()
+            fn = C.cast(qs.cuda.load().do_quantsmooth, C.c_void_p)
+            sessions = [ol.BoundarySession(im, scatter_rows=True) for _ in range(nbuf)]
 
-        from jpegqs_b200.image import CoefImage, Component
-        works = []
-        for i in range(nbuf):                      # views over the pinned buffers, built up front
-            works.append(CoefImage(im.width, im.height, im.colorspace,
-                                   [Component(pinned[i][k].array, c.quant.copy(), c.h_samp, c.v_samp, c.quant_tbl_no)
-                                    for k, c in enumerate(im.comps)]))
+            def e2e_step(i):
+                ret = sessions[i].run(fn, FLAGS | 64, NITER)          # 64 = JPEGQS_TRANSCODE
+                if ret != 0:
+                    raise SystemExit(f"do_quantsmooth returned {ret}")
+            api = ("do_quantsmooth(j_decompress_ptr, jvirt_barray_ptr*, jpegqs_control_t*) of libjpegqs_b200.so, "
+                   "called through a fake libjpeg with scattered pageable block rows")
+        else:
+            pinned = []
+            for _ in range(nbuf):
+                row = []
+                for c in im.comps:
+                    p = qs.cuda.PinnedArray(c.coef.shape)
+                    p.array[...] = c.coef
+                    row.append(p)
+                pinned.append(row)
 
-        def e2e_step(i):
-            if world == 1:
-                ctx.do_quantsmooth(works[i], FLAGS, NITER, inplace=True)
-            else:
+            def e2e_step(i):
                 for k in range(len(im.comps)):
                     dev_bufs[i][k].copy_(torch.from_numpy(pinned[i][k].array), non_blocking=True)
                 step(i)
                 for k in range(len(im.comps)):
                     torch.from_numpy(pinned[i][k].array).copy_(dev_bufs[i][k], non_blocking=True)
                 torch.cuda.synchronize()
+            api = "pinned host -> slab tensors -> pass-level C ABI -> pinned host"
 
         for i in range(Wm):
             e2e_step(i)
@@ -373,12 +385,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": round(mpix_job * K / dt, 2), "unit": "Mpixels/s", "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": d2h * world, "ms_per_step": round(dt / K * 1e3, 3),
-               "api": "jpegqs_cuda_run_host (C ABI, pinned host buffers)" if world == 1 else
-                      "pinned host -> slab tensors -> pass-level C ABI -> pinned host"}
-        for row in pinned:
-            for p in row:
-                p.close()
+               "d2h_bytes_per_step": d2h * world, "ms_per_step": round(dt / K * 1e3, 3), "api": api}
+        if world == 1:
+            for sess in sessions:
+                sess.close()
+        else:
+            for row in pinned:
+                for p in row:
+                    p.close()
 
     clocks = sampler.stop() if rank == 0 else None     # after the e2e phase: more samples under load
 

@@ -44,6 +44,14 @@ typedef struct {
 	int16_t *coef_up;       /* out, comps 1..2 only: luma-sized array filled when
 	                           UPSAMPLE_UV replaces the chroma arrays (2691-2752); may be
 	                           NULL when UPSAMPLE_UV cannot trigger                        */
+	/* Host entry points only - libjpeg's own layout: hblk pointers to block rows of wblk*64
+	 * coefficients each, rows not necessarily adjacent (access_virt_barray, quantsmooth.h:
+	 * 2592-2594).  When rows != NULL it replaces coef (which may be NULL), rows_up likewise
+	 * replaces coef_up: the library gathers the rows into its pinned staging memory band by band
+	 * on worker threads, overlapped with the uploads, and scatters the results back the same
+	 * way.  The row memory must stay valid and untouched by the caller during the call. */
+	int16_t **rows;
+	int16_t **rows_up;
 } jpegqs_cuda_comp;
 
 typedef struct {
@@ -87,7 +95,10 @@ void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *i
  * key 4: 1 = packed FP32x2 pair path (FMUL2/FFMA2; exact, but measured slower), 0 = scalar (default) */
 int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value);
 
-/* pinned host memory for coefficient arrays (fast H2D/D2H); plain malloc'd memory works too */
+/* pinned host memory for coefficient arrays: the copy engines read / write it directly.  Plain
+ * malloc'd memory (flat or as block-row tables, see jpegqs_cuda_comp.rows) works too and goes
+ * through the context's pinned staging buffer, which is kept between calls (grow-only).
+ * Environment: JPEGQS_IO_THREADS = threads used for that gather / scatter (default: up to 8). */
 void *jpegqs_cuda_host_alloc(size_t bytes);
 void jpegqs_cuda_host_free(void *p);
 

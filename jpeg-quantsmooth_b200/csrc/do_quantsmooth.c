@@ -3,10 +3,11 @@
  * kept in C like the reference's host code.  They do what the reference driver does on
  * the libjpeg side of the boundary (reference quantsmooth.h:2404-2453 argument handling,
  * 2836-2876 result plumbing, 2880-2904 decode helpers) and hand the arithmetic to the CUDA
- * back end through the C ABI of include/jpegqs_cuda.h: each component's block rows are
- * gathered from libjpeg's virtual arrays (access_virt_barray, one row contiguous, rows not
- * necessarily adjacent - SURVEY.md 8b) into one pinned array, smoothed on the device, and
- * scattered back in place.
+ * back end through the C ABI of include/jpegqs_cuda.h: the block rows of libjpeg's virtual
+ * arrays (access_virt_barray, one row contiguous, rows not necessarily adjacent - SURVEY.md 8b)
+ * are passed as row-pointer tables; the back end gathers them into its pinned staging memory
+ * band by band on worker threads while the first bands are already being smoothed, and
+ * scatters the results back the same way (jpegqs_cuda_comp.rows).
  *
  * There is no CPU implementation here: if the CUDA back end cannot run, the call reports
  * the error on stderr and returns a negative code with the coefficients untouched.
@@ -45,10 +46,13 @@ EXTERN(void) jinit_upsampler(j_decompress_ptr);
 EXTERN(void) jinit_color_deconverter(j_decompress_ptr);
 #endif
 
-/* one lazily created context per device ordinal; callers are serialised like the
- * reference's plugin does with its own lock (irfanview/plugin.c:148-162) */
+/* one lazily created context per device ordinal.  The reference function is re-entrant; this one
+ * shares a device context (arena, staging, streams) between callers, so calls are serialised
+ * by a lock - like the reference's own plugin does around it (irfanview/plugin.c:148-162). */
+#include <pthread.h>
 #define QS_MAX_DEVICES 16
 static jpegqs_cuda_ctx *g_ctx[QS_MAX_DEVICES + 1];
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 
 static jpegqs_cuda_ctx *get_ctx(int ordinal_plus1) {
 	int slot = ordinal_plus1 < 0 || ordinal_plus1 > QS_MAX_DEVICES ? 0 : ordinal_plus1;
@@ -62,13 +66,49 @@ static jpegqs_cuda_ctx *get_ctx(int ordinal_plus1) {
 	return g_ctx[slot];
 }
 
+/* Block-row table of one virtual array: libjpeg keeps a whole-image coefficient array in memory
+ * as separately allocated row groups (jmemmgr.c alloc_barray), and access_virt_barray returns
+ * pointers into them.  The reference calls it once per row from inside its OpenMP loops
+ * (quantsmooth.h:2592-2594, 2706-2710); here every row is touched once, in order, on the
+ * calling thread and the pointers are handed to the back end, whose worker threads gather /
+ * scatter the rows while the device is already working.  A memory manager that pages the array
+ * through a backing store would hand out the same buffer for different rows: then (distinct ==
+ * 0) the rows are copied one by one on this thread instead. */
+static int16_t **row_table(j_decompress_ptr cinfo, jvirt_barray_ptr arr, JDIMENSION h, int *distinct) {
+	JDIMENSION y; int16_t **t = (int16_t**)malloc(sizeof(int16_t*) * (h ? h : 1));
+	if (!t) return NULL;
+	for (y = 0; y < h; y++)
+		t[y] = (int16_t*)(*cinfo->mem->access_virt_barray)((j_common_ptr)cinfo, arr, y, 1, TRUE)[0];
+	*distinct = 1;
+	if (h > 1) {
+		/* all pointers distinct <=> the array is fully resident (rows of a backing-store window repeat) */
+		int16_t **u = (int16_t**)malloc(sizeof(int16_t*) * h);
+		if (!u) { free(t); return NULL; }
+		memcpy(u, t, sizeof(int16_t*) * h);
+		{	/* shell sort: no libc comparator call per element, h <= 65500/8 */
+			JDIMENSION gap, i, j;
+			for (gap = h / 2; gap; gap /= 2)
+				for (i = gap; i < h; i++) {
+					int16_t *v = u[i];
+					for (j = i; j >= gap && (uintptr_t)u[j - gap] > (uintptr_t)v; j -= gap) u[j] = u[j - gap];
+					u[j] = v;
+				}
+		}
+		for (y = 1; y < h; y++) if (u[y] == u[y - 1]) { *distinct = 0; break; }
+		free(u);
+	}
+	return t;
+}
+
 JPEGQS_ATTR
 int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpegqs_control_t *opts) {
 	jpegqs_cuda_image img; jpegqs_cuda_ctx *ctx;
 	jpeg_component_info *comp = srcinfo->comp_info;
 	int ci, i, ret, ncomp = srcinfo->num_components, niter = opts->niter;
-	int need_downsample = 0, flags = opts->flags;
-	int16_t *host[JPEGQS_CUDA_MAX_COMP], *host_up[2] = { NULL, NULL };
+	int need_downsample = 0, flags = opts->flags, resident = 1, will_upsample;
+	int16_t **rows[JPEGQS_CUDA_MAX_COMP], **rows_up[2] = { NULL, NULL };
+	int16_t *flat[JPEGQS_CUDA_MAX_COMP], *flat_up[2] = { NULL, NULL };
+	jvirt_barray_ptr up[2] = { NULL, NULL };
 	JDIMENSION y;
 #ifdef WITH_LOG
 	int64_t t0 = 0;
@@ -98,43 +138,70 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 			comp[2].h_samp_factor == 1 && comp[2].v_samp_factor == 1) need_downsample = 1;
 	if (niter > JPEGQS_ITER_MAX) niter = JPEGQS_ITER_MAX;
 	if (niter <= 0 && !(flags & JPEGQS_UPSAMPLE_UV && need_downsample)) return 0;
+	will_upsample = need_downsample && flags & JPEGQS_UPSAMPLE_UV &&
+			(comp[0].h_samp_factor != 1 || comp[0].v_samp_factor != 1);
 
+	pthread_mutex_lock(&g_lock);
 	ctx = get_ctx((flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK);
-	if (!ctx) return JPEGQS_ERR_CUDA;
+	if (!ctx) { pthread_mutex_unlock(&g_lock); return JPEGQS_ERR_CUDA; }
 #ifdef WITH_LOG
 	if (flags & JPEGQS_INFO_CPU) logfmt("SIMD type: CUDA sm_100a (%s)\n", jpegqs_cuda_device_name(ctx));
 	LOG_COMP2                                          /* quantsmooth.h:2569-2572 */
 #endif
 
 	memset(&img, 0, sizeof(img));
-	memset(host, 0, sizeof(host));
+	memset(rows, 0, sizeof(rows)); memset(flat, 0, sizeof(flat));
 	img.ncomp = ncomp;
 	img.is_ycbcr = srcinfo->jpeg_color_space == JCS_YCbCr;
 	img.image_width = srcinfo->image_width; img.image_height = srcinfo->image_height;
 	ret = JPEGQS_ERR_CUDA;
+	if (will_upsample) {
+		/* the luma-sized chroma arrays of quantsmooth.h:2700-2702: requested up front so that
+		 * their rows exist while the device results stream back (if the run stops they stay
+		 * unused in the image pool, which libjpeg frees with the image) */
+		JDIMENSION W0 = comp[0].width_in_blocks, H0 = comp[0].height_in_blocks;
+		for (i = 0; i < 2; i++)
+			up[i] = (*srcinfo->mem->request_virt_barray)((j_common_ptr)srcinfo, JPOOL_IMAGE, FALSE, W0, H0, 1);
+		(*srcinfo->mem->realize_virt_arrays)((j_common_ptr)srcinfo);
+		if (!up[0] || !up[1]) goto done;               /* a memory manager that returns instead of error_exit */
+	}
 	for (ci = 0; ci < ncomp; ci++) {
-		jpegqs_cuda_comp *c = &img.comp[ci];
-		size_t rowb = (size_t)comp[ci].width_in_blocks * sizeof(JBLOCK);
+		jpegqs_cuda_comp *c = &img.comp[ci]; int distinct = 1;
 		c->wblk = comp[ci].width_in_blocks; c->hblk = comp[ci].height_in_blocks;
 		c->h_samp = comp[ci].h_samp_factor; c->v_samp = comp[ci].v_samp_factor;
 		c->has_qtbl = comp[ci].quant_table != NULL;
 		if (c->has_qtbl) memcpy(c->quant, comp[ci].quant_table->quantval, sizeof(c->quant));
-		host[ci] = (int16_t*)jpegqs_cuda_host_alloc(rowb * c->hblk);
-		if (!host[ci]) goto done;
-		c->coef = host[ci];
-		for (y = 0; y < c->hblk; y++) {
-			JBLOCKARRAY rows = (*srcinfo->mem->access_virt_barray)
-					((j_common_ptr)srcinfo, coef_arrays[ci], y, 1, TRUE);
-			memcpy((char*)host[ci] + y * rowb, rows[0], rowb);
+		rows[ci] = row_table(srcinfo, coef_arrays[ci], c->hblk, &distinct);
+		if (!rows[ci]) goto done;
+		resident &= distinct;
+	}
+	if (will_upsample) for (i = 0; i < 2; i++) {
+		int distinct = 1;
+		rows_up[i] = row_table(srcinfo, up[i], comp[0].height_in_blocks, &distinct);
+		if (!rows_up[i]) goto done;
+		resident &= distinct;
+	}
+	if (resident) {
+		for (ci = 0; ci < ncomp; ci++) img.comp[ci].rows = rows[ci];
+		for (i = 0; i < 2; i++) img.comp[1 + i].rows_up = rows_up[i];
+	} else {
+		/* paged arrays: one row at a time on this thread, into flat buffers the back end stages */
+		for (ci = 0; ci < ncomp; ci++) {
+			jpegqs_cuda_comp *c = &img.comp[ci]; size_t rowb = (size_t)c->wblk * sizeof(JBLOCK);
+			flat[ci] = (int16_t*)malloc(rowb * c->hblk + 1);
+			if (!flat[ci]) goto done;
+			c->coef = flat[ci];
+			for (y = 0; y < c->hblk; y++) {
+				JBLOCKARRAY r = (*srcinfo->mem->access_virt_barray)((j_common_ptr)srcinfo, coef_arrays[ci], y, 1, TRUE);
+				memcpy((char*)flat[ci] + y * rowb, r[0], rowb);
+			}
+		}
+		if (will_upsample) for (i = 0; i < 2; i++) {
+			flat_up[i] = (int16_t*)malloc((size_t)img.comp[0].wblk * img.comp[0].hblk * sizeof(JBLOCK) + 1);
+			if (!flat_up[i]) goto done;
+			img.comp[1 + i].coef_up = flat_up[i];
 		}
 	}
-	if (need_downsample && flags & JPEGQS_UPSAMPLE_UV &&
-			(comp[0].h_samp_factor != 1 || comp[0].v_samp_factor != 1))
-		for (i = 0; i < 2; i++) {
-			host_up[i] = (int16_t*)jpegqs_cuda_host_alloc((size_t)img.comp[0].wblk * img.comp[0].hblk * sizeof(JBLOCK));
-			if (!host_up[i]) goto done;
-			img.comp[1 + i].coef_up = host_up[i];
-		}
 
 	ret = jpegqs_cuda_run_host(ctx, &img, flags & JPEGQS_FLAGS_MASK, opts->niter, opts->progprec,
 			opts->progress, opts->userdata);
@@ -143,28 +210,26 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 		goto done;
 	}
 
-	for (ci = 0; ci < ncomp; ci++) {
-		jpegqs_cuda_comp *c = &img.comp[ci];
-		size_t rowb = (size_t)c->wblk * sizeof(JBLOCK);
-		if (img.upsampled && (ci == 1 || ci == 2)) continue;
-		for (y = 0; y < c->hblk; y++) {
-			JBLOCKARRAY rows = (*srcinfo->mem->access_virt_barray)
-					((j_common_ptr)srcinfo, coef_arrays[ci], y, 1, TRUE);
-			memcpy(rows[0], (char*)host[ci] + y * rowb, rowb);
+	if (!resident) {
+		for (ci = 0; ci < ncomp; ci++) {
+			jpegqs_cuda_comp *c = &img.comp[ci]; size_t rowb = (size_t)c->wblk * sizeof(JBLOCK);
+			if (img.upsampled && (ci == 1 || ci == 2)) continue;
+			for (y = 0; y < c->hblk; y++) {
+				JBLOCKARRAY r = (*srcinfo->mem->access_virt_barray)((j_common_ptr)srcinfo, coef_arrays[ci], y, 1, TRUE);
+				memcpy(r[0], (char*)flat[ci] + y * rowb, rowb);
+			}
+		}
+		if (img.upsampled) for (i = 0; i < 2; i++) {
+			size_t rowb = (size_t)comp[0].width_in_blocks * sizeof(JBLOCK);
+			for (y = 0; y < comp[0].height_in_blocks; y++) {
+				JBLOCKARRAY r = (*srcinfo->mem->access_virt_barray)((j_common_ptr)srcinfo, up[i], y, 1, TRUE);
+				memcpy(r[0], (char*)flat_up[i] + y * rowb, rowb);
+			}
 		}
 	}
-	if (img.upsampled) {                               /* quantsmooth.h:2700-2702, 2836-2849 */
+	if (img.upsampled) {                               /* quantsmooth.h:2836-2849 */
 		JDIMENSION W0 = comp[0].width_in_blocks, H0 = comp[0].height_in_blocks;
-		size_t rowb = (size_t)W0 * sizeof(JBLOCK);
-		jvirt_barray_ptr up[2];
-		for (i = 0; i < 2; i++)
-			up[i] = (*srcinfo->mem->request_virt_barray)((j_common_ptr)srcinfo, JPOOL_IMAGE, FALSE, W0, H0, 1);
-		(*srcinfo->mem->realize_virt_arrays)((j_common_ptr)srcinfo);
 		for (i = 0; i < 2; i++) {
-			for (y = 0; y < H0; y++) {
-				JBLOCKARRAY rows = (*srcinfo->mem->access_virt_barray)((j_common_ptr)srcinfo, up[i], y, 1, TRUE);
-				memcpy(rows[0], (char*)host_up[i] + y * rowb, rowb);
-			}
 			coef_arrays[1 + i] = up[i];
 			comp[1 + i].width_in_blocks = W0; comp[1 + i].height_in_blocks = H0;
 		}
@@ -201,8 +266,9 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 	}
 #endif
 done:
-	for (ci = 0; ci < ncomp; ci++) jpegqs_cuda_host_free(host[ci]);
-	jpegqs_cuda_host_free(host_up[0]); jpegqs_cuda_host_free(host_up[1]);
+	for (ci = 0; ci < ncomp; ci++) { free(rows[ci]); free(flat[ci]); }
+	for (i = 0; i < 2; i++) { free(rows_up[i]); free(flat_up[i]); }
+	pthread_mutex_unlock(&g_lock);
 	return ret;
 }
 

@@ -13,10 +13,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <memory>
 #include <unordered_map>
 #include <vector>
 #include "qs_common.h"
 #include "qs_kernels.h"
+#include "qs_hostio.h"
 #include "../../include/jpegqs_cuda.h"
 
 /* ------------------------------------------------------------------------------------------
@@ -179,7 +182,13 @@ struct jpegqs_cuda_ctx {
 	int device, num_sms;
 	char devname[256];
 	cudaStream_t stream;
-	cudaStream_t copy_stream;              /* H2D / D2H of the host entry points, overlapped with compute */
+	cudaStream_t up_stream, down_stream;   /* H2D / D2H of the host entry points, overlapped with compute */
+	/* host I/O of the host entry points (qs_hostio.h): pinned staging (grow-only), the gather /
+	 * scatter pool and the two queues that keep uploads and downloads going */
+	char *stage; size_t stage_cap;
+	int io_threads;
+	QsPool *pool; QsWorker *up, *down;
+	std::vector<cudaEvent_t> io_ev; size_t io_ev_used;
 	std::vector<cudaEvent_t> sync_ev;      /* per group: coefficients uploaded / group finished */
 	std::vector<cudaEvent_t> slab_ev;      /* per slab of a pipelined group: uploaded / smoothed */
 	float *tab_plain, *tab_diag;
@@ -228,7 +237,11 @@ extern "C" void jpegqs_cuda_destroy(jpegqs_cuda_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-	if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+	delete ctx->up; delete ctx->down; delete ctx->pool;      /* joins the threads */
+	if (ctx->up_stream) { cudaStreamSynchronize(ctx->up_stream); cudaStreamDestroy(ctx->up_stream); }
+	if (ctx->down_stream) { cudaStreamSynchronize(ctx->down_stream); cudaStreamDestroy(ctx->down_stream); }
+	for (cudaEvent_t e : ctx->io_ev) cudaEventDestroy(e);
+	if (ctx->stage) cudaFreeHost(ctx->stage);
 	for (cudaEvent_t e : ctx->sync_ev) cudaEventDestroy(e);
 	for (cudaEvent_t e : ctx->slab_ev) cudaEventDestroy(e);
 	cudaFree(ctx->tab_plain); cudaFree(ctx->tab_diag); cudaFree(ctx->tab2_plain); cudaFree(ctx->tab2_diag); cudaFree(ctx->quant_dev);
@@ -261,7 +274,16 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->device = device; ctx->num_sms = prop.multiProcessorCount;
 	snprintf(ctx->devname, sizeof(ctx->devname), "%s", prop.name);
 	ctx->tab2_plain = ctx->tab2_diag = NULL; ctx->nslots2 = 0;
-	ctx->stream = NULL; ctx->copy_stream = NULL; ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
+	ctx->stream = NULL; ctx->up_stream = ctx->down_stream = NULL;
+	ctx->stage = NULL; ctx->stage_cap = 0; ctx->pool = NULL; ctx->up = ctx->down = NULL; ctx->io_ev_used = 0;
+	{
+		const char *e = getenv("JPEGQS_IO_THREADS");
+		int hw = (int)std::thread::hardware_concurrency();
+		ctx->io_threads = e ? atoi(e) : (hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1);
+		if (ctx->io_threads < 1) ctx->io_threads = 1;
+		if (ctx->io_threads > 64) ctx->io_threads = 64;
+	}
+	ctx->tab_plain = ctx->tab_diag = NULL; ctx->quant_dev = NULL; ctx->quant_cap = 0;
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
@@ -269,7 +291,8 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
 		CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
 		std::vector<float> t(64 * QS_TAB_DIAG);
 		const float pre = 1073741824.0f;               /* 2^(2*QS_SCALE_BITS) */
@@ -328,6 +351,67 @@ static void *arena_take(jpegqs_cuda_ctx *ctx, size_t bytes) {
 	return ctx->arena + p;
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+/* pinned staging of the host entry points: grow-only, so a caller that smooths image after image
+ * pays cudaHostAlloc once (round 1 allocated and freed 100-300 MB of pinned memory per call) */
+static int stage_reserve(jpegqs_cuda_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->stage_cap) return 0;
+	if (ctx->stage) { CK(cudaFreeHost(ctx->stage)); ctx->stage = NULL; ctx->stage_cap = 0; }
+	size_t cap = bytes + bytes / 8 + (1 << 20);
+	CK(cudaHostAlloc((void **)&ctx->stage, cap, cudaHostAllocPortable));
+	ctx->stage_cap = cap;
+	return 0;
+}
+static int io_start(jpegqs_cuda_ctx *ctx) {
+	if (!ctx->pool) ctx->pool = new QsPool(ctx->io_threads - 1);   /* the caller of parallel_for works too */
+	if (!ctx->up) ctx->up = new QsWorker();
+	if (!ctx->down) ctx->down = new QsWorker();
+	return 0;
+}
+static int io_event(jpegqs_cuda_ctx *ctx, cudaEvent_t *e) {
+	if (ctx->io_ev_used == ctx->io_ev.size()) {
+		cudaEvent_t n; CK(cudaEventCreateWithFlags(&n, cudaEventDisableTiming | cudaEventBlockingSync));
+		ctx->io_ev.push_back(n);
+	}
+	*e = ctx->io_ev[ctx->io_ev_used++];
+	return 0;
+}
+/* is p memory the copy engines can read directly (cudaHostAlloc / cudaHostRegister)? */
+static bool is_pinned(const void *p) {
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return at.type == cudaMemoryTypeHost;
+}
+
+/* One contiguous run of block rows of one coefficient array moving between the host and the
+ * device.  rows != NULL: the host side is a table of separately allocated block rows (libjpeg's
+ * virtual arrays, or a flat pageable array cut into rows) that is gathered into / scattered from
+ * the pinned memory at `pin`; rows == NULL: `pin` is the caller's own pinned flat array. */
+struct IoSeg {
+	int16_t *dev, *pin; int16_t *const *rows;
+	int wblk, r0, r1;
+};
+/* gather (dir 0: rows -> pin) or scatter (dir 1: pin -> rows) the segments on the pool */
+static void io_rows_copy(QsPool *pool, const std::vector<IoSeg> &segs, int dir) {
+	struct Task { const IoSeg *s; int r0, r1; };
+	std::vector<Task> tasks;
+	for (const IoSeg &sg : segs) {
+		if (!sg.rows || sg.r1 <= sg.r0) continue;
+		size_t rowb = (size_t)sg.wblk * 128;
+		int step = (int)std::max<size_t>(1, (512 << 10) / std::max<size_t>(rowb, 1));    /* ~512 KB per task */
+		for (int r = sg.r0; r < sg.r1; r += step) tasks.push_back({ &sg, r, std::min(sg.r1, r + step) });
+	}
+	if (tasks.empty()) return;
+	auto run = [&](int i) {
+		const Task &t = tasks[i]; size_t rowb = (size_t)t.s->wblk * 128;
+		for (int r = t.r0; r < t.r1; r++) {
+			char *pin = (char *)t.s->pin + (size_t)r * rowb;
+			if (dir == 0) memcpy(pin, t.s->rows[r], rowb); else memcpy(t.s->rows[r], pin, rowb);
+		}
+	};
+	if (pool) pool->parallel_for((int)tasks.size(), run);
+	else for (int i = 0; i < (int)tasks.size(); i++) run(i);
+}
 
 static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int maxn = 4, int uniform = 1) {
 	int val = 0;
@@ -492,6 +576,10 @@ struct CompWork {
 	bool dequant_only;     /* stop was already set: quantsmooth.h:2551-2566 */
 	bool done_clamp;
 	bool downloaded;       /* the slab pipeline already sent the coefficients back */
+	/* host side (host entry points only): pinned memory the copy engines use, and the block-row
+	 * table it is gathered from / scattered to (NULL: pin is the caller's own pinned array) */
+	int16_t *pin; int16_t *const *rows;
+	int16_t *pin_up; int16_t *const *rows_up;
 };
 
 struct ImgState {
@@ -527,7 +615,10 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 
 	std::vector<ImgState> S(nimg);
 	std::vector<CompWork> all;
-	size_t bytes = 0; int nquant = 0, max_groups = 0;
+	size_t bytes = 0, stage_bytes = 0; int nquant = 0, max_groups = 0;
+	if (ctx->up) ctx->up->drain();                      /* nothing of an earlier (failed) call may linger */
+	if (ctx->down) ctx->down->drain();
+	ctx->io_ev_used = 0;
 	for (int n = 0; n < nimg; n++) {
 		jpegqs_cuda_image *im = &imgs[n]; ImgState &s = S[n];
 		memset(&s, 0, sizeof(s)); s.im = im; im->upsampled = 0; s.stop_ci = 1 << 30;
@@ -542,9 +633,13 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			return JPEGQS_ERR_ARG;
 		for (int ci = 0; ci < im->ncomp; ci++) {
 			jpegqs_cuda_comp *c = &im->comp[ci];
-			if (!c->coef && c->wblk && c->hblk) return JPEGQS_ERR_ARG;
+			bool have = c->coef || (!on_device && c->rows);
+			if (!have && c->wblk && c->hblk) return JPEGQS_ERR_ARG;
 			size_t cb = (size_t)c->wblk * c->hblk * 128;
-			if (!on_device) bytes += align256(cb);
+			if (!on_device) {
+				bytes += align256(cb);
+				if (c->rows || !is_pinned(c->coef)) stage_bytes += align256(cb);
+			}
 			bytes += align256(QS_PLANE_BYTES(c->wblk, c->hblk));
 			nquant++;
 		}
@@ -552,10 +647,14 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		if (sub) {
 			bytes += align256(QS_PLANE_BYTES(im->comp[1].wblk, im->comp[1].hblk));
 			if (flags & QS_UPSAMPLE_UV) for (int j = 0; j < 2; j++) {
-				if (!im->comp[1 + j].coef_up) return JPEGQS_ERR_ARG;
+				jpegqs_cuda_comp *c = &im->comp[1 + j];
+				if (!c->coef_up && !(!on_device && c->rows_up)) return JPEGQS_ERR_ARG;
 				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk;
 				bytes += align256(yb * 64);                 /* up-sampled pixel plane */
-				if (!on_device) bytes += align256(yb * 128);
+				if (!on_device) {
+					bytes += align256(yb * 128);
+					if (c->rows_up || !is_pinned(c->coef_up)) stage_bytes += align256(yb * 128);
+				}
 			}
 		}
 		/* host buffers: luma and chroma are separate phases even when independent, so that the
@@ -565,6 +664,17 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	}
 	if (arena_reserve(ctx, bytes + 4096)) return JPEGQS_ERR_CUDA;
 	if (quant_reserve(ctx, nquant)) return JPEGQS_ERR_CUDA;
+	if (stage_bytes && stage_reserve(ctx, stage_bytes)) return JPEGQS_ERR_CUDA;
+	size_t stage_pos = 0;
+	auto stage_take = [&](size_t b) { char *p = ctx->stage + stage_pos; stage_pos += align256(b); return (int16_t *)p; };
+	/* block-row tables made up for flat pageable arrays (one pointer per block row) */
+	std::vector<std::unique_ptr<int16_t *[]> > rowstore;
+	auto flat_rows = [&](int16_t *base, uint32_t wblk, uint32_t hblk) -> int16_t *const * {
+		rowstore.emplace_back(new int16_t *[hblk ? hblk : 1]);
+		int16_t **t = rowstore.back().get();
+		for (uint32_t y = 0; y < hblk; y++) t[y] = base + (size_t)y * wblk * 64;
+		return t;
+	};
 
 	/* carve device memory, upload coefficients and quant constants */
 	std::vector<QsQuantDev> qhost; qhost.reserve(nquant);
@@ -583,6 +693,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			if (on_device) w.coef_dev = c->coef;
 			else {
 				w.coef_dev = (int16_t *)arena_take(ctx, cb);
+				if (c->rows) { w.rows = c->rows; w.pin = stage_take(cb); }
+				else if (is_pinned(c->coef)) { w.rows = NULL; w.pin = c->coef; }
+				else { w.rows = flat_rows(c->coef, c->wblk, c->hblk); w.pin = stage_take(cb); }
 			}
 			w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
 			w.qslot = (int)qhost.size();
@@ -595,6 +708,12 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk;
 				s.mem_buf[j] = (uint8_t *)arena_take(ctx, yb * 64);
 				s.coef_up_dev[j] = on_device ? im->comp[1 + j].coef_up : (int16_t *)arena_take(ctx, yb * 128);
+				if (!on_device) {
+					jpegqs_cuda_comp *c = &im->comp[1 + j]; CompWork &w = W[n][1 + j];
+					if (c->rows_up) { w.rows_up = c->rows_up; w.pin_up = stage_take(yb * 128); }
+					else if (is_pinned(c->coef_up)) { w.rows_up = NULL; w.pin_up = c->coef_up; }
+					else { w.rows_up = flat_rows(c->coef_up, im->comp[0].wblk, im->comp[0].hblk); w.pin_up = stage_take(yb * 128); }
+				}
 			}
 		}
 	}
@@ -608,10 +727,31 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		else if (s.ngroups == 2) { *c0 = g ? 1 : 0; *c1 = g ? s.im->ncomp : 1; }
 		else { *c0 = 0; *c1 = s.im->ncomp; }
 	};
-	cudaStream_t cst = ctx->copy_stream;
+	cudaStream_t cup = ctx->up_stream, cdn = ctx->down_stream;
 	std::vector<SlabPlan> plan(max_groups > 0 ? max_groups : 1);
 	for (SlabPlan &pl : plan) pl.K = 0;
-	if (!on_device) {                                   /* uploads, group by group, on the copy stream */
+
+	/* ---- uploads.  The host side of a run is a list of units (one slab of one group, or a whole
+	 * group): gather the unit's block rows into pinned memory (pool threads), H2D on the upload
+	 * stream, record the unit's event.  With anything to gather the list runs on the context's
+	 * upload thread so that this thread can go on enqueueing kernels; up_wait(unit) makes the
+	 * compute stream wait for a unit (after its event has actually been recorded). */
+	struct UpUnit { std::vector<IoSeg> segs; cudaEvent_t ev; };
+	struct UpState { std::atomic<int> recorded; std::atomic<int> failed; char err[256]; };
+	std::vector<UpUnit> units;
+	UpState upst; upst.recorded = 0; upst.failed = 0; upst.err[0] = 0;
+	std::vector<int> unit_of_group(max_groups > 0 ? max_groups : 1, -1);
+	std::vector<std::vector<int> > unit_of_slab(max_groups > 0 ? max_groups : 1);
+	struct IoGuard {              /* no return path may leave a worker running on this frame's data */
+		jpegqs_cuda_ctx *c;
+		~IoGuard() { if (c->up) c->up->drain(); if (c->down) c->down->drain(); }
+	} io_guard = { ctx };
+	(void)io_guard;
+	auto seg_of = [&](const CompWork &w, int r0, int r1) {
+		IoSeg sg; sg.dev = w.coef_dev; sg.pin = w.pin; sg.rows = w.rows; sg.wblk = w.W; sg.r0 = r0; sg.r1 = r1;
+		return sg;
+	};
+	if (!on_device) {
 		while ((int)ctx->sync_ev.size() < 2 * max_groups) {
 			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->sync_ev.push_back(e);
 		}
@@ -629,13 +769,6 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 					CompWork &w = W[0][ci];
 					ok = w.c->has_qtbl && qval[0][ci] > 1 && qval[0][ci] < 0x800 && w.W > 0 && w.H > 0 &&
 							w.W == W[0][c0].W && w.H == W[0][c0].H;
-					if (ok) {
-						/* pageable host memory makes every async copy block the calling thread:
-						 * the pipeline only pays off (and only then is used) with pinned buffers */
-						cudaPointerAttributes at;
-						if (cudaPointerGetAttributes(&at, w.c->coef) != cudaSuccess) { cudaGetLastError(); ok = false; }
-						else ok = at.type == cudaMemoryTypeHost;
-					}
 				}
 				if (ok) {
 					int Wb = W[0][c0].W, Hb = W[0][c0].H, nc = c1 - c0;
@@ -656,29 +789,77 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			if (plan[g].K) {
 				int c0, c1; group_range(S[0], g, &c0, &c1);
 				for (int k = 0; k < plan[g].K; k++) {
-					for (int ci = c0; ci < c1; ci++) {
-						CompWork &w = W[0][ci];
-						size_t off = (size_t)plan[g].r[k] * w.W * 64, cnt = (size_t)(plan[g].r[k + 1] - plan[g].r[k]) * w.W * 64;
-						CK(cudaMemcpyAsync(w.coef_dev + off, w.c->coef + off, cnt * 2, cudaMemcpyHostToDevice, cst));
-					}
-					CK(cudaEventRecord(ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k], cst));
+					UpUnit u; u.ev = ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k];
+					for (int ci = c0; ci < c1; ci++) u.segs.push_back(seg_of(W[0][ci], plan[g].r[k], plan[g].r[k + 1]));
+					unit_of_slab[g].push_back((int)units.size());
+					units.push_back(std::move(u));
 				}
-				CK(cudaEventRecord(ctx->sync_ev[2 * g], cst));
+				unit_of_group[g] = (int)units.size() - 1;
 				continue;
 			}
+			UpUnit u; u.ev = ctx->sync_ev[2 * g];
 			for (int n = 0; n < nimg; n++) {
 				ImgState &s = S[n];
 				if (s.skip || g >= s.ngroups) continue;
 				int c0, c1; group_range(s, g, &c0, &c1);
-				for (int ci = c0; ci < c1; ci++) {
-					CompWork &w = W[n][ci];
-					size_t cb = (size_t)w.W * w.H * 128;
-					if (cb) CK(cudaMemcpyAsync(w.coef_dev, w.c->coef, cb, cudaMemcpyHostToDevice, cst));
-				}
+				for (int ci = c0; ci < c1; ci++) if (W[n][ci].W && W[n][ci].H) u.segs.push_back(seg_of(W[n][ci], 0, W[n][ci].H));
 			}
-			CK(cudaEventRecord(ctx->sync_ev[2 * g], cst));
+			unit_of_group[g] = (int)units.size();
+			units.push_back(std::move(u));
 		}
+		bool gather = false;
+		for (const UpUnit &u : units) for (const IoSeg &sg : u.segs) gather = gather || sg.rows != NULL;
+		if (gather && io_start(ctx)) return JPEGQS_ERR_CUDA;
+		QsPool *pool = ctx->pool; int devno = ctx->device;
+		auto run_units = [&units, &upst, pool, cup, devno]() {
+			cudaError_t e = cudaSetDevice(devno);
+			for (size_t i = 0; i < units.size() && e == cudaSuccess; i++) {
+				io_rows_copy(pool, units[i].segs, 0);
+				for (const IoSeg &sg : units[i].segs) {
+					size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
+					if (cnt && e == cudaSuccess)
+						e = cudaMemcpyAsync(sg.dev + off, sg.pin + off, cnt * 2, cudaMemcpyHostToDevice, cup);
+				}
+				if (e == cudaSuccess) e = cudaEventRecord(units[i].ev, cup);
+				if (e == cudaSuccess) upst.recorded.store((int)i + 1, std::memory_order_release);
+			}
+			if (e != cudaSuccess) {
+				snprintf(upst.err, sizeof(upst.err), "upload: %s", cudaGetErrorString(e));
+				upst.failed.store(1, std::memory_order_release);
+			}
+		};
+		if (gather) ctx->up->post(run_units); else run_units();
 	}
+	auto up_wait = [&](int unit) -> int {
+		if (unit < 0) return 0;
+		while (upst.recorded.load(std::memory_order_acquire) <= unit && !upst.failed.load(std::memory_order_acquire))
+			std::this_thread::yield();
+		if (upst.failed.load()) { snprintf(ctx->err, sizeof(ctx->err), "%s", upst.err); return JPEGQS_ERR_CUDA; }
+		CK(cudaStreamWaitEvent(st, units[unit].ev, 0));
+		return 0;
+	};
+	/* downloads: D2H on the download stream behind `after`; block-row tables are scattered by the
+	 * download thread + pool once the copy has landed in pinned memory */
+	auto download = [&](std::vector<IoSeg> segs, cudaEvent_t after) -> int {
+		CK(cudaStreamWaitEvent(cdn, after, 0));
+		bool scatter = false;
+		for (const IoSeg &sg : segs) {
+			size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
+			if (cnt) CK(cudaMemcpyAsync(sg.pin + off, sg.dev + off, cnt * 2, cudaMemcpyDeviceToHost, cdn));
+			scatter = scatter || sg.rows != NULL;
+		}
+		if (scatter) {
+			cudaEvent_t e;
+			if (io_event(ctx, &e) || io_start(ctx)) return JPEGQS_ERR_CUDA;
+			CK(cudaEventRecord(e, cdn));
+			QsPool *pool = ctx->pool; int devno = ctx->device;
+			ctx->down->post([segs, e, pool, devno]() {
+				cudaSetDevice(devno);
+				if (cudaEventSynchronize(e) == cudaSuccess) io_rows_copy(pool, segs, 1);
+			});
+		}
+		return 0;
+	};
 
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	int *bad_dev = ctx->flags_dev, *tile_counter = ctx->flags_dev + QS_MAX_JOBS;
@@ -727,7 +908,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 
 	for (int g = 0; g < max_groups; g++) {
 		bool slab_in = !on_device && plan[g].K > 0 && !S[0].stop;
-		if (!on_device && !slab_in) CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0));
+		if (!on_device && !slab_in && up_wait(unit_of_group[g])) return JPEGQS_ERR_CUDA;
 		/* ---- which components belong to this phase; per-component prelude 2484-2566 ---- */
 		std::vector<CompWork *> works;
 		int prog_cur = 0, prog_inc = 0;
@@ -764,12 +945,12 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			int c0, c1; group_range(S[0], g, &c0, &c1);
 			bool ok = (int)works.size() == c1 - c0;
 			for (CompWork *w : works) ok = ok && w->niter2 == works[0]->niter2 && w->extra == works[0]->extra && w->niter2 >= 1;
-			if (!ok) { slab_in = false; CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0)); }
+			if (!ok) { slab_in = false; if (up_wait(unit_of_group[g])) return JPEGQS_ERR_CUDA; }
 		}
 		/* the download pipeline needs the slab plan but not the upload pipeline, and vice versa:
 		 * a middle group's transfers hide behind its neighbours' kernels anyway */
 		bool slab_out = slab_in && works[0]->niter2 >= 2 && !works[0]->extra && g == S[0].ngroups - 1;
-		if (slab_in && g > 0) { slab_in = false; CK(cudaStreamWaitEvent(st, ctx->sync_ev[2 * g], 0)); }
+		if (slab_in && g > 0) { slab_in = false; if (up_wait(unit_of_group[g])) return JPEGQS_ERR_CUDA; }
 		for (int iter = 0; iter < max_pass; iter++) {
 			if (iter == 0 && slab_in) {
 				/* ---- iteration 0 behind the upload, slab by slab ---- */
@@ -779,7 +960,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				for (int k = 0; k <= pl.K; k++) {
 					const QsJob *jd; int tiles;
 					if (k < pl.K) {
-						CK(cudaStreamWaitEvent(st, ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k], 0));
+						if (up_wait(unit_of_slab[g][k])) return JPEGQS_ERR_CUDA;
 						std::vector<QsJob> jobs;
 						for (CompWork *w : works) jobs.push_back(make_slab_job(*w, NULL, pl.r[k], pl.r[k + 1]));
 						if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles)) return JPEGQS_ERR_CUDA;
@@ -808,7 +989,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 				 * fetch the group again and take the plain path, which implements the stop. */
 				for (CompWork *w : works) {
 					size_t cb = (size_t)w->W * w->H * 128;
-					CK(cudaMemcpyAsync(w->coef_dev, w->c->coef, cb, cudaMemcpyHostToDevice, st));
+					CK(cudaMemcpyAsync(w->coef_dev, w->pin, cb, cudaMemcpyHostToDevice, st));
 				}
 				slab_in = slab_out = false;
 			}
@@ -862,11 +1043,9 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 					if (launch_smooth(jd, (int)jobs.size(), tiles, 1)) return JPEGQS_ERR_CUDA;
 					cudaEvent_t e = ctx->slab_ev[(2 * g + 1) * QS_MAX_SLABS + k];
 					CK(cudaEventRecord(e, st));
-					CK(cudaStreamWaitEvent(cst, e, 0));
-					for (CompWork *w : works) {
-						size_t off = (size_t)pl.r[k] * w->W * 64, cnt = (size_t)(pl.r[k + 1] - pl.r[k]) * w->W * 64;
-						CK(cudaMemcpyAsync(w->c->coef + off, w->coef_dev + off, cnt * 2, cudaMemcpyDeviceToHost, cst));
-					}
+					std::vector<IoSeg> segs;
+					for (CompWork *w : works) segs.push_back(seg_of(*w, pl.r[k], pl.r[k + 1]));
+					if (download(std::move(segs), e)) return JPEGQS_ERR_CUDA;
 				}
 				for (CompWork *w : works) { w->done_clamp = true; w->downloaded = true; }
 				continue;
@@ -933,21 +1112,22 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		/* ---- downloads of this phase, on the copy stream, behind the phase's last kernel ---- */
 		if (!on_device) {
 			CK(cudaEventRecord(ctx->sync_ev[2 * g + 1], st));
-			CK(cudaStreamWaitEvent(cst, ctx->sync_ev[2 * g + 1], 0));
+			std::vector<IoSeg> segs;
 			for (int n = 0; n < nimg; n++) {
 				ImgState &s = S[n]; jpegqs_cuda_image *im = s.im;
 				if (s.skip || g >= s.ngroups) continue;
 				int c0, c1; group_range(s, g, &c0, &c1);
 				for (int ci = c0; ci < c1; ci++) {
 					CompWork &w = W[n][ci];
-					size_t cb = (size_t)w.W * w.H * 128;
-					if (cb && !w.downloaded) CK(cudaMemcpyAsync(w.c->coef, w.coef_dev, cb, cudaMemcpyDeviceToHost, cst));
+					if (w.W && w.H && !w.downloaded) segs.push_back(seg_of(w, 0, w.H));
 					if (s.image1 && !s.stop && ci >= 1 && ci <= 2) {
-						size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk * 128;
-						CK(cudaMemcpyAsync(w.c->coef_up, s.coef_up_dev[ci - 1], yb, cudaMemcpyDeviceToHost, cst));
+						IoSeg sg; sg.dev = s.coef_up_dev[ci - 1]; sg.pin = w.pin_up; sg.rows = w.rows_up;
+						sg.wblk = im->comp[0].wblk; sg.r0 = 0; sg.r1 = im->comp[0].hblk;
+						segs.push_back(sg);
 					}
 				}
 			}
+			if (download(std::move(segs), ctx->sync_ev[2 * g + 1])) return JPEGQS_ERR_CUDA;
 		}
 	}
 	CK(cudaEventRecord(ctx->ev1, st));
@@ -965,7 +1145,11 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		if (ret) ret[n] = s.stop;
 	}
 	CK(cudaStreamSynchronize(st));
-	if (!on_device) CK(cudaStreamSynchronize(cst));
+	if (!on_device) {
+		CK(cudaStreamSynchronize(cdn));
+		if (ctx->up) ctx->up->drain();
+		if (ctx->down) ctx->down->drain();              /* the last scatter has finished */
+	}
 	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 	if (prof_collect(ctx)) return JPEGQS_ERR_CUDA;
 	return 0;

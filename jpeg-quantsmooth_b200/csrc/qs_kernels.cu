@@ -45,8 +45,8 @@ struct QsPh {};
 
 /* table-independent schedule: used by a lock-step group whose warps work on components with
  * different schedules (their barrier sequences must match) */
-__constant__ QsChunk c_chunks[QS_MAX_CHUNKS];
-__constant__ int c_nchunks;
+__device__ QsChunk d_chunks[QS_MAX_CHUNKS];
+__device__ int d_nchunks;
 
 /* ------------------------------------------------------------------------------------------
  * small helpers
@@ -88,12 +88,17 @@ __device__ __forceinline__ int qs_cvtt_x86(float x) {
 /* ------------------------------------------------------------------------------------------
  * integer islow IDCT (reference idct.h:39-89 butterfly, 469-538 passes)
  * ------------------------------------------------------------------------------------------ */
+/* RND: rounding constant of the descale that follows (idct.h:469-538: +1024 before >> 11 in
+ * pass 1, +(257 << 17) before >> 18 in pass 2).  Every output is e_j +- t_k with e_j containing
+ * exactly one of t0/t1 below, so adding RND there once is the same integer sum as adding it to
+ * each of the eight outputs - and it is free inside the IMAD that forms (in0 +- in4) << 13. */
+template <int RND>
 __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	int z1, z2, z3, z4, z5, e0, e1, e2, e3, t0, t1, t2, t3, a, b;
 	z2 = in[2]; z3 = in[6];
 	z1 = (z2 + z3) * 4433;
 	a = z1 - z3 * 15137; b = z1 + z2 * 6270;
-	t0 = (in[0] + in[4]) << 13; t1 = (in[0] - in[4]) << 13;
+	t0 = (in[0] + in[4]) * 8192 + RND; t1 = (in[0] - in[4]) * 8192 + RND;
 	e0 = t0 + b; e3 = t0 - b; e1 = t1 + a; e2 = t1 - a;
 	t0 = in[7]; t1 = in[5]; t2 = in[3]; t3 = in[1];
 	z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;
@@ -120,9 +125,9 @@ __device__ __forceinline__ void qs_islow_rows(const int *ws, uint32_t *lo, uint3
 #pragma unroll
 	for (int y = 0; y < 8; y++) {
 		int o[8];
-		qs_islow_1d(ws + y * 8, o);
+		qs_islow_1d<(257 << 17)>(ws + y * 8, o);
 #pragma unroll
-		for (int k = 0; k < 8; k++) o[k] = (o[k] + (257 << 17)) >> 18;
+		for (int k = 0; k < 8; k++) o[k] >>= 18;
 		/* clamp to [0,255] and pack: one saturating I2IP per two pixels (idct.h:509-511) */
 		lo[y] = qs_pack_sat_u8(o[0], o[1], o[2], o[3]);
 		hi[y] = qs_pack_sat_u8(o[4], o[5], o[6], o[7]);
@@ -208,100 +213,123 @@ __device__ __forceinline__ float qs_regress(const uint8_t *__restrict__ A, const
 }
 
 /* ------------------------------------------------------------------------------------------
- * K1: IDCT pass.  One thread per block; lanes of a warp own 32 consecutive blocks, so the
- * eight 8-byte row stores of a warp cover 256 contiguous bytes per pixel row.
+ * K1: IDCT pass (HBM bound: 128 B of coefficients in, 64 B of pixels out per block, + 128 B
+ * back in the de-quantizing / clamping modes).  One thread per block, a warp owns 32
+ * consecutive blocks = 4 KB of contiguous coefficients.  The warp moves those 4 KB with eight
+ * fully coalesced 512-byte requests and transposes them through shared memory ([word][block],
+ * row stride 33 words: conflict free both ways), so a request touches 4 cache lines instead of
+ * the 32 that per-thread int4 loads at a 128-byte lane stride touch, and the coefficients live
+ * in shared memory instead of 64 registers: 2 CTAs per SM keep 16 warps x 4 KB of loads in
+ * flight (round 1: thread-private loads, 169 registers, 8 warps per SM, 0.33 of HBM peak).
+ * The eight 8-byte row stores of a warp cover 256 contiguous bytes per pixel row.
  * ------------------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(256) qs_idct_pass_kernel(const QsJob *__restrict__ jobs, int njobs,
-		int total_tiles, int mode, int *__restrict__ bad_flags) {
-	int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	if (tile >= total_tiles) return;
-	int lane = threadIdx.x & 31;
+#ifndef QS_IDCT_MINB
+#define QS_IDCT_MINB 2
+#endif
+#define QS_IDCT_THREADS 256
+#define QS_IDCT_SROW 33
+__global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_kernel(const QsJob *__restrict__ jobs,
+		int njobs, int total_tiles, int mode, int *__restrict__ bad_flags) {
+	__shared__ uint32_t sm[QS_IDCT_THREADS / 32][32 * QS_IDCT_SROW];
+	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int tile = blockIdx.x * (QS_IDCT_THREADS / 32) + warp;
+	if (tile >= total_tiles) return;                    /* whole warps leave: only __syncwarp below */
 	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
-	int b = (tile - job->tile_begin) * 32 + lane;
-	if (b >= job->nblocks) return;
+	int b0 = (tile - job->tile_begin) * 32;
+	int nb = min(32, job->nblocks - b0);
+	uint32_t *sw = sm[warp];
+	int4 *g = (int4 *)(job->coef + (size_t)b0 * 64);
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		int P = j * 32 + lane;                          /* 16-byte piece P of the tile: block P/8, words 4*(P%8).. */
+		if ((P >> 3) < nb) {
+			int4 v = g[P];
+			uint32_t *d = sw + (4 * (P & 7)) * QS_IDCT_SROW + (P >> 3);
+			d[0] = v.x; d[QS_IDCT_SROW] = v.y; d[2 * QS_IDCT_SROW] = v.z; d[3 * QS_IDCT_SROW] = v.w;
+		}
+	}
+	__syncwarp();
+	const bool valid = lane < nb;
 	int W = job->wblk, H = job->hblk, stride = job->stride;
+	int b = b0 + (valid ? lane : 0);
 	int by = b / W, bx = b - by * W;
-	int16_t *cptr = job->coef + (size_t)b * 64;
 	const QsQuantDev *qd = job->quant;
+	uint32_t *cwp = sw + lane;                          /* coefficient pair p of this lane's block: cwp[p * SROW] */
 
-	int c[64];
-	{
-		const int4 *p = (const int4 *)cptr;
+	if (valid) {
+		int ws[64], val = 0;
+#pragma unroll
+		for (int xp = 0; xp < 4; xp++) {
+			int a[8], c[8], oa[8], oc[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				uint32_t w = cwp[(k * 4 + xp) * QS_IDCT_SROW];
+				a[k] = (short)(w & 0xffff); c[k] = (int)w >> 16;
+				if (mode & QS_IDCT_DEQUANT) {               /* quantsmooth.h:2596-2603 */
+					int t0 = a[k] * (int)__ldg(&qd->qraw[k * 8 + 2 * xp]);
+					int t1 = c[k] * (int)__ldg(&qd->qraw[k * 8 + 2 * xp + 1]);
+					val |= (t0 + 0x800) | (t1 + 0x800);
+					a[k] = (short)t0; c[k] = (short)t1;
+					cwp[(k * 4 + xp) * QS_IDCT_SROW] = (uint32_t)(a[k] & 0xffff) | ((uint32_t)c[k] << 16);
+				}
+			}
+			if (!(mode & QS_IDCT_NOPLANE)) {
+				qs_islow_1d<1024>(a, oa); qs_islow_1d<1024>(c, oc);
+#pragma unroll
+				for (int k = 0; k < 8; k++) { ws[k * 8 + 2 * xp] = oa[k] >> 11; ws[k * 8 + 2 * xp + 1] = oc[k] >> 11; }
+			}
+		}
+		if ((mode & QS_IDCT_DEQUANT) && (val >> 12)) atomicOr(&bad_flags[job->bad_slot], 1);
+
+		if (!(mode & QS_IDCT_NOPLANE)) {
+			uint32_t lo[8], hi[8];
+			qs_islow_rows(ws, lo, hi);
+			uint8_t *p = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+#pragma unroll
+			for (int y = 0; y < 8; y++) *(uint2 *)(p + (size_t)y * stride) = make_uint2(lo[y], hi[y]);
+			/* replicated borders, quantsmooth.h:2612-2620 */
+			bool left = bx == 0, right = bx == W - 1;
+			if (left) {
+#pragma unroll
+				for (int y = 0; y < 8; y++) p[(size_t)y * stride - 1] = (uint8_t)(lo[y] & 0xff);
+			}
+			if (right) {
+#pragma unroll
+				for (int y = 0; y < 8; y++) p[(size_t)y * stride + 8] = (uint8_t)(hi[y] >> 24);
+			}
+			if (by == 0 && job->top_edge) {
+				uint8_t *r = p - stride;
+				*(uint2 *)r = make_uint2(lo[0], hi[0]);
+				if (left) r[-1] = (uint8_t)(lo[0] & 0xff);
+				if (right) r[8] = (uint8_t)(hi[0] >> 24);
+			}
+			if (by == H - 1 && job->bottom_edge) {
+				uint8_t *r = p + (size_t)8 * stride;
+				*(uint2 *)r = make_uint2(lo[7], hi[7]);
+				if (left) r[-1] = (uint8_t)(lo[7] & 0xff);
+				if (right) r[8] = (uint8_t)(hi[7] >> 24);
+			}
+		}
+		if (mode & QS_IDCT_CLAMP) {                         /* quantsmooth.h:2670-2689 */
+#pragma unroll
+			for (int p2 = 0; p2 < 32; p2++) {
+				uint32_t w = cwp[p2 * QS_IDCT_SROW];
+				int a = (short)(w & 0xffff), c = (int)w >> 16;
+				a = min(max(a, -1023), 1023); c = min(max(c, -1023), 1023);
+				cwp[p2 * QS_IDCT_SROW] = (uint32_t)(a & 0xffff) | ((uint32_t)c << 16);
+			}
+		}
+	}
+
+	if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {         /* coefficients back, coalesced */
+		__syncwarp();
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
-			int4 v = p[j];
-			c[j * 8 + 0] = (short)(v.x & 0xffff); c[j * 8 + 1] = v.x >> 16;
-			c[j * 8 + 2] = (short)(v.y & 0xffff); c[j * 8 + 3] = v.y >> 16;
-			c[j * 8 + 4] = (short)(v.z & 0xffff); c[j * 8 + 5] = v.z >> 16;
-			c[j * 8 + 6] = (short)(v.w & 0xffff); c[j * 8 + 7] = v.w >> 16;
-		}
-	}
-	if (mode & QS_IDCT_DEQUANT) {                       /* quantsmooth.h:2596-2603 */
-		int val = 0;
-#pragma unroll
-		for (int k = 0; k < 64; k++) {
-			int t = c[k] * (int)__ldg(&qd->qraw[k]);
-			val |= t + 0x800;
-			c[k] = (short)t;
-		}
-		if (val >> 12) atomicOr(&bad_flags[job->bad_slot], 1);
-	}
-
-	if (!(mode & QS_IDCT_NOPLANE)) {
-		int ws[64];
-#pragma unroll
-		for (int x = 0; x < 8; x++) {
-			int in[8], o[8];
-#pragma unroll
-			for (int k = 0; k < 8; k++) in[k] = c[k * 8 + x];
-			qs_islow_1d(in, o);
-#pragma unroll
-			for (int k = 0; k < 8; k++) ws[k * 8 + x] = (o[k] + 1024) >> 11;
-		}
-		uint32_t lo[8], hi[8];
-		qs_islow_rows(ws, lo, hi);
-
-		uint8_t *p = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
-#pragma unroll
-		for (int y = 0; y < 8; y++) *(uint2 *)(p + (size_t)y * stride) = make_uint2(lo[y], hi[y]);
-		/* replicated borders, quantsmooth.h:2612-2620 */
-		bool left = bx == 0, right = bx == W - 1;
-		if (left) {
-#pragma unroll
-			for (int y = 0; y < 8; y++) p[(size_t)y * stride - 1] = (uint8_t)(lo[y] & 0xff);
-		}
-		if (right) {
-#pragma unroll
-			for (int y = 0; y < 8; y++) p[(size_t)y * stride + 8] = (uint8_t)(hi[y] >> 24);
-		}
-		if (by == 0 && job->top_edge) {
-			uint8_t *r = p - stride;
-			*(uint2 *)r = make_uint2(lo[0], hi[0]);
-			if (left) r[-1] = (uint8_t)(lo[0] & 0xff);
-			if (right) r[8] = (uint8_t)(hi[0] >> 24);
-		}
-		if (by == H - 1 && job->bottom_edge) {
-			uint8_t *r = p + (size_t)8 * stride;
-			*(uint2 *)r = make_uint2(lo[7], hi[7]);
-			if (left) r[-1] = (uint8_t)(lo[7] & 0xff);
-			if (right) r[8] = (uint8_t)(hi[7] >> 24);
-		}
-	}
-
-	if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {
-		if (mode & QS_IDCT_CLAMP) {                     /* quantsmooth.h:2670-2689 */
-#pragma unroll
-			for (int k = 0; k < 64; k++) c[k] = min(max(c[k], -1023), 1023);
-		}
-		int4 *p = (int4 *)cptr;
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			int4 v;
-			v.x = (c[j * 8 + 0] & 0xffff) | (c[j * 8 + 1] << 16);
-			v.y = (c[j * 8 + 2] & 0xffff) | (c[j * 8 + 3] << 16);
-			v.z = (c[j * 8 + 4] & 0xffff) | (c[j * 8 + 5] << 16);
-			v.w = (c[j * 8 + 6] & 0xffff) | (c[j * 8 + 7] << 16);
-			p[j] = v;
+			int P = j * 32 + lane;
+			if ((P >> 3) < nb) {
+				const uint32_t *d = sw + (4 * (P & 7)) * QS_IDCT_SROW + (P >> 3);
+				g[P] = make_int4((int)d[0], (int)d[QS_IDCT_SROW], (int)d[2 * QS_IDCT_SROW], (int)d[3 * QS_IDCT_SROW]);
+			}
 		}
 	}
 }
@@ -542,27 +570,40 @@ __device__ __forceinline__ void qs_section_sync(int grp) {
 	if (QS_SYNC_LEVEL(SYNC) == 1) qs_group_sync<SYNC>(grp);
 }
 
-/* division, rounding and clamped update of one coefficient, quantsmooth.h:1548-1564 */
-__device__ __forceinline__ void qs_coef_update(float a2s, float a3, int i, const QsQuantDev *__restrict__ qd,
-		uint16_t *cs) {
-	float qv = FM(__fdiv_rn(a2s, a3), 35184372088832.0f);      /* * 2^45, exact */
-	int r = qs_cvtt_x86(roundf(qv));
-	if (r) {
-		uint16_t *slot = cs + (i >> 1) * 64 + (i & 1);
-		int c = (short)*slot;
-		int q = __ldg(&qd->q[i]);
-		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[i]));
-		int d0 = (q - 1) >> 1, d1 = q >> 1;
+/* division, rounding and clamped update of the N coefficients of a chunk, quantsmooth.h:1548-1564.
+ * Written without control flow (the reference's `if (r)` becomes a select, and the store is
+ * unconditional) so that the N dependent chains - divide, round, quant constants, exact
+ * division, clamp - interleave; in lock step nothing else could hide their latencies. */
+template <int N>
+__device__ __forceinline__ void qs_coef_update(const float *a2s, const float *a3, const uint8_t *idx,
+		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+	int q[N], c[N], r[N]; uint32_t m31[N]; uint16_t *slot[N];
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		int i = idx[k];
+		slot[k] = cs + (i >> 1) * 64 + (i & 1);
+		q[k] = __ldg(&qd->q[i]); m31[k] = __ldg(&qd->m31[i]);
+		c[k] = (short)*slot[k];
+	}
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		float qv = FM(__fdiv_rn(a2s[k], a3[k]), 35184372088832.0f);     /* * 2^45, exact */
+		r[k] = qs_cvtt_x86(roundf(qv));
+	}
+#pragma unroll
+	for (int k = 0; k < N; k++) {
+		int a0 = qs_orig_coef(c[k], q[k], m31[k]);
+		int d0 = (q[k] - 1) >> 1, d1 = q[k] >> 1;
 		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
-		int add = (int)((unsigned)c - (unsigned)r);
+		int add = (int)((unsigned)c[k] - (unsigned)r[k]);
 		add = min(add, dh); add = max(add, dl);
-		*slot = (uint16_t)add;
+		*slot[k] = (uint16_t)(r[k] ? add : c[k]);
 	}
 }
 
 template <int N, bool DIAG, int SYNC, bool UNI>
 __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h) {
 	const float *tab[N]; float Rs[N], a2[N], a3[N];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -582,8 +623,9 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<N, UNI>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
 	QS_PH_MARK(ph, 8);
-#pragma unroll
-	for (int c = 0; c < N; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+	/* the next chunk's header travels while the divisions below are in flight */
+	h[0] = __ldg(nh); h[1] = __ldg(nh + 1); h[2] = __ldg(nh + 2);
+	qs_coef_update<N>(a2, a3, ch.idx, qd, cs);
 	QS_PH_MARK(ph, 9);
 }
 
@@ -591,7 +633,7 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
  * terms), idx[1] in column 0 (i & 7 == 0: no horizontal terms) */
 template <bool DIAG, int SYNC>
 __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h) {
 	const float *tab[2]; float Rs[2], a2[2], a3[2];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -611,8 +653,8 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<2, false>(pw, tab, Rs, a2, a3); }
 	qs_section_sync<SYNC>(grp);
 	QS_PH_MARK(ph, 8);
-#pragma unroll
-	for (int c = 0; c < 2; c++) qs_coef_update(a2[c], a3[c], ch.idx[c], qd, cs);
+	h[0] = __ldg(nh); h[1] = __ldg(nh + 1); h[2] = __ldg(nh + 2);
+	qs_coef_update<2>(a2, a3, ch.idx, qd, cs);
 	QS_PH_MARK(ph, 9);
 }
 
@@ -631,11 +673,11 @@ __device__ __forceinline__ void qs_refresh(const uint32_t *cw, uint2 *pw) {
 			uint32_t w = cw[(k * 4 + xp) * 32];
 			a[k] = (short)(w & 0xffff); b[k] = (int)w >> 16;
 		}
-		qs_islow_1d(a, oa); qs_islow_1d(b, ob);
+		qs_islow_1d<1024>(a, oa); qs_islow_1d<1024>(b, ob);
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
-			ws[k * 8 + 2 * xp] = (oa[k] + 1024) >> 11;
-			ws[k * 8 + 2 * xp + 1] = (ob[k] + 1024) >> 11;
+			ws[k * 8 + 2 * xp] = oa[k] >> 11;
+			ws[k * 8 + 2 * xp + 1] = ob[k] >> 11;
 		}
 	}
 	uint32_t lo[8], hi[8];
@@ -686,7 +728,9 @@ __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, c
 /* rebalance, quantsmooth.h:1566-1568, 1823-1848 */
 __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs) {
 	long long m0 = 0, m1 = 0;
-#pragma unroll 1
+	/* both loops: 63 independent iterations, latency bound when rolled (LDS -> LDG -> IMAD.HI);
+	 * unrolled by 7 the loads of seven coefficients are in flight together */
+#pragma unroll 7
 	for (int k = 1; k < 64; k++) {
 		int c = (short)cs[(k >> 1) * 64 + (k & 1)];
 		int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
@@ -694,7 +738,7 @@ __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, 
 	}
 	if (m1 > m0 && m0 != 0) {
 		int mul = (int)(((m1 << 13) + (m0 >> 1)) / m0);
-#pragma unroll 1
+#pragma unroll 7
 		for (int k = 1; k < 64; k++) {
 			uint16_t *slot = cs + (k >> 1) * 64 + (k & 1);
 			int c = (short)*slot;
@@ -877,34 +921,34 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			}
 		}
 #endif
-		int nch = X2 ? 0 : (mixed ? c_nchunks : __ldg(&qd->nchunks));
+		int nch = X2 ? 0 : (mixed ? d_nchunks : __ldg(&qd->nchunks));
+		/* 12-byte chunk headers (type, n, first, -, idx[8]); warp-uniform.  Each chunk fetches its
+		 * successor's header before its own divisions, so no chunk starts with a load latency. */
+		const uint32_t *cp = (const uint32_t *)(mixed ? d_chunks : qd->chunks);
+		uint32_t h[3] = { __ldg(cp), __ldg(cp + 1), __ldg(cp + 2) };
 #pragma unroll 1
 		for (int ci = 0; ci < nch; ci++) {
 			QsChunk ch;
-			if (mixed) ch = c_chunks[ci];
-			else {
-				const uint32_t *cp = (const uint32_t *)&qd->chunks[ci];     /* 12 bytes, warp-uniform */
-				uint32_t c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
-				ch.type = c0 & 255; ch.n = (c0 >> 8) & 255; ch.first = (c0 >> 16) & 255; ch.pad = 0;
-				ch.idx[0] = c1 & 255; ch.idx[1] = (c1 >> 8) & 255; ch.idx[2] = (c1 >> 16) & 255; ch.idx[3] = c1 >> 24;
-				ch.idx[4] = c2 & 255; ch.idx[5] = (c2 >> 8) & 255; ch.idx[6] = (c2 >> 16) & 255; ch.idx[7] = c2 >> 24;
-			}
+			ch.type = h[0] & 255; ch.n = (h[0] >> 8) & 255; ch.first = (h[0] >> 16) & 255; ch.pad = 0;
+			ch.idx[0] = h[1] & 255; ch.idx[1] = (h[1] >> 8) & 255; ch.idx[2] = (h[1] >> 16) & 255; ch.idx[3] = h[1] >> 24;
+			ch.idx[4] = h[2] & 255; ch.idx[5] = (h[2] >> 8) & 255; ch.idx[6] = (h[2] >> 16) & 255; ch.idx[7] = h[2] >> 24;
+			const uint32_t *nh = cp + 3 * min(ci + 1, nch - 1);
 			qs_group_sync<SYNC>(gsync);
 			QS_PH_MARK(ph, 2);
 			/* the reference re-renders only if a coefficient changed (need_refresh); an
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 			QS_PH_MARK(ph, 3);
-			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph);
+			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
 			else if (ch.type == 2) {
-				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
-				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
-				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph);
+				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
 			}
-			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
-			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
 		}
 		QS_PH_MARK(ph, 10);
 
@@ -1163,9 +1207,9 @@ __global__ void qs_copy_flags_kernel(const int *__restrict__ src, volatile int *
  * launch wrappers
  * ------------------------------------------------------------------------------------------ */
 cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
-	cudaError_t e = cudaMemcpyToSymbol(c_chunks, chunks, sizeof(QsChunk) * n);
+	cudaError_t e = cudaMemcpyToSymbol(d_chunks, chunks, sizeof(QsChunk) * n);
 	if (e != cudaSuccess) return e;
-	return cudaMemcpyToSymbol(c_nchunks, &n, sizeof(int));
+	return cudaMemcpyToSymbol(d_nchunks, &n, sizeof(int));
 }
 
 typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
@@ -1251,8 +1295,8 @@ cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tile
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
 		int *bad_flags, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
-	int wpb = 256 / 32;
-	qs_idct_pass_kernel<<<(total_tiles + wpb - 1) / wpb, 256, 0, st>>>(jobs_dev, njobs, total_tiles, mode, bad_flags);
+	int wpb = QS_IDCT_THREADS / 32;
+	qs_idct_pass_kernel<<<(total_tiles + wpb - 1) / wpb, QS_IDCT_THREADS, 0, st>>>(jobs_dev, njobs, total_tiles, mode, bad_flags);
 	return cudaGetLastError();
 }
 

@@ -33,7 +33,8 @@ def lib_path() -> str:
 class _Comp(C.Structure):
     _fields_ = [("coef", C.c_void_p), ("wblk", C.c_uint32), ("hblk", C.c_uint32),
                 ("h_samp", C.c_int32), ("v_samp", C.c_int32), ("has_qtbl", C.c_int32),
-                ("quant", C.c_uint16 * 64), ("coef_up", C.c_void_p)]
+                ("quant", C.c_uint16 * 64), ("coef_up", C.c_void_p),
+                ("rows", C.c_void_p), ("rows_up", C.c_void_p)]
 
 
 class _Image(C.Structure):

@@ -40,7 +40,7 @@ for v in args.variants.split(","):
     ctx.set_tuning(1, maxn)
     ctx.set_tuning(2, wpg)
     ctx.set_tuning(3, gs)
-    sm, n, tot = 0.0, 0, 0.0
+    sm, n, tot, idm, idn = 0.0, 0, 0.0, 0.0, 0
     for i in range(args.steps + 1):
         bufs = [h.to(dev) for h in host]
         ups = []
@@ -51,9 +51,9 @@ for v in args.variants.split(","):
         ctx.run_device(im, [t.data_ptr() for t in bufs], ups, args.flags, args.niter, stream)
         if i:
             a, b, c, d = ctx.kernel_stats()
-            sm += c; n += d; tot += ctx.last_device_ms
+            sm += c; n += d; tot += ctx.last_device_ms; idm += a; idn += b
     h = hashlib.sha1(b"".join(t.cpu().numpy().tobytes() for t in bufs)).hexdigest()
     if ref_hash is None:
         ref_hash = h
-    print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs} x2={x2} uni={uni}: smooth {sm / n:.3f} ms/launch, whole run {tot / args.steps:.3f} ms, "
+    print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs} x2={x2} uni={uni}: smooth {sm / n:.3f} ms/launch, idct pass {1e3 * idm / max(idn, 1):.1f} us/launch, whole run {tot / args.steps:.3f} ms, "
           f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
