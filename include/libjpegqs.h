@@ -3,8 +3,11 @@
  *
  * Source compatible with the reference's API header (reference libjpegqs.h:14-55): the same
  * identifiers with the same values, the same jpegqs_control_t layout and the same three entry
- * points, so a caller written against the reference (quantsmooth.c:550, example.c:96,
- * irfanview/plugin.c:103) compiles and links against libjpegqs_b200.so unchanged.
+ * points.  A caller that includes "libjpegqs.h" (irfanview/plugin.c, and quantsmooth.c in its
+ * SIMD_SELECT build, which includes libjpegqs.c -> libjpegqs.h) compiles against this header and
+ * links against libjpegqs_b200.so as is; quantsmooth.c:89 and example.c:37 include the
+ * implementation header "quantsmooth.h" instead and need that one line changed to "libjpegqs.h"
+ * (example.c:36 says so itself).  INTEGRATION.md section 2 has the build lines that were run.
  * Include <jpeglib.h> before this header.
  *
  * Behavioural differences:
@@ -60,6 +63,9 @@ enum jpegqs_limits { JPEGQS_ITER_MAX = 100 };   /* niter is clamped to [0, JPEGQ
 #endif
 
 #define JPEGQS_VERSION "1.20230818-b200"
+/* the reference CLI prints this next to the version (quantsmooth.c:472); the algorithm is its
+ * author's, the sm_100a back end is this repository's */
+#define JPEGQS_COPYRIGHT "algorithm (C) 2020-2026 Ilya Kurdyukov, B200 back end (C) 2026 jpeg-quantsmooth_b200"
 
 typedef struct jpegqs_control {
 	int flags;                         /* JPEGQS_* bits                                          */

@@ -107,6 +107,7 @@ typedef struct {
 	const unsigned char *p, *end;
 	uint64_t buf; int nbits;
 	int hit_marker;                      /* a marker (not a stuffed FF00) stopped the feed */
+	int warn;                            /* bad Huffman codes met (decoding goes on, like libjpeg) */
 } jq_bits;
 
 static void bits_fill(jq_bits *b) {
@@ -148,10 +149,12 @@ static inline int huff_decode(jq_bits *b, const jq_dhuff *h) {
 	unsigned look = bits_peek(b, 16), e = h->look[look >> 7];
 	int l, code;
 	if (e) { b->nbits -= e >> 8; return e & 255; }
-	for (l = 10, code = (int)(look >> 6); l <= 16; l++, code = (int)(look >> (16 - l)))
+	for (l = 10; l <= 16; l++) {
+		code = (int)(look >> (16 - l));
 		if (code <= h->maxcode[l]) { b->nbits -= l; return h->val[h->valptr[l] + code - h->mincode[l]]; }
-	b->nbits -= 16;
-	return 0;                            /* corrupt data: keep going like libjpeg's warning path */
+	}
+	b->nbits -= 16; b->warn++;
+	return 0;                            /* corrupt data: keep going like libjpeg's JWRN_HUFF_BAD_CODE path */
 }
 static inline int extend(unsigned v, int s) { return s && v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v; }
 
@@ -290,6 +293,7 @@ static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const u
 		*next = q;
 	} else *next = b.p;
 	(void)rst;
+	im->warnings += b.warn;
 	return 0;
 }
 
@@ -314,9 +318,10 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 	p += 2;
 	while (!done) {
 		unsigned code, seglen; const unsigned char *seg;
+		if (p < end && *p != 0xFF) im->warnings++;      /* libjpeg: JWRN_EXTRANEOUS_DATA */
 		while (p < end && *p != 0xFF) p++;              /* tolerate garbage between segments */
 		while (p < end && *p == 0xFF) p++;
-		if (p >= end) break;
+		if (p >= end) { im->warnings++; break; }        /* no EOI: libjpeg's JWRN_JPEG_EOF */
 		code = *p++;
 		if (code == 0xD9) break;                        /* EOI */
 		if (code == 0x01 || (code >= 0xD0 && code <= 0xD7) || code == 0) continue;
@@ -411,6 +416,11 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 			int want = code == 0xFE ? copy > 0 : copy > 1;
 			if (code == 0xEE && seglen >= 12 && !memcmp(seg, "Adobe", 5)) {       /* transform flag, jdmarker.c */
 				adobe = seg[11];
+				im->saw_adobe = 1; im->adobe_transform = seg[11];
+			}
+			if (code == 0xE0 && seglen >= 14 && !memcmp(seg, "JFIF", 5)) {         /* jdmarker.c examine_app0 */
+				im->saw_jfif = 1; im->jfif_major = seg[5]; im->jfif_minor = seg[6];
+				im->density_unit = seg[7]; im->x_density = (int)be16(seg + 8); im->y_density = (int)be16(seg + 10);
 			}
 			if (want) {
 				jq_marker *m = (jq_marker*)calloc(1, sizeof(*m));
@@ -421,7 +431,8 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 		}
 	}
 	if (!have_frame) { snprintf(err, 256, "no frame header found"); goto fail; }
-	if (adobe >= 0) {                                   /* jdapimin.c default_decompress_parms */
+	if (im->saw_jfif && im->cinfo.num_components == 3) im->cinfo.jpeg_color_space = JCS_YCbCr;
+	if (adobe >= 0 && !(im->saw_jfif && im->cinfo.num_components == 3)) {      /* jdapimin.c default_decompress_parms */
 		if (im->cinfo.num_components == 3) im->cinfo.jpeg_color_space = adobe == 0 ? JCS_RGB : JCS_YCbCr;
 		if (im->cinfo.num_components == 4) im->cinfo.jpeg_color_space = adobe == 2 ? JCS_YCCK : JCS_CMYK;
 	}
@@ -741,9 +752,36 @@ int jq_write(jq_image *im, jvirt_barray_ptr *arrays, int optimize, unsigned char
 	for (i = 0; i < nt; i++) { ehuff_codes(&dc[i]); ehuff_codes(&ac[i]); }
 
 	out_be16(&o, 0xFFD8);
-	for (m = im->markers; m; m = m->next) {              /* jcopy_markers_execute, quantsmooth.c:581-590 */
-		out_byte(&o, 0xFF); out_byte(&o, (unsigned)m->code); out_be16(&o, (unsigned)m->len + 2);
-		for (i = 0; i < (int)m->len; i++) out_byte(&o, m->data[i]);
+	{
+		/* What libjpeg writes for every output file, whatever -c says (jcmarker.c write_file_header
+		 * after jpeg_copy_critical_parameters -> jpeg_set_colorspace): a JFIF APP0 for grayscale /
+		 * YCbCr with the source's version (if 1.x or 2.x) and density, an Adobe APP14 carrying the
+		 * colour transform for RGB / CMYK / YCCK - without it a decoder would guess YCbCr / CMYK. */
+		J_COLOR_SPACE cs = ci->jpeg_color_space;
+		int jfif = cs == JCS_GRAYSCALE || cs == JCS_YCbCr, adobe = cs == JCS_RGB || cs == JCS_CMYK || cs == JCS_YCCK;
+		if (jfif) {
+			int major = 1, minor = 1, unit = 0, xd = 1, yd = 1;
+			if (im->saw_jfif) {                              /* jctrans.c jpeg_copy_critical_parameters */
+				if (im->jfif_major == 1 || im->jfif_major == 2) { major = im->jfif_major; minor = im->jfif_minor; }
+				unit = im->density_unit; xd = im->x_density; yd = im->y_density;
+			}
+			out_be16(&o, 0xFFE0); out_be16(&o, 16);
+			out_byte(&o, 'J'); out_byte(&o, 'F'); out_byte(&o, 'I'); out_byte(&o, 'F'); out_byte(&o, 0);
+			out_byte(&o, (unsigned)major); out_byte(&o, (unsigned)minor); out_byte(&o, (unsigned)unit);
+			out_be16(&o, (unsigned)xd); out_be16(&o, (unsigned)yd); out_byte(&o, 0); out_byte(&o, 0);
+		}
+		if (adobe) {
+			out_be16(&o, 0xFFEE); out_be16(&o, 14);
+			out_byte(&o, 'A'); out_byte(&o, 'd'); out_byte(&o, 'o'); out_byte(&o, 'b'); out_byte(&o, 'e');
+			out_be16(&o, 100); out_be16(&o, 0); out_be16(&o, 0);
+			out_byte(&o, cs == JCS_YCCK ? 2u : 0u);          /* jcmarker.c emit_adobe_app14 (1 = YCbCr never gets here) */
+		}
+		for (m = im->markers; m; m = m->next) {              /* jcopy_markers_execute, quantsmooth.c:581-590 */
+			if (jfif && m->code == 0xE0 && m->len >= 5 && !memcmp(m->data, "JFIF", 5)) continue;   /* written above */
+			if (adobe && m->code == 0xEE && m->len >= 5 && !memcmp(m->data, "Adobe", 5)) continue;
+			out_byte(&o, 0xFF); out_byte(&o, (unsigned)m->code); out_be16(&o, (unsigned)m->len + 2);
+			for (i = 0; i < (int)m->len; i++) out_byte(&o, m->data[i]);
+		}
 	}
 	for (k = 0; k < ci->num_components; k++) {           /* DQT for every table in use */
 		int tq = ci->comp_info[k].quant_tbl_no & 3, prec = 0;

@@ -7,7 +7,8 @@
  * (SURVEY.md 8f row f1): it parses baseline, extended-sequential and progressive Huffman
  * JPEGs into exactly the structures do_quantsmooth consumes (the compat jpeg_decompress_struct
  * with an in-memory jpeg_memory_mgr and one virtual block array per component) and writes the
- * arrays back as a sequential Huffman JPEG, copying APPn/COM markers.  No pixels are decoded.
+ * arrays back as a sequential Huffman JPEG with libjpeg's own JFIF / Adobe header markers
+ * (jcmarker.c write_file_header) followed by the copied APPn/COM markers.  No pixels are decoded.
  * Arithmetic-coded, lossless, hierarchical and 12-bit files are rejected.
  */
 #ifndef JPEGCOEF_H
@@ -34,6 +35,11 @@ typedef struct jq_image {
 	int progressive;                         /* the input was SOF2 */
 	int restart_interval;                    /* of the input (not reproduced on output) */
 	int comp_id[MAX_COMPONENTS];             /* component identifiers of the frame header */
+	/* what libjpeg keeps in saw_JFIF_marker / JFIF_*_version / density / saw_Adobe_marker /
+	 * Adobe_transform (jdmarker.c) and jpeg_copy_critical_parameters hands to the writer */
+	int saw_jfif, jfif_major, jfif_minor, density_unit, x_density, y_density;
+	int saw_adobe, adobe_transform;
+	int warnings;                            /* recoverable anomalies (libjpeg: err->num_warnings) */
 	void *priv;
 } jq_image;
 

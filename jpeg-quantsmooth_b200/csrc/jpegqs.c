@@ -19,7 +19,8 @@
  * The flow is the reference's (quantsmooth.c:494-596): read coefficients, do_quantsmooth,
  * write coefficients + copied markers.  libjpeg is replaced by jpegcoef.c because its headers
  * are not available in this build image.  Exit code: 0 ok, 1 usage / I/O / codec error,
- * 2 when do_quantsmooth reported an error.
+ * 2 when the input had recoverable damage (the reference: libjpeg warnings, quantsmooth.c:626)
+ * or the CUDA back end failed (negative do_quantsmooth return).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -61,7 +62,7 @@ static int usage(const char *prog) {
 
 int main(int argc, char **argv) {
 	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
-	int i, ret, flags = 0, ppm = 0;
+	int i, ret, flags = 0, ppm = 0, io_err = 0, warnings;
 	const char *in_name, *out_name;
 	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
 	jq_image im; char err[256]; jpegqs_control_t opts;
@@ -143,7 +144,7 @@ int main(int argc, char **argv) {
 			jpeg_component_info *k = &im.cinfo.comp_info[c]; JDIMENSION y;
 			size_t rowb = (size_t)k->width_in_blocks * sizeof(JBLOCK);
 			bufs[c] = (int16_t*)malloc(rowb * k->height_in_blocks + 1);
-			for (y = 0; y < k->height_in_blocks; y++)
+			if (bufs[c]) for (y = 0; y < k->height_in_blocks; y++)
 				memcpy((char*)bufs[c] + y * rowb, (*im.cinfo.mem->access_virt_barray)((j_common_ptr)&im.cinfo,
 						im.coef_arrays[c], y, 1, FALSE)[0], rowb);
 			ci.comp[c].coef = bufs[c]; ci.comp[c].wblk = k->width_in_blocks; ci.comp[c].hblk = k->height_in_blocks;
@@ -152,6 +153,12 @@ int main(int argc, char **argv) {
 			if (k->quant_table) memcpy(ci.comp[c].quant, k->quant_table->quantval, sizeof(ci.comp[c].quant));
 		}
 		rgb = (unsigned char*)malloc(npx * 3 + 1);
+		for (c = 0; c < nc; c++) if (!bufs[c]) rgb = (free(rgb), (unsigned char*)NULL);
+		if (!rgb) {
+			fprintf(stderr, "%s: out of memory\n", argv[0]);
+			for (c = 0; c < nc; c++) free(bufs[c]);
+			jpegqs_cuda_destroy(ctx); jq_free(&im); return 1;
+		}
 		rc = jpegqs_cuda_render_rgb(ctx, &ci, 0, rgb, NULL);
 		if (rc) fprintf(stderr, "%s: render failed (%d): %s\n", argv[0], rc, jpegqs_cuda_last_error(ctx));
 		for (c = 0; c < nc; c++) free(bufs[c]);
@@ -161,6 +168,7 @@ int main(int argc, char **argv) {
 		hl = snprintf(hdr, sizeof(hdr), "P%d\n%u %u\n255\n", nc == 1 ? 5 : 6, im.cinfo.image_width, im.cinfo.image_height);
 		outlen = hl + npx * (nc == 1 ? 1 : 3);
 		out = (unsigned char*)malloc(outlen);
+		if (!out) { fprintf(stderr, "%s: out of memory\n", argv[0]); free(rgb); jq_free(&im); return 1; }
 		memcpy(out, hdr, hl); memcpy(out + hl, rgb, outlen - hl);
 		free(rgb);
 	} else
@@ -171,8 +179,12 @@ int main(int argc, char **argv) {
 	/* the output is opened after the input was read, so it may name the same file */
 	f = strcmp(out_name, "-") ? fopen(out_name, "wb") : stdout;
 	if (!f) { fprintf(stderr, "%s: can't open output file \"%s\"\n", argv[0], out_name); free(out); jq_free(&im); return 1; }
-	if (fwrite(out, 1, outlen, f) != outlen) { fprintf(stderr, "%s: write error\n", argv[0]); ret = 1; }
-	if (f != stdout) fclose(f);
+	if (fwrite(out, 1, outlen, f) != outlen) io_err = 1;
+	if (f != stdout ? fclose(f) != 0 : fflush(f) != 0) io_err = 1;      /* ENOSPC shows up at the flush */
+	if (io_err) fprintf(stderr, "%s: error writing \"%s\"\n", argv[0], out_name);
+	warnings = im.warnings;
 	free(out); jq_free(&im);
-	return ret > 0 ? 0 : ret;
+	/* the reference's exit status (quantsmooth.c:626): 2 when the codec met recoverable damage
+	 * (libjpeg's num_warnings), else 0 - do_quantsmooth's "stopped early" value is not an error */
+	return io_err ? 1 : warnings ? 2 : 0;
 }

@@ -111,13 +111,58 @@ def test_writer_bytes_do_not_depend_on_the_thread_count(jpegs, tmp_path):
 
 
 def test_marker_copy_levels(jpegs, tmp_path):
-    src = jpegs["base420"]
+    """-c selects the COPIED markers; the JFIF APP0 is not one of them: libjpeg writes it itself
+    for every grayscale / YCbCr output (jcmarker.c write_file_header) with the source's version
+    and density (jctrans.c jpeg_copy_critical_parameters), and so does this codec."""
+    src = str(tmp_path / "src.jpg")
+    _picture(64, 48, False, 3).save(src, quality=75, comment=b"made by the test suite", dpi=(300, 150),
+                                    exif=b"Exif\x00\x00II*\x00\x08\x00\x00\x00\x00\x00\x00\x00\x00\x00")
     for level, want_com, want_app in ((2, True, True), (1, True, False), (0, False, False)):
         out = str(tmp_path / f"c{level}.jpg")
         assert subprocess.run([EXE, "-n", "0", "-i", "0", "-c", str(level), src, out]).returncode == 0
         m = _markers(out)
         assert any(c == 0xFE and b"made by the test suite" in d for c, d in m) == want_com
-        assert any(0xE0 <= c <= 0xEF for c, _ in m) == want_app
+        jfif = [d for c, d in m if c == 0xE0 and d[:5] == b"JFIF\x00"]
+        assert len(jfif) == 1 and m[0][0] == 0xE0                      # once, first, at every level
+        assert jfif[0][7] == 1 and jfif[0][8:12] == (300).to_bytes(2, "big") + (150).to_bytes(2, "big")
+        assert any(c == 0xE1 and d[:4] == b"Exif" for c, d in m) == want_app
+        assert PIL.open(out).info.get("dpi") == (300, 150)
+
+
+@pytest.mark.parametrize("mode", ["CMYK", "RGB"])
+def test_adobe_marker_keeps_the_colour_transform(tmp_path, mode):
+    """RGB / CMYK / YCCK files carry their colour transform in the Adobe APP14 marker; libjpeg
+    writes it for every such output whatever -c says.  Without it a decoder guesses YCbCr / CMYK
+    and shows wrong colours."""
+    src = str(tmp_path / "src.jpg")
+    pic = _picture(80, 56, False, 5)
+    if mode == "CMYK":
+        pic.convert("CMYK").save(src, quality=85)
+    else:
+        try:
+            pic.save(src, quality=85, keep_rgb=True)                     # Pillow >= 10.2: JCS_RGB, no transform
+        except TypeError:
+            pytest.skip("this Pillow cannot write untransformed RGB JPEGs")
+    want = np.asarray(PIL.open(src).convert("RGB"))
+    for level in (0, 2):
+        out = str(tmp_path / f"o{level}.jpg")
+        assert subprocess.run([EXE, "-n", "0", "-i", "0", "-c", str(level), src, out]).returncode == 0
+        adobe = [d for c, d in _markers(out) if c == 0xEE and d[:5] == b"Adobe"]
+        assert len(adobe) == 1 and not any(c == 0xE0 for c, _ in _markers(out))
+        assert np.array_equal(np.asarray(PIL.open(out).convert("RGB")), want)
+
+
+def test_exit_status_follows_the_reference(jpegs, tmp_path):
+    """quantsmooth.c:626: 2 when the codec met recoverable damage (libjpeg warnings), else 0;
+    an unwritable output is 1 (round 1 returned 0 for it)."""
+    data = open(jpegs["base420"], "rb").read()
+    cut = tmp_path / "cut.jpg"
+    cut.write_bytes(data[:len(data) * 2 // 3])                            # truncated: no EOI
+    r = subprocess.run([EXE, "-n", "0", "-i", "0", str(cut), str(tmp_path / "o.jpg")], capture_output=True)
+    assert r.returncode == 2 and (tmp_path / "o.jpg").exists()
+    if os.path.exists("/dev/full"):
+        r = subprocess.run([EXE, "-n", "0", "-i", "0", jpegs["base420"], "/dev/full"], capture_output=True)
+        assert r.returncode == 1
 
 
 def test_bad_input_and_usage(tmp_path):
