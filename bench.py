@@ -254,32 +254,28 @@ def main():
     dev_bufs = [[h.to(dev) for h in host_coefs] for _ in range(nbuf)]
     torch.cuda.synchronize()
 
+    hblk_total, row0 = None, None
+    link = None
     if world == 1:
         def step(i):
             ret, _ = ctx.run_device(im, [t.data_ptr() for t in dev_bufs[i]], [], FLAGS, NITER, stream)
             return ret
     else:
-        class TimedPasses(mg.CudaPasses):
-            """CUDA events around every smoothing pass (on the launching stream) for the roofline."""
-            events = []
-            timing = False
-
-            def smooth(self, *a, **k):
-                if not self.timing:
-                    return super().smooth(*a, **k)
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(); super().smooth(*a, **k); e1.record()
-                self.events.append((e0, e1))
-
-        passes = TimedPasses(ctx, stream)
-        planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev)
-                  for c in im.comps]
-        allreduce_flag = mg.make_flag_allreduce(dist, dev)
+        # The C slab engine (include/jpegqs_cuda.h "one image sharded by MCU rows"): every rank
+        # smooths its MCU rows; halo rows and out-of-range masks travel between the ranks inside
+        # CUDA kernels through peer mailboxes (CUDA IPC over NVLink).  torch.distributed only
+        # carries the IPC handles at start-up and the timing reductions.
+        maxv = max(c.v_samp for c in im.comps)
+        hblk_total = [-(-HEIGHT * world * c.v_samp // (8 * maxv)) for c in im.comps]
+        row0 = [mg.comp_block_rows(mcu_rng, c.v_samp, ht)[0] for c, ht in zip(im.comps, hblk_total)]
+        link = qs.cuda.QsLink(ctx, rank, world, max(c.wblk for c in im.comps))
+        handles = [None] * world
+        dist.all_gather_object(handles, link.export())
+        link.connect_ipc(handles)
 
         def step(i):
-            comps = [mg.SlabComp(dev_bufs[i][k], planes[k], c.wblk, c.hblk, c.quant, k == 0)
-                     for k, c in enumerate(im.comps)]
-            return mg.run_slab(passes, comps, FLAGS, NITER, rank, world, dist, allreduce_flag)[0]
+            return ctx.run_slab(link, im, rank, world, row0, hblk_total, FLAGS, NITER,
+                                coef_ptrs=[t.data_ptr() for t in dev_bufs[i]], up_ptrs=[], stream=stream)[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -298,26 +294,17 @@ def main():
     launches = 0
     smooth_ms, smooth_n, idct_ms, idct_n = 0.0, 0, 0.0, 0
     barrier()
-    if world > 1:
-        passes.timing = True
     sampler.t0 = time.perf_counter()
     e0.record()
     for i in range(K):
         step(Wm + i)
-        if world == 1:
-            launches += ctx.last_launches
-            a, b, c, d = ctx.kernel_stats()
-            idct_ms += a; idct_n += b; smooth_ms += c; smooth_n += d
-        else:
-            launches += 2 * NITER
+        launches += ctx.last_launches
+        a, b, c, d = ctx.kernel_stats()
+        idct_ms += a; idct_n += b; smooth_ms += c; smooth_n += d
     e1.record()
     barrier()
     sampler.t1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        passes.timing = False
-        smooth_ms = sum(a.elapsed_time(b) for a, b in passes.events)
-        smooth_n = len(passes.events)
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -363,14 +350,17 @@ def main():
                     row.append(p)
                 pinned.append(row)
 
+            from jpegqs_b200.image import CoefImage, Component
+            hosts = [CoefImage(im.width, im.height, im.colorspace,
+                               [Component(pinned[i][k].array, c.quant.copy(), c.h_samp, c.v_samp, c.quant_tbl_no)
+                                for k, c in enumerate(im.comps)]) for i in range(nbuf)]
+
             def e2e_step(i):
-                for k in range(len(im.comps)):
-                    dev_bufs[i][k].copy_(torch.from_numpy(pinned[i][k].array), non_blocking=True)
-                step(i)
-                for k in range(len(im.comps)):
-                    torch.from_numpy(pinned[i][k].array).copy_(dev_bufs[i][k], non_blocking=True)
-                torch.cuda.synchronize()
-            api = "pinned host -> slab tensors -> pass-level C ABI -> pinned host"
+                ret = ctx.run_slab(link, hosts[i], rank, world, row0, hblk_total, FLAGS, NITER)[0]
+                if ret != 0:
+                    raise SystemExit(f"run_slab returned {ret}")
+            api = ("jpegqs_cuda_run_slab (C slab engine) on every rank with caller-pinned host slabs: "
+                   "H2D, kernels + kernel-side halo exchange over CUDA IPC mailboxes, D2H")
 
         for i in range(Wm):
             e2e_step(i)
@@ -445,11 +435,12 @@ def main():
                        "blocks": total_blocks,
                        "cache": "a distinct pristine input buffer per step (100 MB each, "
                                 f"{nbuf} buffers > 126 MB L2)",
-                       "sharding": "none" if world == 1 else f"MCU rows over {world} GPUs, NCCL halo rows"},
+                       "sharding": "none" if world == 1 else
+                       f"MCU rows over {world} GPUs (one process each); halo rows + out-of-range masks exchanged by "
+                       "CUDA kernels through peer mailboxes (CUDA IPC / NVLink), no host sync, no NCCL on the data path"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "roofline_fp32": roofline_fp32, "cpu_baseline": cpu,
-            "kernel_ms_per_step": {"idct_pass": round(idct_ms / K, 4), "smooth_pass": round(smooth_ms / K, 4)}
-            if world == 1 else None,
+            "kernel_ms_per_step": {"idct_pass": round(idct_ms / K, 4), "smooth_pass": round(smooth_ms / K, 4)},
         }
         print(json.dumps(out), flush=True)
     if dist is not None:

@@ -118,6 +118,54 @@ int jpegqs_cuda_run_device(jpegqs_cuda_ctx *ctx, jpegqs_cuda_image *img, int fla
 int jpegqs_cuda_run_batch(jpegqs_cuda_ctx *ctx, int nimages, jpegqs_cuda_image *imgs, int flags,
 		int niter, int on_device, int *ret, void *stream);
 
+/* ---- one image sharded by MCU rows over several GPUs ----------------------
+ * Every rank - a device of this process, or another process on the same box - smooths one slab
+ * of contiguous MCU rows and exchanges ONE pixel row per plane with each neighbour after every
+ * IDCT pass (quantsmooth.h:1396-1401: a pass reads only start-of-pass neighbour pixels).  The
+ * exchange runs inside CUDA kernels over peer memory (NVLink P2P / CUDA IPC mailboxes, sequence
+ * numbers instead of events): no host round trip, no NCCL call on the data path.  The
+ * reference's `stop` logic is evaluated on the device from flags the ranks OR-combine, so all
+ * ranks issue the same schedule whatever their data.  Results are bit-identical to the
+ * unsharded run for any rank count.
+ *
+ *   link_create on every rank -> link_export + (all-gather of the handles by the caller) +
+ *   link_connect_ipc, or link_connect_local for the devices of one process -> run_slab, as often
+ *   as wanted, by all ranks alike -> link_destroy.                                            */
+typedef struct jpegqs_cuda_link jpegqs_cuda_link;
+typedef struct {
+	int32_t rank, world;
+	uint32_t row0[JPEGQS_CUDA_MAX_COMP];        /* first block row of the slab inside component c  */
+	uint32_t hblk_total[JPEGQS_CUDA_MAX_COMP];  /* block rows of the whole component               */
+} jpegqs_cuda_slab;
+/* max_wblk: widest component (in blocks) any later run will exchange */
+int jpegqs_cuda_link_create(jpegqs_cuda_ctx *ctx, int rank, int world, uint32_t max_wblk, jpegqs_cuda_link **out);
+void jpegqs_cuda_link_destroy(jpegqs_cuda_link *link);
+int jpegqs_cuda_link_handle_bytes(void);
+int jpegqs_cuda_link_export(jpegqs_cuda_link *link, void *handle);
+int jpegqs_cuda_link_connect_ipc(jpegqs_cuda_link *link, const void *handles_in_rank_order);
+int jpegqs_cuda_link_connect_local(jpegqs_cuda_link **links_in_rank_order, int world);
+/* slab: the image with comp[].hblk = block rows held by this rank and coef / rows / coef_up
+ * covering exactly those rows (host memory, or device memory with on_device != 0);
+ * image_width / image_height are the WHOLE image's.  No progress callback.  link may be NULL
+ * for world == 1.  Returns the reference's stop value (identical on every rank) or an error. */
+int jpegqs_cuda_run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_image *slab,
+		const jpegqs_cuda_slab *geom, int flags, int niter, int on_device, void *stream);
+
+/* The devices of ONE process behind one call (what do_quantsmooth uses when JPEGQS_GPUS is
+ * set): contexts + links for ndev devices (devices == NULL: ordinals 0..ndev-1; ndev <= 0: all),
+ * one host thread per device inside run_host_multi.  An image is spread over as many devices as
+ * it has waves of the smoothing kernel (JPEGQS_MIN_BLOCKS_PER_GPU luma blocks per device,
+ * default 148*16*32), so a small image stays on device 0 with the slab-pipelined run_host. */
+typedef struct jpegqs_cuda_multi jpegqs_cuda_multi;
+int jpegqs_cuda_multi_create(int ndev, const int *devices, jpegqs_cuda_multi **out);
+void jpegqs_cuda_multi_destroy(jpegqs_cuda_multi *m);
+int jpegqs_cuda_multi_devices(const jpegqs_cuda_multi *m);
+jpegqs_cuda_ctx *jpegqs_cuda_multi_ctx(jpegqs_cuda_multi *m, int i);
+const char *jpegqs_cuda_multi_last_error(const jpegqs_cuda_multi *m);
+int jpegqs_cuda_multi_plan(const jpegqs_cuda_multi *m, const jpegqs_cuda_image *img);   /* devices it would use */
+/* host buffers / block-row tables like jpegqs_cuda_run_host; no progress callback */
+int jpegqs_cuda_run_host_multi(jpegqs_cuda_multi *m, jpegqs_cuda_image *img, int flags, int niter);
+
 /* ---- pass-level entry points (multi-GPU slabs: the caller exchanges halo rows between
  *      the passes).  All pointers are DEVICE pointers. ---------- */
 typedef struct {

@@ -17,11 +17,6 @@
 #include <string.h>
 #include <stdint.h>
 #include <jpeglib.h>
-#ifdef JPEGQS_COMPAT_JPEGLIB
-#ifndef TRANSCODE_ONLY
-#define TRANSCODE_ONLY          /* the stand-in header has no decoder internals */
-#endif
-#endif
 #include "libjpegqs.h"
 #include "jpegqs_cuda.h"
 
@@ -36,14 +31,49 @@ static int64_t now_usec(void) {
 #endif
 
 #if !defined(TRANSCODE_ONLY) && !defined(JPEG_INTERNALS)
-/* decoder re-initialisation hooks from jpegint.h, used when the caller goes on to
- * jpeg_read_scanlines (reference quantsmooth.h:33-61, 2861-2876) */
+/* What the decode helpers need from libjpeg beyond jpeglib.h (the reference declares the same
+ * things by hand, quantsmooth.h:33-61): two decoder states, the four module initialisers that
+ * re-arm the output side after the coefficient arrays were replaced (2861-2876), and - for
+ * libjpeg-turbo, whose IDCT stops at master->last_MCU_col - the private master record. */
 #define DSTATE_SCANNING 205
 #define DSTATE_RAW_OK 206
-EXTERN(void) jinit_d_main_controller(j_decompress_ptr, boolean);
-EXTERN(void) jinit_inverse_dct(j_decompress_ptr);
-EXTERN(void) jinit_upsampler(j_decompress_ptr);
-EXTERN(void) jinit_color_deconverter(j_decompress_ptr);
+#define QS_WEAK __attribute__((weak))
+EXTERN(void) jinit_d_main_controller(j_decompress_ptr, boolean) QS_WEAK;
+EXTERN(void) jinit_inverse_dct(j_decompress_ptr) QS_WEAK;
+EXTERN(void) jinit_upsampler(j_decompress_ptr) QS_WEAK;
+EXTERN(void) jinit_color_deconverter(j_decompress_ptr) QS_WEAK;
+struct jpeg_decomp_master {
+	void (*prepare_for_output_pass)(j_decompress_ptr);
+	void (*finish_output_pass)(j_decompress_ptr);
+	boolean is_dummy_pass;
+#ifdef LIBJPEG_TURBO_VERSION
+#if LIBJPEG_TURBO_VERSION_NUMBER >= 2001090
+	boolean lossless;
+#endif
+	JDIMENSION first_iMCU_col, last_iMCU_col;
+	JDIMENSION first_MCU_col[MAX_COMPONENTS];
+	JDIMENSION last_MCU_col[MAX_COMPONENTS];
+	boolean jinit_upsampler_no_alloc;
+#if LIBJPEG_TURBO_VERSION_NUMBER >= 2000090
+	JDIMENSION last_good_iMCU_row;
+#endif
+#endif
+};
+#endif
+#ifndef TRANSCODE_ONLY
+/* The library does not pull in a libjpeg of its own: the application that calls the decode
+ * helpers has one loaded, and these weak references bind to it.  A process without libjpeg
+ * (the Python tests, a transcoder built on another codec) can still load the library; the
+ * helpers then report the missing symbols instead of crashing. */
+#ifndef QS_WEAK
+#define QS_WEAK __attribute__((weak))
+#endif
+EXTERN(boolean) jpeg_start_decompress(j_decompress_ptr) QS_WEAK;
+EXTERN(boolean) jpeg_input_complete(j_decompress_ptr) QS_WEAK;
+EXTERN(boolean) jpeg_start_output(j_decompress_ptr, int) QS_WEAK;
+EXTERN(boolean) jpeg_finish_output(j_decompress_ptr) QS_WEAK;
+EXTERN(jvirt_barray_ptr *) jpeg_read_coefficients(j_decompress_ptr) QS_WEAK;
+EXTERN(boolean) jpeg_finish_decompress(j_decompress_ptr) QS_WEAK;
 #endif
 
 /* one lazily created context per device ordinal.  The reference function is re-entrant; this one
@@ -53,6 +83,28 @@ EXTERN(void) jinit_color_deconverter(j_decompress_ptr);
 #define QS_MAX_DEVICES 16
 static jpegqs_cuda_ctx *g_ctx[QS_MAX_DEVICES + 1];
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+/* JPEGQS_GPUS=n (or "all"): images large enough are sharded by MCU rows over n devices of this
+ * process (include/jpegqs_cuda.h jpegqs_cuda_run_host_multi).  The reference's
+ * knob for parallelism is opts->threads (quantsmooth.h:2467-2472), which callers set to CPU
+ * counts - an environment variable cannot be misread that way.  Not with a progress callback
+ * (its sequence is per component, quantsmooth.h:2656-2664) and not with an explicit device. */
+static jpegqs_cuda_multi *g_multi;
+static int g_multi_tried;
+static jpegqs_cuda_multi *get_multi(void) {
+	if (!g_multi_tried) {
+		const char *e = getenv("JPEGQS_GPUS");
+		g_multi_tried = 1;
+		if (e && *e) {
+			int n = !strcmp(e, "all") ? 0 : atoi(e);
+			if ((n > 1 || !strcmp(e, "all")) && jpegqs_cuda_multi_create(n, NULL, &g_multi)) {
+				fprintf(stderr, "jpegqs: JPEGQS_GPUS=%s ignored: %s\n", e, jpegqs_cuda_last_error(NULL));
+				g_multi = NULL;
+			}
+		}
+	}
+	return g_multi;
+}
 
 static jpegqs_cuda_ctx *get_ctx(int ordinal_plus1) {
 	int slot = ordinal_plus1 < 0 || ordinal_plus1 > QS_MAX_DEVICES ? 0 : ordinal_plus1;
@@ -102,7 +154,7 @@ static int16_t **row_table(j_decompress_ptr cinfo, jvirt_barray_ptr arr, JDIMENS
 
 JPEGQS_ATTR
 int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpegqs_control_t *opts) {
-	jpegqs_cuda_image img; jpegqs_cuda_ctx *ctx;
+	jpegqs_cuda_image img; jpegqs_cuda_ctx *ctx; jpegqs_cuda_multi *multi = NULL;
 	jpeg_component_info *comp = srcinfo->comp_info;
 	int ci, i, ret, ncomp = srcinfo->num_components, niter = opts->niter;
 	int need_downsample = 0, flags = opts->flags, resident = 1, will_upsample;
@@ -142,10 +194,14 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 			(comp[0].h_samp_factor != 1 || comp[0].v_samp_factor != 1);
 
 	pthread_mutex_lock(&g_lock);
-	ctx = get_ctx((flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK);
+	if (!opts->progress && !((flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK)) multi = get_multi();
+	ctx = multi ? jpegqs_cuda_multi_ctx(multi, 0) : get_ctx((flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK);
 	if (!ctx) { pthread_mutex_unlock(&g_lock); return JPEGQS_ERR_CUDA; }
 #ifdef WITH_LOG
-	if (flags & JPEGQS_INFO_CPU) logfmt("SIMD type: CUDA sm_100a (%s)\n", jpegqs_cuda_device_name(ctx));
+	if (flags & JPEGQS_INFO_CPU) {
+		if (multi) logfmt("SIMD type: CUDA sm_100a (%s x %d)\n", jpegqs_cuda_device_name(ctx), jpegqs_cuda_multi_devices(multi));
+		else logfmt("SIMD type: CUDA sm_100a (%s)\n", jpegqs_cuda_device_name(ctx));
+	}
 	LOG_COMP2                                          /* quantsmooth.h:2569-2572 */
 #endif
 
@@ -203,10 +259,12 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 		}
 	}
 
-	ret = jpegqs_cuda_run_host(ctx, &img, flags & JPEGQS_FLAGS_MASK, opts->niter, opts->progprec,
+	if (multi) ret = jpegqs_cuda_run_host_multi(multi, &img, flags & JPEGQS_FLAGS_MASK, opts->niter);
+	else ret = jpegqs_cuda_run_host(ctx, &img, flags & JPEGQS_FLAGS_MASK, opts->niter, opts->progprec,
 			opts->progress, opts->userdata);
 	if (ret < 0) {
-		fprintf(stderr, "jpegqs: CUDA back end failed (%d): %s\n", ret, jpegqs_cuda_last_error(ctx));
+		fprintf(stderr, "jpegqs: CUDA back end failed (%d): %s\n", ret,
+				multi ? jpegqs_cuda_multi_last_error(multi) : jpegqs_cuda_last_error(ctx));
 		goto done;
 	}
 
@@ -246,6 +304,10 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 	}
 #ifndef TRANSCODE_ONLY
 	if (!(flags & JPEGQS_TRANSCODE)) {                 /* quantsmooth.h:2861-2876 */
+		if (!jinit_inverse_dct || !jinit_upsampler || !jinit_color_deconverter || !jinit_d_main_controller) {
+			fprintf(stderr, "jpegqs: no libjpeg in this process to re-arm the decoder (JPEGQS_TRANSCODE not set)\n");
+			ret = JPEGQS_ERR_ARG;
+		} else {
 		if (img.upsampled) {
 #ifdef LIBJPEG_TURBO_VERSION
 			srcinfo->master->last_MCU_col[1] = srcinfo->master->last_MCU_col[0];
@@ -257,6 +319,7 @@ int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, jpeg
 			srcinfo->input_iMCU_row = (srcinfo->output_height + DCTSIZE - 1) / DCTSIZE;
 		}
 		jinit_inverse_dct(srcinfo);
+		}
 	}
 #endif
 #ifdef WITH_LOG
@@ -272,6 +335,19 @@ done:
 	return ret;
 }
 
+/* The reference's SIMD_SELECT build (Makefile:176-185) links one do_quantsmooth per
+ * instruction-set tier and picks one at run time (libjpegqs.c:80-156, declarations 38-58).  The
+ * CUDA back end occupies exactly that slot: with these four names a caller compiled as
+ * `quantsmooth.c -DSIMD_SELECT` (which includes the dispatcher libjpegqs.c) links against this
+ * library unchanged, whichever tier its cpuid logic picks.  The tier cap the dispatcher leaves in
+ * the flags' CPU field is not a device ordinal: cleared. */
+#define QS_TIER(name) JPEGQS_ATTR int do_quantsmooth_##name(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays, \
+		jpegqs_control_t *opts) { \
+	jpegqs_control_t o = *opts; \
+	o.flags &= ~(JPEGQS_CPU_MASK << JPEGQS_CPU_SHIFT); \
+	return do_quantsmooth(srcinfo, coef_arrays, &o); }
+QS_TIER(base) QS_TIER(sse2) QS_TIER(avx2) QS_TIER(avx512)
+
 #ifndef TRANSCODE_ONLY
 /* decode helpers, reference quantsmooth.h:2880-2904: read every scan in buffered-image
  * mode, smooth the coefficient arrays, then let the caller pull scanlines as usual */
@@ -279,6 +355,11 @@ JPEGQS_ATTR
 boolean jpegqs_start_decompress(j_decompress_ptr cinfo, jpegqs_control_t *opts) {
 	boolean ok;
 	int active = opts->niter > 0 || (opts->flags & JPEGQS_UPSAMPLE_UV);
+	if (!jpeg_start_decompress || !jpeg_input_complete || !jpeg_start_output || !jpeg_finish_output ||
+			!jpeg_read_coefficients) {
+		fprintf(stderr, "jpegqs: jpegqs_start_decompress needs libjpeg loaded in this process\n");
+		return FALSE;
+	}
 	if (active) cinfo->buffered_image = TRUE;
 	ok = jpeg_start_decompress(cinfo);
 	if (!active) return ok;
@@ -293,6 +374,7 @@ boolean jpegqs_start_decompress(j_decompress_ptr cinfo, jpegqs_control_t *opts) 
 
 JPEGQS_ATTR
 boolean jpegqs_finish_decompress(j_decompress_ptr cinfo) {
+	if (!jpeg_finish_output || !jpeg_finish_decompress) return FALSE;
 	if (cinfo->buffered_image &&
 			(cinfo->global_state == DSTATE_SCANNING || cinfo->global_state == DSTATE_RAW_OK))
 		jpeg_finish_output(cinfo);

@@ -5,7 +5,7 @@
  * jpeg_write_coefficients, reference quantsmooth.c:548-596).  libjpeg's headers are not
  * available in this build image, so the `jpegqs` tool here carries its own front/back end
  * (SURVEY.md 8f row f1): it parses baseline, extended-sequential and progressive Huffman
- * JPEGs into exactly the structures do_quantsmooth consumes (the compat jpeg_decompress_struct
+ * JPEGs into exactly the structures do_quantsmooth consumes (a jpeg_decompress_struct
  * with an in-memory jpeg_memory_mgr and one virtual block array per component) and writes the
  * arrays back as a sequential Huffman JPEG with libjpeg's own JFIF / Adobe header markers
  * (jcmarker.c write_file_header) followed by the copied APPn/COM markers.  No pixels are decoded.

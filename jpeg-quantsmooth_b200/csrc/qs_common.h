@@ -67,8 +67,39 @@ typedef struct {
 	int32_t luma;            /* rebalance class (quantsmooth.h:2639) */
 	int32_t top_edge;        /* 1: slab top is the image top -> replicate row -1 */
 	int32_t bottom_edge;     /* 1: slab bottom is the image bottom */
-	int32_t bad_slot;        /* index into the per-launch "coefficient out of range" flags */
+	int32_t bad_slot;        /* index into the "coefficient out of range" flags */
+	/* Device-side stop handling (sharded runs, qs_cuda.cu run_slab): bad_slot is then the
+	 * component's slot in flags that live for the whole run, bad_first the slot of component 0 of
+	 * the same image, and the kernels decide by themselves what the reference's `stop` logic
+	 * (quantsmooth.h:2504, 2551-2566, 2602-2610) leaves to do: 0 = smooth, 1 = this component
+	 * overflowed (clamp only), 2 = an earlier one did (de-quantize only).  stop_aware = 0: the
+	 * host has already sorted that out (run_images). */
+	int32_t bad_first, stop_aware;
 } QsJob;
+
+/* sharded runs: ranks exchange pixel rows and the out-of-range masks through mailboxes in peer
+ * memory (NVLink P2P, or CUDA IPC between processes); see qs_kernels.cu qs_xchg_*_kernel */
+#define QS_MAX_RANKS 16
+#define QS_XCHG_SLOTS 12          /* planes per exchange: MAX_COMPONENTS + the down-sampled luma */
+#define QS_XCHG_MAX_ROWS (2 * QS_XCHG_SLOTS)
+typedef struct { const uint8_t *src; uint8_t *dst; uint32_t bytes, pad; } QsXchgRow;
+typedef struct {
+	QsXchgRow rows[QS_XCHG_MAX_ROWS]; int32_t nrows;
+	uint32_t seq;
+	uint32_t *flag[2];                       /* the neighbours' "rows have arrived" words (or NULL) */
+	const int32_t *bad_src; int32_t bad_n;   /* out-of-range flags of this rank -> every peer */
+	int32_t npeers;
+	uint32_t *bad_dst[QS_MAX_RANKS], *bad_flag[QS_MAX_RANKS];
+} QsXchgPush;
+typedef struct {
+	QsXchgRow rows[QS_XCHG_MAX_ROWS]; int32_t nrows;
+	uint32_t seq;
+	const uint32_t *flag[2];                 /* this rank's "rows have arrived" words to wait for */
+	int32_t *bad_io; int32_t bad_n;          /* local flags, OR-ed with every peer's message */
+	int32_t npeers;
+	const uint32_t *bad_in[QS_MAX_RANKS], *bad_flag[QS_MAX_RANKS];
+	int32_t *timeout_flag;                   /* mapped host word set if a peer never signalled */
+} QsXchgPull;
 
 #define QS_MAX_JOBS 1024
 

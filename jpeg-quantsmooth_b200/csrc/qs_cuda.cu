@@ -413,6 +413,90 @@ static void io_rows_copy(QsPool *pool, const std::vector<IoSeg> &segs, int dir) 
 	else for (int i = 0; i < (int)tasks.size(); i++) run(i);
 }
 
+/* The host side of one run of a host entry point.
+ * Uploads are a list of units (one slab of one phase, or a whole phase): gather the unit's block
+ * rows into pinned memory (pool threads), H2D on the upload stream, record the unit's event.  With
+ * anything to gather the list runs on the context's upload thread, so that the calling thread
+ * can go on enqueueing kernels; wait(unit, st) makes stream st wait for a unit (after its event
+ * has actually been recorded).  Downloads: D2H on the download stream behind an event of the
+ * compute stream; block-row tables are scattered by the download thread + pool once the copy
+ * has landed in pinned memory.  The destructor drains both threads: no return path may leave a
+ * worker running on the caller's frame. */
+struct HostIo {
+	struct Unit { std::vector<IoSeg> segs; cudaEvent_t ev; };
+	jpegqs_cuda_ctx *ctx;
+	std::vector<Unit> units;
+	std::atomic<int> recorded, failed;
+	char err[256];
+	explicit HostIo(jpegqs_cuda_ctx *c) : ctx(c), recorded(0), failed(0) { err[0] = 0; }
+	~HostIo() { if (ctx->up) ctx->up->drain(); if (ctx->down) ctx->down->drain(); }
+	int add_unit(std::vector<IoSeg> segs, cudaEvent_t ev) {
+		Unit u; u.segs = std::move(segs); u.ev = ev;
+		units.push_back(std::move(u));
+		return (int)units.size() - 1;
+	}
+	int start() {                                        /* all units are known: go */
+		bool gather = false;
+		for (const Unit &u : units) for (const IoSeg &sg : u.segs) gather = gather || sg.rows != NULL;
+		if (gather && io_start(ctx)) return JPEGQS_ERR_CUDA;
+		if (gather) ctx->up->post([this] { run_units(); }); else run_units();
+		return 0;
+	}
+	void run_units() {
+		cudaStream_t cup = ctx->up_stream;
+		cudaError_t e = cudaSetDevice(ctx->device);
+		for (size_t i = 0; i < units.size() && e == cudaSuccess; i++) {
+			io_rows_copy(ctx->pool, units[i].segs, 0);
+			for (const IoSeg &sg : units[i].segs) {
+				size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
+				if (cnt && e == cudaSuccess)
+					e = cudaMemcpyAsync(sg.dev + off, sg.pin + off, cnt * 2, cudaMemcpyHostToDevice, cup);
+			}
+			if (e == cudaSuccess) e = cudaEventRecord(units[i].ev, cup);
+			if (e == cudaSuccess) recorded.store((int)i + 1, std::memory_order_release);
+		}
+		if (e != cudaSuccess) {
+			snprintf(err, sizeof(err), "upload: %s", cudaGetErrorString(e));
+			failed.store(1, std::memory_order_release);
+		}
+	}
+	int wait(int unit, cudaStream_t st) {
+		if (unit < 0) return 0;
+		while (recorded.load(std::memory_order_acquire) <= unit && !failed.load(std::memory_order_acquire))
+			std::this_thread::yield();
+		if (failed.load()) { snprintf(ctx->err, sizeof(ctx->err), "%s", err); return JPEGQS_ERR_CUDA; }
+		CK(cudaStreamWaitEvent(st, units[unit].ev, 0));
+		return 0;
+	}
+	int download(std::vector<IoSeg> segs, cudaEvent_t after) {
+		cudaStream_t cdn = ctx->down_stream;
+		CK(cudaStreamWaitEvent(cdn, after, 0));
+		bool scatter = false;
+		for (const IoSeg &sg : segs) {
+			size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
+			if (cnt) CK(cudaMemcpyAsync(sg.pin + off, sg.dev + off, cnt * 2, cudaMemcpyDeviceToHost, cdn));
+			scatter = scatter || sg.rows != NULL;
+		}
+		if (scatter) {
+			cudaEvent_t e;
+			if (io_event(ctx, &e) || io_start(ctx)) return JPEGQS_ERR_CUDA;
+			CK(cudaEventRecord(e, cdn));
+			QsPool *pool = ctx->pool; int devno = ctx->device;
+			ctx->down->post([segs, e, pool, devno]() {
+				cudaSetDevice(devno);
+				if (cudaEventSynchronize(e) == cudaSuccess) io_rows_copy(pool, segs, 1);
+			});
+		}
+		return 0;
+	}
+	int finish() {                                       /* everything has landed in the caller's memory */
+		CK(cudaStreamSynchronize(ctx->down_stream));
+		if (ctx->up) ctx->up->drain();
+		if (ctx->down) ctx->down->drain();
+		return 0;
+	}
+};
+
 static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int maxn = 4, int uniform = 1) {
 	int val = 0;
 	for (int i = 0; i < 64; i++) {
@@ -465,10 +549,11 @@ static void assign_sched_slots(QsQuantDev *q, int n) {
 
 /* upload a job list into one of the two device slots unless it is already there */
 static int upload_jobs(jpegqs_cuda_ctx *ctx, int slot, std::vector<QsJob> &jobs, cudaStream_t st,
-		const QsJob **dev, int *total_tiles) {
+		const QsJob **dev, int *total_tiles, bool keep_bad_slots = false) {
 	int tiles = 0;
 	for (size_t i = 0; i < jobs.size(); i++) {
-		jobs[i].tile_begin = tiles; jobs[i].bad_slot = (int)i;
+		jobs[i].tile_begin = tiles;
+		if (!keep_bad_slots) jobs[i].bad_slot = (int)i;
 		tiles += (jobs[i].nblocks + 31) / 32;
 	}
 	*total_tiles = tiles;
@@ -727,26 +812,13 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		else if (s.ngroups == 2) { *c0 = g ? 1 : 0; *c1 = g ? s.im->ncomp : 1; }
 		else { *c0 = 0; *c1 = s.im->ncomp; }
 	};
-	cudaStream_t cup = ctx->up_stream, cdn = ctx->down_stream;
 	std::vector<SlabPlan> plan(max_groups > 0 ? max_groups : 1);
 	for (SlabPlan &pl : plan) pl.K = 0;
 
-	/* ---- uploads.  The host side of a run is a list of units (one slab of one group, or a whole
-	 * group): gather the unit's block rows into pinned memory (pool threads), H2D on the upload
-	 * stream, record the unit's event.  With anything to gather the list runs on the context's
-	 * upload thread so that this thread can go on enqueueing kernels; up_wait(unit) makes the
-	 * compute stream wait for a unit (after its event has actually been recorded). */
-	struct UpUnit { std::vector<IoSeg> segs; cudaEvent_t ev; };
-	struct UpState { std::atomic<int> recorded; std::atomic<int> failed; char err[256]; };
-	std::vector<UpUnit> units;
-	UpState upst; upst.recorded = 0; upst.failed = 0; upst.err[0] = 0;
+	/* ---- uploads / downloads: HostIo above ---- */
+	HostIo io(ctx);
 	std::vector<int> unit_of_group(max_groups > 0 ? max_groups : 1, -1);
 	std::vector<std::vector<int> > unit_of_slab(max_groups > 0 ? max_groups : 1);
-	struct IoGuard {              /* no return path may leave a worker running on this frame's data */
-		jpegqs_cuda_ctx *c;
-		~IoGuard() { if (c->up) c->up->drain(); if (c->down) c->down->drain(); }
-	} io_guard = { ctx };
-	(void)io_guard;
 	auto seg_of = [&](const CompWork &w, int r0, int r1) {
 		IoSeg sg; sg.dev = w.coef_dev; sg.pin = w.pin; sg.rows = w.rows; sg.wblk = w.W; sg.r0 = r0; sg.r1 = r1;
 		return sg;
@@ -789,77 +861,26 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			if (plan[g].K) {
 				int c0, c1; group_range(S[0], g, &c0, &c1);
 				for (int k = 0; k < plan[g].K; k++) {
-					UpUnit u; u.ev = ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k];
-					for (int ci = c0; ci < c1; ci++) u.segs.push_back(seg_of(W[0][ci], plan[g].r[k], plan[g].r[k + 1]));
-					unit_of_slab[g].push_back((int)units.size());
-					units.push_back(std::move(u));
+					std::vector<IoSeg> segs;
+					for (int ci = c0; ci < c1; ci++) segs.push_back(seg_of(W[0][ci], plan[g].r[k], plan[g].r[k + 1]));
+					unit_of_slab[g].push_back(io.add_unit(std::move(segs), ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k]));
 				}
-				unit_of_group[g] = (int)units.size() - 1;
+				unit_of_group[g] = unit_of_slab[g].back();
 				continue;
 			}
-			UpUnit u; u.ev = ctx->sync_ev[2 * g];
+			std::vector<IoSeg> segs;
 			for (int n = 0; n < nimg; n++) {
 				ImgState &s = S[n];
 				if (s.skip || g >= s.ngroups) continue;
 				int c0, c1; group_range(s, g, &c0, &c1);
-				for (int ci = c0; ci < c1; ci++) if (W[n][ci].W && W[n][ci].H) u.segs.push_back(seg_of(W[n][ci], 0, W[n][ci].H));
+				for (int ci = c0; ci < c1; ci++) if (W[n][ci].W && W[n][ci].H) segs.push_back(seg_of(W[n][ci], 0, W[n][ci].H));
 			}
-			unit_of_group[g] = (int)units.size();
-			units.push_back(std::move(u));
+			unit_of_group[g] = io.add_unit(std::move(segs), ctx->sync_ev[2 * g]);
 		}
-		bool gather = false;
-		for (const UpUnit &u : units) for (const IoSeg &sg : u.segs) gather = gather || sg.rows != NULL;
-		if (gather && io_start(ctx)) return JPEGQS_ERR_CUDA;
-		QsPool *pool = ctx->pool; int devno = ctx->device;
-		auto run_units = [&units, &upst, pool, cup, devno]() {
-			cudaError_t e = cudaSetDevice(devno);
-			for (size_t i = 0; i < units.size() && e == cudaSuccess; i++) {
-				io_rows_copy(pool, units[i].segs, 0);
-				for (const IoSeg &sg : units[i].segs) {
-					size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
-					if (cnt && e == cudaSuccess)
-						e = cudaMemcpyAsync(sg.dev + off, sg.pin + off, cnt * 2, cudaMemcpyHostToDevice, cup);
-				}
-				if (e == cudaSuccess) e = cudaEventRecord(units[i].ev, cup);
-				if (e == cudaSuccess) upst.recorded.store((int)i + 1, std::memory_order_release);
-			}
-			if (e != cudaSuccess) {
-				snprintf(upst.err, sizeof(upst.err), "upload: %s", cudaGetErrorString(e));
-				upst.failed.store(1, std::memory_order_release);
-			}
-		};
-		if (gather) ctx->up->post(run_units); else run_units();
+		if (io.start()) return JPEGQS_ERR_CUDA;
 	}
-	auto up_wait = [&](int unit) -> int {
-		if (unit < 0) return 0;
-		while (upst.recorded.load(std::memory_order_acquire) <= unit && !upst.failed.load(std::memory_order_acquire))
-			std::this_thread::yield();
-		if (upst.failed.load()) { snprintf(ctx->err, sizeof(ctx->err), "%s", upst.err); return JPEGQS_ERR_CUDA; }
-		CK(cudaStreamWaitEvent(st, units[unit].ev, 0));
-		return 0;
-	};
-	/* downloads: D2H on the download stream behind `after`; block-row tables are scattered by the
-	 * download thread + pool once the copy has landed in pinned memory */
-	auto download = [&](std::vector<IoSeg> segs, cudaEvent_t after) -> int {
-		CK(cudaStreamWaitEvent(cdn, after, 0));
-		bool scatter = false;
-		for (const IoSeg &sg : segs) {
-			size_t off = (size_t)sg.r0 * sg.wblk * 64, cnt = (size_t)(sg.r1 - sg.r0) * sg.wblk * 64;
-			if (cnt) CK(cudaMemcpyAsync(sg.pin + off, sg.dev + off, cnt * 2, cudaMemcpyDeviceToHost, cdn));
-			scatter = scatter || sg.rows != NULL;
-		}
-		if (scatter) {
-			cudaEvent_t e;
-			if (io_event(ctx, &e) || io_start(ctx)) return JPEGQS_ERR_CUDA;
-			CK(cudaEventRecord(e, cdn));
-			QsPool *pool = ctx->pool; int devno = ctx->device;
-			ctx->down->post([segs, e, pool, devno]() {
-				cudaSetDevice(devno);
-				if (cudaEventSynchronize(e) == cudaSuccess) io_rows_copy(pool, segs, 1);
-			});
-		}
-		return 0;
-	};
+	auto up_wait = [&](int unit) -> int { return io.wait(unit, st); };
+	auto download = [&](std::vector<IoSeg> segs, cudaEvent_t after) -> int { return io.download(std::move(segs), after); };
 
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
 	int *bad_dev = ctx->flags_dev, *tile_counter = ctx->flags_dev + QS_MAX_JOBS;
@@ -894,13 +915,13 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 	};
 	auto launch_smooth = [&](const QsJob *jd, int nj, int tiles, int clampv) -> int {
 		if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
-		if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, nj, tiles, flags, clampv, st));
+		if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, nj, tiles, flags, clampv, NULL, st));
 #ifdef QS_EXPERIMENTS
 		else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, nj, tiles,
 				(flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain, ctx->nslots2, tile_counter, flags, clampv,
 				ctx->num_sms, ctx->tune_sync, st));
 #endif
-		else CK(qs_launch_smooth(jd, nj, tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
+		else CK(qs_launch_smooth(jd, nj, tiles, tabs, tile_counter, flags, clampv, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, NULL, st));
 		if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
 		ctx->launches++;
 		return 0;
@@ -1145,11 +1166,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 		if (ret) ret[n] = s.stop;
 	}
 	CK(cudaStreamSynchronize(st));
-	if (!on_device) {
-		CK(cudaStreamSynchronize(cdn));
-		if (ctx->up) ctx->up->drain();
-		if (ctx->down) ctx->down->drain();              /* the last scatter has finished */
-	}
+	if (!on_device && io.finish()) return JPEGQS_ERR_CUDA;  /* the last scatter has finished */
 	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
 	if (prof_collect(ctx)) return JPEGQS_ERR_CUDA;
 	return 0;
@@ -1186,6 +1203,624 @@ extern "C" int jpegqs_cuda_run_batch(jpegqs_cuda_ctx *ctx, int nimages, jpegqs_c
 		i += n;
 	}
 	return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One image sharded by MCU rows over several GPUs: links + run_slab.
+ *
+ * Every rank (a device of this process, or another process on the box) owns a mailbox in its
+ * device memory and maps the mailboxes of all ranks: cudaDeviceEnablePeerAccess inside a
+ * process, CUDA IPC handles between processes - NVLink / NVSwitch peer memory either way.  The
+ * exchange kernels (qs_kernels.cu qs_xchg_*) store pixel rows and the out-of-range masks
+ * straight into the peers' mailboxes and hand over by sequence numbers, so between the IDCT pass
+ * and the smoothing pass of an iteration there is neither a host round trip nor a library call.
+ * ------------------------------------------------------------------------------------------ */
+#define QS_BOX_HALO_FLAG 0            /* uint32[2]: rows from the upper / lower neighbour have arrived */
+#define QS_BOX_BAD_FLAG 64            /* uint32[QS_MAX_RANKS]: mask message of rank r has arrived */
+#define QS_BOX_BAD_MASK 128           /* uint32[QS_MAX_RANKS][16] */
+#define QS_BOX_ROWS 2048              /* uint8 [2 parity][2 side][QS_XCHG_SLOTS][row_bytes] */
+
+struct jpegqs_cuda_link {
+	jpegqs_cuda_ctx *ctx;
+	int rank, world;
+	size_t row_bytes, box_bytes;
+	char *box;                           /* this rank's mailbox */
+	char *peer[QS_MAX_RANKS];            /* every rank's mailbox in this rank's address space */
+	bool ipc_open[QS_MAX_RANKS];
+	bool connected;
+	uint32_t seq;                        /* exchanges so far: every rank counts the same */
+	int *timeout_host;                   /* mapped: set by a pull kernel whose peer never signalled */
+};
+
+extern "C" int jpegqs_cuda_link_create(jpegqs_cuda_ctx *ctx, int rank, int world, uint32_t max_wblk,
+		jpegqs_cuda_link **out) {
+	if (!ctx || !out || world < 1 || world > QS_MAX_RANKS || rank < 0 || rank >= world || !max_wblk) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	jpegqs_cuda_link *l = new jpegqs_cuda_link();
+	memset(l, 0, sizeof(*l));
+	l->ctx = ctx; l->rank = rank; l->world = world;
+	l->row_bytes = align256((size_t)QS_PLANE_STRIDE(max_wblk));
+	l->box_bytes = QS_BOX_ROWS + (size_t)2 * 2 * QS_XCHG_SLOTS * l->row_bytes;
+	cudaError_t e = cudaMalloc((void **)&l->box, l->box_bytes);
+	if (e == cudaSuccess) e = cudaMemset(l->box, 0, l->box_bytes);
+	if (e == cudaSuccess) e = cudaHostAlloc((void **)&l->timeout_host, sizeof(int), cudaHostAllocMapped);
+	if (e != cudaSuccess) {
+		snprintf(ctx->err, sizeof(ctx->err), "link_create: %s", cudaGetErrorString(e));
+		cudaFree(l->box); delete l; return JPEGQS_ERR_CUDA;
+	}
+	*l->timeout_host = 0;
+	l->peer[rank] = l->box;
+	l->connected = world == 1;
+	*out = l;
+	return 0;
+}
+
+extern "C" void jpegqs_cuda_link_destroy(jpegqs_cuda_link *l) {
+	if (!l) return;
+	cudaSetDevice(l->ctx->device);
+	cudaStreamSynchronize(l->ctx->stream);
+	for (int r = 0; r < l->world; r++) if (l->ipc_open[r]) cudaIpcCloseMemHandle(l->peer[r]);
+	cudaFree(l->box);
+	if (l->timeout_host) cudaFreeHost(l->timeout_host);
+	delete l;
+}
+
+extern "C" int jpegqs_cuda_link_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+/* this rank's mailbox as a CUDA IPC handle (jpegqs_cuda_link_handle_bytes() bytes) */
+extern "C" int jpegqs_cuda_link_export(jpegqs_cuda_link *l, void *handle) {
+	if (!l || !handle) return JPEGQS_ERR_ARG;
+	jpegqs_cuda_ctx *ctx = l->ctx;
+	CK(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, l->box));
+	memcpy(handle, &h, sizeof(h));
+	return 0;
+}
+
+/* ranks in different processes: handles = world x jpegqs_cuda_link_handle_bytes(), in rank order
+ * (gathered by whatever the caller uses to talk between processes) */
+extern "C" int jpegqs_cuda_link_connect_ipc(jpegqs_cuda_link *l, const void *handles) {
+	if (!l || !handles) return JPEGQS_ERR_ARG;
+	jpegqs_cuda_ctx *ctx = l->ctx;
+	CK(cudaSetDevice(ctx->device));
+	for (int r = 0; r < l->world; r++) {
+		if (r == l->rank || l->peer[r]) continue;
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+		void *p = NULL;
+		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		l->peer[r] = (char *)p; l->ipc_open[r] = true;
+	}
+	l->connected = true;
+	return 0;
+}
+
+/* ranks on several devices of THIS process: peer access + plain pointers */
+extern "C" int jpegqs_cuda_link_connect_local(jpegqs_cuda_link **links, int world) {
+	if (!links || world < 1 || world > QS_MAX_RANKS) return JPEGQS_ERR_ARG;
+	for (int a = 0; a < world; a++) {
+		jpegqs_cuda_link *l = links[a];
+		if (!l || l->world != world || l->rank != a) return JPEGQS_ERR_ARG;
+		jpegqs_cuda_ctx *ctx = l->ctx;
+		CK(cudaSetDevice(ctx->device));
+		for (int b = 0; b < world; b++) {
+			if (b == a) continue;
+			int can = 0;
+			if (links[b]->ctx->device != ctx->device) {
+				CK(cudaDeviceCanAccessPeer(&can, ctx->device, links[b]->ctx->device));
+				if (!can) {
+					snprintf(ctx->err, sizeof(ctx->err), "device %d cannot access device %d's memory (no P2P path)",
+							ctx->device, links[b]->ctx->device);
+					return JPEGQS_ERR_CUDA;
+				}
+				cudaError_t e = cudaDeviceEnablePeerAccess(links[b]->ctx->device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+				cudaGetLastError();
+			}
+			l->peer[b] = links[b]->box;
+		}
+		l->connected = true;
+	}
+	return 0;
+}
+
+static char *box_rows(const jpegqs_cuda_link *l, char *box, int parity, int side, int slot) {
+	return box + QS_BOX_ROWS + (((size_t)parity * 2 + side) * QS_XCHG_SLOTS + slot) * l->row_bytes;
+}
+
+struct XchgPlane { uint8_t *plane; int wblk, rows; };
+
+/* one exchange on stream st: first / last pixel row of every plane to the neighbours, theirs into
+ * the halo rows; with bad_n > 0 also the OR of bad_dev[0..bad_n) over all ranks */
+static int slab_exchange(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *l, const std::vector<XchgPlane> &planes,
+		int *bad_dev, int bad_n, cudaStream_t st) {
+	if (!l || l->world == 1) return 0;
+	if (planes.size() > QS_XCHG_SLOTS || bad_n > 16) return JPEGQS_ERR_ARG;
+	uint32_t seq = ++l->seq; int parity = (int)(seq & 1), rank = l->rank, world = l->world;
+	QsXchgPush ps; QsXchgPull pl;
+	memset(&ps, 0, sizeof(ps)); memset(&pl, 0, sizeof(pl));
+	ps.seq = pl.seq = seq;
+	for (size_t k = 0; k < planes.size(); k++) {
+		const XchgPlane &p = planes[k];
+		uint32_t stride = (uint32_t)QS_PLANE_STRIDE(p.wblk); int h = p.rows * 8;
+		if (p.rows < 1 || stride > l->row_bytes) {
+			snprintf(ctx->err, sizeof(ctx->err), "sharded run: a rank holds no block row of a component, or the link is too narrow");
+			return JPEGQS_ERR_ARG;
+		}
+		if (rank > 0) {          /* my first pixel row is the upper neighbour's bottom halo (side 1 there) */
+			ps.rows[ps.nrows++] = { p.plane + (size_t)1 * stride, (uint8_t *)box_rows(l, l->peer[rank - 1], parity, 1, (int)k), stride, 0 };
+			pl.rows[pl.nrows++] = { (const uint8_t *)box_rows(l, l->box, parity, 0, (int)k), p.plane, stride, 0 };
+		}
+		if (rank < world - 1) {
+			ps.rows[ps.nrows++] = { p.plane + (size_t)h * stride, (uint8_t *)box_rows(l, l->peer[rank + 1], parity, 0, (int)k), stride, 0 };
+			pl.rows[pl.nrows++] = { (const uint8_t *)box_rows(l, l->box, parity, 1, (int)k), p.plane + (size_t)(h + 1) * stride, stride, 0 };
+		}
+	}
+	if (rank > 0) {
+		ps.flag[0] = (uint32_t *)(l->peer[rank - 1] + QS_BOX_HALO_FLAG) + 1;
+		pl.flag[0] = (const uint32_t *)(l->box + QS_BOX_HALO_FLAG) + 0;
+	}
+	if (rank < world - 1) {
+		ps.flag[1] = (uint32_t *)(l->peer[rank + 1] + QS_BOX_HALO_FLAG) + 0;
+		pl.flag[1] = (const uint32_t *)(l->box + QS_BOX_HALO_FLAG) + 1;
+	}
+	if (bad_n > 0) {
+		ps.bad_src = bad_dev; ps.bad_n = bad_n; pl.bad_io = bad_dev; pl.bad_n = bad_n;
+		for (int r = 0; r < world; r++) {
+			if (r == rank) continue;
+			ps.bad_dst[ps.npeers] = (uint32_t *)(l->peer[r] + QS_BOX_BAD_MASK) + (size_t)rank * 16;
+			ps.bad_flag[ps.npeers] = (uint32_t *)(l->peer[r] + QS_BOX_BAD_FLAG) + rank;
+			ps.npeers++;
+			pl.bad_in[pl.npeers] = (const uint32_t *)(l->box + QS_BOX_BAD_MASK) + (size_t)r * 16;
+			pl.bad_flag[pl.npeers] = (const uint32_t *)(l->box + QS_BOX_BAD_FLAG) + r;
+			pl.npeers++;
+		}
+	}
+	CK(cudaHostGetDevicePointer((void **)&pl.timeout_flag, l->timeout_host, 0));
+	CK(qs_launch_xchg(&ps, &pl, st));
+	ctx->launches += 2;
+	return 0;
+}
+
+/* do_quantsmooth on ONE SLAB of an image: img describes the slab (comp[].hblk = block rows held
+ * by this rank, coef / rows = those rows), geom where it sits.  The slab-local restatement of
+ * run_images (itself the reference driver, quantsmooth.h:2404-2878); the schedule is
+ * unconditional - what the reference decides with `stop` is decided on the device from the
+ * run's out-of-range flags (QsJob.stop_aware), which the ranks OR-combine in the first exchange
+ * of a phase - so every rank issues the same exchanges whatever its data look like. */
+static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_image *im, const jpegqs_cuda_slab *geom,
+		int flags, int niter, bool on_device, int *ret, cudaStream_t st) {
+	if (!ctx || !im || !geom) return JPEGQS_ERR_ARG;
+	const int rank = link ? link->rank : 0, world = link ? link->world : 1;
+	if (link && (link->ctx != ctx || !link->connected)) return JPEGQS_ERR_ARG;
+	if (geom->rank != rank || geom->world != world) return JPEGQS_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	ctx->launches = 0; ctx->last_ms = 0; ctx->ev_kind.clear(); ctx->ev_used = 0;
+	if (niter < 0) niter = 0;
+	if (niter > 100) niter = 100;
+	const int nc = im->ncomp;
+	if (nc < 1 || nc > JPEGQS_CUDA_MAX_COMP) return JPEGQS_ERR_ARG;
+	const bool top = rank == 0, bottom = rank == world - 1;
+	im->upsampled = 0;
+	if (ret) *ret = 0;
+	bool need_ds = (flags & (QS_JOINT_YUV | QS_UPSAMPLE_UV)) && im->is_ycbcr && nc >= 3 &&
+			im->comp[1].h_samp == 1 && im->comp[1].v_samp == 1 && im->comp[2].h_samp == 1 && im->comp[2].v_samp == 1;
+	if (niter <= 0 && !((flags & QS_UPSAMPLE_UV) && need_ds)) return 0;                   /* 2458 */
+	if (need_ds && (im->comp[1].wblk != im->comp[2].wblk || im->comp[1].hblk != im->comp[2].hblk)) return JPEGQS_ERR_ARG;
+	const bool sub = need_ds && !(im->comp[0].h_samp == 1 && im->comp[0].v_samp == 1);
+	const bool ups = sub && (flags & QS_UPSAMPLE_UV);
+	if (ctx->up) ctx->up->drain();
+	if (ctx->down) ctx->down->drain();
+	ctx->io_ev_used = 0;
+
+	/* ---- memory ---- */
+	size_t bytes = 0, stage_bytes = 0;
+	for (int ci = 0; ci < nc; ci++) {
+		jpegqs_cuda_comp *c = &im->comp[ci];
+		if (!(c->coef || (!on_device && c->rows)) && c->wblk && c->hblk) return JPEGQS_ERR_ARG;
+		if (world > 1 && (!c->hblk || !c->wblk)) {
+			snprintf(ctx->err, sizeof(ctx->err), "sharded run: rank %d holds no block row of component %d", rank, ci);
+			return JPEGQS_ERR_ARG;
+		}
+		size_t cb = (size_t)c->wblk * c->hblk * 128;
+		if (!on_device) { bytes += align256(cb); if (c->rows || !is_pinned(c->coef)) stage_bytes += align256(cb); }
+		bytes += align256(QS_PLANE_BYTES(c->wblk, c->hblk));
+	}
+	const size_t yb = (size_t)im->comp[0].wblk * im->comp[0].hblk;
+	if (sub) {
+		bytes += align256(QS_PLANE_BYTES(im->comp[1].wblk, im->comp[1].hblk));
+		if (ups) for (int j = 0; j < 2; j++) {
+			jpegqs_cuda_comp *c = &im->comp[1 + j];
+			if (!c->coef_up && !(!on_device && c->rows_up)) return JPEGQS_ERR_ARG;
+			bytes += align256(yb * 64);
+			if (!on_device) { bytes += align256(yb * 128); if (c->rows_up || !is_pinned(c->coef_up)) stage_bytes += align256(yb * 128); }
+		}
+	}
+	if (arena_reserve(ctx, bytes + 4096)) return JPEGQS_ERR_CUDA;
+	if (quant_reserve(ctx, nc)) return JPEGQS_ERR_CUDA;
+	if (stage_bytes && stage_reserve(ctx, stage_bytes)) return JPEGQS_ERR_CUDA;
+	size_t stage_pos = 0;
+	auto stage_take = [&](size_t b) { char *p = ctx->stage + stage_pos; stage_pos += align256(b); return (int16_t *)p; };
+	std::vector<std::unique_ptr<int16_t *[]> > rowstore;
+	auto flat_rows = [&](int16_t *base, uint32_t wblk, uint32_t hblk) -> int16_t *const * {
+		rowstore.emplace_back(new int16_t *[hblk ? hblk : 1]);
+		int16_t **t = rowstore.back().get();
+		for (uint32_t y = 0; y < hblk; y++) t[y] = base + (size_t)y * wblk * 64;
+		return t;
+	};
+	std::vector<CompWork> W(nc); std::vector<QsQuantDev> qhost(nc); std::vector<int> qval(nc);
+	for (int ci = 0; ci < nc; ci++) {
+		jpegqs_cuda_comp *c = &im->comp[ci]; CompWork &w = W[ci];
+		memset(&w, 0, sizeof(w));
+		w.ci = ci; w.c = c; w.W = c->wblk; w.H = c->hblk; w.luma = !ci || !im->is_ycbcr; w.qslot = ci;
+		size_t cb = (size_t)c->wblk * c->hblk * 128;
+		if (on_device) w.coef_dev = c->coef;
+		else {
+			w.coef_dev = (int16_t *)arena_take(ctx, cb);
+			if (c->rows) { w.rows = c->rows; w.pin = stage_take(cb); }
+			else if (is_pinned(c->coef)) { w.rows = NULL; w.pin = c->coef; }
+			else { w.rows = flat_rows(c->coef, c->wblk, c->hblk); w.pin = stage_take(cb); }
+		}
+		w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
+		quant_prepare(c->quant, &qhost[ci], &qval[ci], ctx->tune_maxn, ctx->tune_uni);
+	}
+	uint8_t *image2_buf = NULL, *mem_buf[2] = { NULL, NULL }; int16_t *coef_up_dev[2] = { NULL, NULL };
+	if (sub) {
+		image2_buf = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(im->comp[1].wblk, im->comp[1].hblk));
+		if (ups) for (int j = 0; j < 2; j++) {
+			jpegqs_cuda_comp *c = &im->comp[1 + j]; CompWork &w = W[1 + j];
+			mem_buf[j] = (uint8_t *)arena_take(ctx, yb * 64);
+			coef_up_dev[j] = on_device ? c->coef_up : (int16_t *)arena_take(ctx, yb * 128);
+			if (!on_device) {
+				if (c->rows_up) { w.rows_up = c->rows_up; w.pin_up = stage_take(yb * 128); }
+				else if (is_pinned(c->coef_up)) { w.rows_up = NULL; w.pin_up = c->coef_up; }
+				else { w.rows_up = flat_rows(c->coef_up, im->comp[0].wblk, im->comp[0].hblk); w.pin_up = stage_take(yb * 128); }
+			}
+		}
+	}
+	assign_sched_slots(qhost.data(), nc);
+	CK(cudaMemcpyAsync(ctx->quant_dev, qhost.data(), (size_t)nc * sizeof(QsQuantDev), cudaMemcpyHostToDevice, st));
+	ctx->jobs_cache[0].clear(); ctx->jobs_cache[1].clear();
+
+	/* ---- phases (luma | chroma when the chroma needs the finished luma, or to overlap the
+	 *      transfers of host buffers), uploads ---- */
+	const int ngroups = (need_ds || (!on_device && nc > 1)) ? 2 : 1;
+	auto group_range = [&](int g, int *c0, int *c1) {
+		if (ngroups == 2) { *c0 = g ? 1 : 0; *c1 = g ? nc : 1; } else { *c0 = 0; *c1 = nc; }
+	};
+	HostIo io(ctx);
+	int unit_of_group[2] = { -1, -1 };
+	auto seg_of = [&](const CompWork &w, int r0, int r1) {
+		IoSeg sg; sg.dev = w.coef_dev; sg.pin = w.pin; sg.rows = w.rows; sg.wblk = w.W; sg.r0 = r0; sg.r1 = r1;
+		return sg;
+	};
+	if (!on_device) {
+		while ((int)ctx->sync_ev.size() < 2 * ngroups) {
+			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->sync_ev.push_back(e);
+		}
+		for (int g = 0; g < ngroups; g++) {
+			int c0, c1; group_range(g, &c0, &c1);
+			std::vector<IoSeg> segs;
+			for (int ci = c0; ci < c1; ci++) if (W[ci].W && W[ci].H) segs.push_back(seg_of(W[ci], 0, W[ci].H));
+			unit_of_group[g] = io.add_unit(std::move(segs), ctx->sync_ev[2 * g]);
+		}
+		if (io.start()) return JPEGQS_ERR_CUDA;
+	}
+
+	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
+	int *bad_dev = ctx->flags_dev, *tile_counter = ctx->flags_dev + QS_MAX_JOBS;
+	CK(cudaMemsetAsync(bad_dev, 0, 16 * sizeof(int), st));
+	CK(cudaEventRecord(ctx->ev0, st));
+	auto make_job = [&](const CompWork &w, const uint8_t *plane2) {
+		QsJob j; memset(&j, 0, sizeof(j));
+		j.coef = w.coef_dev; j.plane = w.plane; j.plane2 = plane2;
+		j.quant = ctx->quant_dev + w.qslot;
+		j.wblk = w.W; j.hblk = w.H; j.stride = QS_PLANE_STRIDE(w.W); j.nblocks = w.W * w.H;
+		j.luma = w.luma; j.top_edge = top; j.bottom_edge = bottom;
+		j.bad_slot = w.ci; j.bad_first = 0; j.stop_aware = 1;
+		return j;
+	};
+	int static_stop_ci = 1 << 30;                          /* quantsmooth.h:2504: a quant value >= 0x800 */
+	uint8_t *image1 = NULL, *image2 = NULL;
+
+	for (int g = 0; g < ngroups; g++) {
+		if (!on_device && io.wait(unit_of_group[g], st)) return JPEGQS_ERR_CUDA;
+		int c0, c1; group_range(g, &c0, &c1);
+		std::vector<CompWork *> works;
+		for (int ci = c0; ci < c1; ci++) {
+			CompWork &w = W[ci];
+			if (!w.c->has_qtbl) continue;                                  /* 2494 */
+			w.extra = (image1 || (!ci && need_ds)) ? 1 : 0;                /* 2495 */
+			w.niter2 = qval[ci] <= 1 ? 0 : niter;                          /* 2501 */
+			if (qval[ci] >= 0x800 && ci < static_stop_ci) static_stop_ci = ci;
+			if (w.niter2 + w.extra == 0) continue;                         /* 2542 */
+			if (ci >= static_stop_ci) {                                    /* 2551-2566 */
+				CK(qs_launch_scale_clamp(w.coef_dev, (size_t)w.W * w.H * 64, ctx->quant_dev + w.qslot, 1, 0, st));
+				ctx->launches++;
+				continue;
+			}
+			if (!(w.W * w.H)) continue;
+			w.iterate = true;
+			works.push_back(&w);
+		}
+		int max_pass = 0;
+		for (CompWork *w : works) max_pass = std::max(max_pass, w->niter2 + w->extra);
+		auto p2_of = [&](const CompWork *w) -> const uint8_t * {
+			return (image2 && (flags & QS_JOINT_YUV) && w->ci > 0) ? image2 : NULL;
+		};
+		for (int iter = 0; iter < max_pass; iter++) {
+			std::vector<XchgPlane> xp;
+			for (int clampv = 0; clampv < 2; clampv++) {                   /* IDCT pass, 2589-2620 (+ final clamp) */
+				std::vector<QsJob> jobs;
+				for (CompWork *w : works) {
+					if (iter >= w->niter2 + w->extra) continue;
+					if (((iter == w->niter2) ? 1 : 0) != clampv) continue;
+					jobs.push_back(make_job(*w, NULL));
+					xp.push_back({ w->plane, w->W, w->H });
+				}
+				if (jobs.empty()) continue;
+				const QsJob *jd; int tiles;
+				if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles, true)) return JPEGQS_ERR_CUDA;
+				int mode = (iter == 0 ? QS_IDCT_DEQUANT : 0) | (clampv ? QS_IDCT_CLAMP : 0);
+				if (prof_begin(ctx, 0, st)) return JPEGQS_ERR_CUDA;
+				CK(qs_launch_idct_pass(jd, (int)jobs.size(), tiles, mode, bad_dev, st));
+				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
+				ctx->launches++;
+			}
+			/* halo rows from the neighbours; the first exchange of a phase also ORs the flags */
+			if ((!xp.empty() || iter == 0) && slab_exchange(ctx, link, xp, bad_dev, iter == 0 ? nc : 0, st)) return JPEGQS_ERR_CUDA;
+			for (int clampv = 0; clampv < 2; clampv++) {                   /* smoothing pass, 2627-2640 */
+				std::vector<QsJob> jobs;
+				for (CompWork *w : works) {
+					if (iter >= w->niter2) continue;
+					if (((iter == w->niter2 - 1 && !w->extra) ? 1 : 0) != clampv) continue;
+					jobs.push_back(make_job(*w, p2_of(w)));
+				}
+				if (jobs.empty()) continue;
+				const QsJob *jd; int tiles;
+				if (upload_jobs(ctx, 1, jobs, st, &jd, &tiles, true)) return JPEGQS_ERR_CUDA;
+				if (prof_begin(ctx, 1, st)) return JPEGQS_ERR_CUDA;
+				if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, (int)jobs.size(), tiles, flags, clampv, bad_dev, st));
+				else CK(qs_launch_smooth(jd, (int)jobs.size(), tiles, tabs, tile_counter, flags, clampv, ctx->num_sms,
+						ctx->tune_sync, ctx->tune_wpg, bad_dev, st));
+				if (prof_end(ctx, st)) return JPEGQS_ERR_CUDA;
+				ctx->launches++;
+			}
+		}
+		{	/* the component that overflowed is clamped only (2602-2610, 2670-2689); on the device */
+			std::vector<QsJob> jobs;
+			for (CompWork *w : works) jobs.push_back(make_job(*w, NULL));
+			if (!jobs.empty()) {
+				const QsJob *jd; int tiles;
+				if (upload_jobs(ctx, 0, jobs, st, &jd, &tiles, true)) return JPEGQS_ERR_CUDA;
+				CK(qs_launch_stop_fixup(jd, (int)jobs.size(), bad_dev, st));
+				ctx->launches++;
+			}
+		}
+		/* post steps: chroma up-sampling (2691-2752), luma planes (2753-2815); results are dropped
+		 * at the end if the run stopped */
+		for (CompWork *w : works) {
+			if (w->ci > 0 && image1 && w->ci <= 2) {
+				int ws = im->comp[0].h_samp, hs = im->comp[0].v_samp;
+				int w1 = ((int)im->image_width + ws - 1) / ws, h1 = ((int)im->image_height + hs - 1) / hs;
+				int W0 = im->comp[0].wblk, H0 = im->comp[0].hblk;
+				CK(qs_launch_upsample(w->plane, image2, QS_PLANE_STRIDE(w->W), image1, QS_PLANE_STRIDE(W0),
+						mem_buf[w->ci - 1], W0 * 8, w1, h1, ws, hs, W0 * 8, H0 * 8, (int)geom->row0[0] * 8, st));
+				CK(qs_launch_fdct_plane(mem_buf[w->ci - 1], W0 * 8, coef_up_dev[w->ci - 1], W0, H0, st));
+				ctx->launches += 2;
+			} else if (w->ci == 0 && need_ds) {
+				int ws = w->c->h_samp, hs = w->c->v_samp;
+				if (ws == 1 && hs == 1) image2 = w->plane;
+				else {
+					if (flags & QS_UPSAMPLE_UV) image1 = w->plane;
+					const jpegqs_cuda_comp *cc = &im->comp[1];
+					int h = (int)geom->hblk_total[0] * 8, h2 = (int)geom->hblk_total[1] * 8, h1_total = (h + hs - 1) / hs;
+					int first = top ? -1 : (int)geom->row0[1] * 8;
+					int last = bottom ? h2 : (int)(geom->row0[1] + cc->hblk) * 8 - 1;
+					int dstride = QS_PLANE_STRIDE(cc->wblk);
+					if (last >= first) {
+						CK(qs_launch_downsample(w->plane, QS_PLANE_STRIDE(w->W), w->W * 8, h,
+								image2_buf + (size_t)(first - (int)geom->row0[1] * 8 + 1) * dstride, dstride, (int)cc->wblk * 8, h2,
+								ws, hs, (int)geom->row0[0] * 8, first, last - first + 1, h1_total, st));
+						ctx->launches++;
+					}
+					image2 = image2_buf;
+					std::vector<XchgPlane> xp; xp.push_back({ image2_buf, (int)cc->wblk, (int)cc->hblk });
+					if (slab_exchange(ctx, link, xp, bad_dev, 0, st)) return JPEGQS_ERR_CUDA;
+				}
+			}
+		}
+		if (!on_device) {                                                  /* downloads of this phase */
+			CK(cudaEventRecord(ctx->sync_ev[2 * g + 1], st));
+			std::vector<IoSeg> segs;
+			for (int ci = c0; ci < c1; ci++) {
+				CompWork &w = W[ci];
+				if (w.W && w.H) segs.push_back(seg_of(w, 0, w.H));
+				if (image1 && ci >= 1 && ci <= 2) {
+					IoSeg sg; sg.dev = coef_up_dev[ci - 1]; sg.pin = w.pin_up; sg.rows = w.rows_up;
+					sg.wblk = im->comp[0].wblk; sg.r0 = 0; sg.r1 = im->comp[0].hblk;
+					segs.push_back(sg);
+				}
+			}
+			if (io.download(std::move(segs), ctx->sync_ev[2 * g + 1])) return JPEGQS_ERR_CUDA;
+		}
+	}
+	CK(cudaEventRecord(ctx->ev1, st));
+	CK(qs_copy_flags(bad_dev, ctx->flags_host, nc, st));
+	CK(cudaStreamSynchronize(st));
+	if (!on_device && io.finish()) return JPEGQS_ERR_CUDA;
+	if (link && *link->timeout_host) {
+		*link->timeout_host = 0;
+		snprintf(ctx->err, sizeof(ctx->err), "sharded run: a peer rank did not answer within 10 s");
+		return JPEGQS_ERR_CUDA;
+	}
+	int stop = static_stop_ci < (1 << 30) ? 1 : 0;
+	for (int ci = 0; ci < nc; ci++) if (W[ci].iterate && ctx->flags_host[ci]) stop = 1;
+	/* NOTE on upsampled chroma when the run stopped: coef_up holds data nobody will look at */
+	for (int ci = 0; ci < nc; ci++) if (im->comp[ci].has_qtbl) for (int k = 0; k < 64; k++) im->comp[ci].quant[k] = 1;
+	im->upsampled = (image1 && !stop) ? 1 : 0;
+	if (ret) *ret = stop;
+	CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+	if (prof_collect(ctx)) return JPEGQS_ERR_CUDA;
+	return 0;
+}
+
+extern "C" int jpegqs_cuda_run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_image *slab,
+		const jpegqs_cuda_slab *geom, int flags, int niter, int on_device, void *stream) {
+	int ret = 0;
+	if (!ctx) return JPEGQS_ERR_ARG;
+	int rc = run_slab(ctx, link, slab, geom, flags, niter, on_device != 0, &ret, stream ? (cudaStream_t)stream : ctx->stream);
+	return rc < 0 ? rc : ret;
+}
+
+/* ---- the devices of one process behind one call ------------------------------------------- */
+struct jpegqs_cuda_multi {
+	std::vector<jpegqs_cuda_ctx *> ctx;
+	std::vector<jpegqs_cuda_link *> link;
+	uint32_t max_wblk;
+	long min_blocks;                      /* luma blocks a device must get before another one is added */
+	char err[512];
+};
+
+static void multi_drop_links(jpegqs_cuda_multi *m) {
+	for (jpegqs_cuda_link *l : m->link) jpegqs_cuda_link_destroy(l);
+	m->link.clear(); m->max_wblk = 0;
+}
+
+extern "C" void jpegqs_cuda_multi_destroy(jpegqs_cuda_multi *m) {
+	if (!m) return;
+	multi_drop_links(m);
+	for (jpegqs_cuda_ctx *c : m->ctx) jpegqs_cuda_destroy(c);
+	delete m;
+}
+
+extern "C" int jpegqs_cuda_multi_create(int ndev, const int *devices, jpegqs_cuda_multi **out) {
+	jpegqs_cuda_ctx *ctx = NULL;
+	if (!out) return JPEGQS_ERR_ARG;
+	*out = NULL;
+	int have = 0;
+	CK(cudaGetDeviceCount(&have));
+	if (ndev <= 0) ndev = have;                          /* all devices */
+	if (ndev < 1 || ndev > QS_MAX_RANKS || (!devices && ndev > have)) {
+		snprintf(g_err, sizeof(g_err), "multi_create: %d device(s) asked for, %d present", ndev, have);
+		return JPEGQS_ERR_ARG;
+	}
+	jpegqs_cuda_multi *m = new jpegqs_cuda_multi();
+	m->max_wblk = 0; m->err[0] = 0;
+	const char *e = getenv("JPEGQS_MIN_BLOCKS_PER_GPU");
+	m->min_blocks = e ? atol(e) : 148L * 16 * 32;        /* one wave of the persistent smoothing kernel */
+	for (int i = 0; i < ndev; i++) {
+		jpegqs_cuda_ctx *c = NULL;
+		int rc = jpegqs_cuda_create(devices ? devices[i] : i, &c);
+		if (rc) { jpegqs_cuda_multi_destroy(m); return rc; }
+		m->ctx.push_back(c);
+	}
+	*out = m;
+	return 0;
+}
+
+extern "C" int jpegqs_cuda_multi_devices(const jpegqs_cuda_multi *m) { return m ? (int)m->ctx.size() : 0; }
+extern "C" jpegqs_cuda_ctx *jpegqs_cuda_multi_ctx(jpegqs_cuda_multi *m, int i) {
+	return m && i >= 0 && i < (int)m->ctx.size() ? m->ctx[i] : NULL;
+}
+extern "C" const char *jpegqs_cuda_multi_last_error(const jpegqs_cuda_multi *m) { return m ? m->err : g_err; }
+
+/* MCU-row ranges, sizes differing by at most one (slabs are MCU aligned, so the
+ * chroma / luma / down-sampled planes of a slab line up) */
+static void split_mcu_rows(int total, int world, int r, int *m0, int *m1) {
+	int base = total / world, rem = total % world;
+	*m0 = r * base + std::min(r, rem);
+	*m1 = *m0 + base + (r < rem ? 1 : 0);
+}
+
+/* how many devices an image of this geometry is worth (the north star's "only when the
+ * component is large enough to shard") */
+extern "C" int jpegqs_cuda_multi_plan(const jpegqs_cuda_multi *m, const jpegqs_cuda_image *img) {
+	if (!m || !img || img->ncomp < 1) return 0;
+	int maxv = 1;
+	for (int c = 0; c < img->ncomp; c++) maxv = std::max(maxv, (int)img->comp[c].v_samp);
+	int mcu_rows = ((int)img->image_height + 8 * maxv - 1) / (8 * maxv);
+	long blocks = (long)img->comp[0].wblk * img->comp[0].hblk;
+	int use = (int)std::min<long>((long)m->ctx.size(), std::max<long>(1, blocks / std::max<long>(1, m->min_blocks)));
+	use = std::min(use, mcu_rows);
+	/* every rank needs at least one block row of every component (libjpeg geometry is not MCU padded) */
+	while (use > 1) {
+		bool ok = true;
+		for (int r = 0; r < use && ok; r++) {
+			int m0, m1; split_mcu_rows(mcu_rows, use, r, &m0, &m1);
+			for (int c = 0; c < img->ncomp && ok; c++) {
+				int v = img->comp[c].v_samp, H = (int)img->comp[c].hblk;
+				ok = std::min(m1 * v, H) - std::min(m0 * v, H) >= 1;
+			}
+		}
+		if (ok) break;
+		use--;
+	}
+	return use;
+}
+
+extern "C" int jpegqs_cuda_run_host_multi(jpegqs_cuda_multi *m, jpegqs_cuda_image *img, int flags, int niter) {
+	if (!m || !img || img->ncomp < 1 || img->ncomp > JPEGQS_CUDA_MAX_COMP) return JPEGQS_ERR_ARG;
+	const int use = jpegqs_cuda_multi_plan(m, img);
+	if (use <= 1) {
+		int rc = jpegqs_cuda_run_host(m->ctx[0], img, flags, niter, 0, NULL, NULL);
+		if (rc < 0) snprintf(m->err, sizeof(m->err), "%s", jpegqs_cuda_last_error(m->ctx[0]));
+		return rc;
+	}
+	uint32_t maxw = 0; int maxv = 1;
+	for (int c = 0; c < img->ncomp; c++) { maxw = std::max(maxw, img->comp[c].wblk); maxv = std::max(maxv, (int)img->comp[c].v_samp); }
+	if ((int)m->link.size() != use || maxw > m->max_wblk) {
+		multi_drop_links(m);
+		for (int r = 0; r < use; r++) {
+			jpegqs_cuda_link *l = NULL;
+			int rc = jpegqs_cuda_link_create(m->ctx[r], r, use, maxw, &l);
+			if (rc) { snprintf(m->err, sizeof(m->err), "%s", jpegqs_cuda_last_error(m->ctx[r])); multi_drop_links(m); return rc; }
+			m->link.push_back(l);
+		}
+		int rc = jpegqs_cuda_link_connect_local(m->link.data(), use);
+		if (rc) { snprintf(m->err, sizeof(m->err), "%s", jpegqs_cuda_last_error(m->ctx[0])); multi_drop_links(m); return rc; }
+		m->max_wblk = maxw;
+	}
+	const int mcu_rows = ((int)img->image_height + 8 * maxv - 1) / (8 * maxv);
+	std::vector<jpegqs_cuda_image> slab(use, *img);
+	std::vector<jpegqs_cuda_slab> geom(use);
+	for (int r = 0; r < use; r++) {
+		int m0, m1; split_mcu_rows(mcu_rows, use, r, &m0, &m1);
+		memset(&geom[r], 0, sizeof(geom[r]));
+		geom[r].rank = r; geom[r].world = use;
+		for (int c = 0; c < img->ncomp; c++) {
+			const jpegqs_cuda_comp *src = &img->comp[c]; jpegqs_cuda_comp *d = &slab[r].comp[c];
+			int v = src->v_samp, H = (int)src->hblk;
+			int r0 = std::min(m0 * v, H), r1 = std::min(m1 * v, H);
+			geom[r].row0[c] = (uint32_t)r0; geom[r].hblk_total[c] = src->hblk;
+			d->hblk = (uint32_t)(r1 - r0);
+			if (src->rows) d->rows = src->rows + r0;
+			if (src->coef) d->coef = src->coef + (size_t)r0 * src->wblk * 64;
+		}
+		for (int c = 1; c <= 2 && c < img->ncomp; c++) {            /* luma-sized outputs of UPSAMPLE_UV */
+			const jpegqs_cuda_comp *src = &img->comp[c]; jpegqs_cuda_comp *d = &slab[r].comp[c];
+			if (src->rows_up) d->rows_up = src->rows_up + geom[r].row0[0];
+			if (src->coef_up) d->coef_up = src->coef_up + (size_t)geom[r].row0[0] * img->comp[0].wblk * 64;
+		}
+	}
+	/* one host thread per device: a rank's pull kernel waits for its neighbours' push kernels,
+	 * which only get enqueued if their host threads run */
+	std::vector<int> rc(use, 0);
+	std::vector<std::thread> th;
+	for (int r = 1; r < use; r++)
+		th.emplace_back([&, r] { rc[r] = jpegqs_cuda_run_slab(m->ctx[r], m->link[r], &slab[r], &geom[r], flags, niter, 0, NULL); });
+	rc[0] = jpegqs_cuda_run_slab(m->ctx[0], m->link[0], &slab[0], &geom[0], flags, niter, 0, NULL);
+	for (std::thread &t : th) t.join();
+	int out = 0;
+	for (int r = 0; r < use; r++) {
+		if (rc[r] < 0 && out >= 0) { out = rc[r]; snprintf(m->err, sizeof(m->err), "device %d: %s", r, jpegqs_cuda_last_error(m->ctx[r])); }
+		else if (out >= 0 && rc[r] > out) out = rc[r];
+	}
+	if (out < 0) { multi_drop_links(m); return out; }               /* sequence numbers may be out of step */
+	for (int c = 0; c < img->ncomp; c++) memcpy(img->comp[c].quant, slab[0].comp[c].quant, sizeof(img->comp[c].quant));
+	img->upsampled = slab[0].upsampled;
+	return out;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1241,12 +1876,12 @@ extern "C" int jpegqs_cuda_pass_smooth(jpegqs_cuda_ctx *ctx, int njobs, const jp
 	int rc = stage_jobs(ctx, njobs, jobs, 1, st, &jd, &tiles);
 	if (rc) return rc;
 	const float *tabs = (flags & QS_DIAGONALS) ? ctx->tab_diag : ctx->tab_plain;
-	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, st));
+	if (flags & QS_LOW_QUALITY) CK(qs_launch_lowq(jd, njobs, tiles, flags, clamp_out, NULL, st));
 #ifdef QS_EXPERIMENTS
 	else if (ctx->tune_x2) CK(qs_launch_smooth_x2(jd, njobs, tiles, (flags & QS_DIAGONALS) ? ctx->tab2_diag : ctx->tab2_plain,
 			ctx->nslots2, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, st));
 #endif
-	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, st));
+	else CK(qs_launch_smooth(jd, njobs, tiles, tabs, ctx->flags_dev + QS_MAX_JOBS, flags, clamp_out, ctx->num_sms, ctx->tune_sync, ctx->tune_wpg, NULL, st));
 	return 0;
 }
 

@@ -60,6 +60,13 @@ __device__ __forceinline__ int qs_find_job(const QsJob *__restrict__ jobs, int n
 	return lo;
 }
 
+/* what the reference's `stop` logic leaves to do for this job (see QsJob.stop_aware) */
+__device__ __forceinline__ int qs_job_state(const QsJob *job, const int *__restrict__ bad) {
+	if (!bad || !job->stop_aware) return 0;
+	for (int s = job->bad_first; s < job->bad_slot; s++) if (*(const volatile int *)&bad[s]) return 2;
+	return *(const volatile int *)&bad[job->bad_slot] ? 1 : 0;
+}
+
 /* a0 = round_half_away(c / q) * q  (reference quantsmooth.h:338-341 plain form; the
  * reference's reciprocal form 324-337 is equal on the valid range).
  * m31 = ceil(2^31 / q) makes floor((|c| + q/2) / q) one IMAD.HI; exact while
@@ -212,6 +219,114 @@ __device__ __forceinline__ float qs_regress(const uint8_t *__restrict__ A, const
 	return scale;
 }
 
+#ifdef QS_IDCT_PRIVATE
+/* measurement variant (make variant DEFS=-DQS_IDCT_PRIVATE): round 1's IDCT pass with
+ * thread-private int4 loads at a 128-byte lane stride, for A/B runs against the coalesced one */
+#ifndef QS_IDCT_MINB
+#define QS_IDCT_MINB 1
+#endif
+#define QS_IDCT_THREADS 256
+/* ------------------------------------------------------------------------------------------
+ * K1: IDCT pass.  One thread per block; lanes of a warp own 32 consecutive blocks, so the
+ * eight 8-byte row stores of a warp cover 256 contiguous bytes per pixel row.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256, QS_IDCT_MINB) qs_idct_pass_kernel(const QsJob *__restrict__ jobs, int njobs,
+		int total_tiles, int mode, int *__restrict__ bad_flags) {
+	int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (tile >= total_tiles) return;
+	int lane = threadIdx.x & 31;
+	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
+	if (!(mode & QS_IDCT_DEQUANT) && qs_job_state(job, bad_flags)) return;
+	int b = (tile - job->tile_begin) * 32 + lane;
+	if (b >= job->nblocks) return;
+	int W = job->wblk, H = job->hblk, stride = job->stride;
+	int by = b / W, bx = b - by * W;
+	int16_t *cptr = job->coef + (size_t)b * 64;
+	const QsQuantDev *qd = job->quant;
+
+	int c[64];
+	{
+		const int4 *p = (const int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int4 v = p[j];
+			c[j * 8 + 0] = (short)(v.x & 0xffff); c[j * 8 + 1] = v.x >> 16;
+			c[j * 8 + 2] = (short)(v.y & 0xffff); c[j * 8 + 3] = v.y >> 16;
+			c[j * 8 + 4] = (short)(v.z & 0xffff); c[j * 8 + 5] = v.z >> 16;
+			c[j * 8 + 6] = (short)(v.w & 0xffff); c[j * 8 + 7] = v.w >> 16;
+		}
+	}
+	if (mode & QS_IDCT_DEQUANT) {                       /* quantsmooth.h:2596-2603 */
+		int val = 0;
+#pragma unroll
+		for (int k = 0; k < 64; k++) {
+			int t = c[k] * (int)__ldg(&qd->qraw[k]);
+			val |= t + 0x800;
+			c[k] = (short)t;
+		}
+		if (val >> 12) atomicOr(&bad_flags[job->bad_slot], 1);
+	}
+
+	if (!(mode & QS_IDCT_NOPLANE)) {
+		int ws[64];
+#pragma unroll
+		for (int x = 0; x < 8; x++) {
+			int in[8], o[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) in[k] = c[k * 8 + x];
+			qs_islow_1d<1024>(in, o);
+#pragma unroll
+			for (int k = 0; k < 8; k++) ws[k * 8 + x] = o[k] >> 11;
+		}
+		uint32_t lo[8], hi[8];
+		qs_islow_rows(ws, lo, hi);
+
+		uint8_t *p = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
+#pragma unroll
+		for (int y = 0; y < 8; y++) *(uint2 *)(p + (size_t)y * stride) = make_uint2(lo[y], hi[y]);
+		/* replicated borders, quantsmooth.h:2612-2620 */
+		bool left = bx == 0, right = bx == W - 1;
+		if (left) {
+#pragma unroll
+			for (int y = 0; y < 8; y++) p[(size_t)y * stride - 1] = (uint8_t)(lo[y] & 0xff);
+		}
+		if (right) {
+#pragma unroll
+			for (int y = 0; y < 8; y++) p[(size_t)y * stride + 8] = (uint8_t)(hi[y] >> 24);
+		}
+		if (by == 0 && job->top_edge) {
+			uint8_t *r = p - stride;
+			*(uint2 *)r = make_uint2(lo[0], hi[0]);
+			if (left) r[-1] = (uint8_t)(lo[0] & 0xff);
+			if (right) r[8] = (uint8_t)(hi[0] >> 24);
+		}
+		if (by == H - 1 && job->bottom_edge) {
+			uint8_t *r = p + (size_t)8 * stride;
+			*(uint2 *)r = make_uint2(lo[7], hi[7]);
+			if (left) r[-1] = (uint8_t)(lo[7] & 0xff);
+			if (right) r[8] = (uint8_t)(hi[7] >> 24);
+		}
+	}
+
+	if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {
+		if (mode & QS_IDCT_CLAMP) {                     /* quantsmooth.h:2670-2689 */
+#pragma unroll
+			for (int k = 0; k < 64; k++) c[k] = min(max(c[k], -1023), 1023);
+		}
+		int4 *p = (int4 *)cptr;
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			int4 v;
+			v.x = (c[j * 8 + 0] & 0xffff) | (c[j * 8 + 1] << 16);
+			v.y = (c[j * 8 + 2] & 0xffff) | (c[j * 8 + 3] << 16);
+			v.z = (c[j * 8 + 4] & 0xffff) | (c[j * 8 + 5] << 16);
+			v.w = (c[j * 8 + 6] & 0xffff) | (c[j * 8 + 7] << 16);
+			p[j] = v;
+		}
+	}
+}
+
+#else
 /* ------------------------------------------------------------------------------------------
  * K1: IDCT pass (HBM bound: 128 B of coefficients in, 64 B of pixels out per block, + 128 B
  * back in the de-quantizing / clamping modes).  One thread per block, a warp owns 32
@@ -235,6 +350,8 @@ __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_ke
 	int tile = blockIdx.x * (QS_IDCT_THREADS / 32) + warp;
 	if (tile >= total_tiles) return;                    /* whole warps leave: only __syncwarp below */
 	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
+	/* a stopped component is only ever de-quantized (iteration 0); nothing else may touch it */
+	if (!(mode & QS_IDCT_DEQUANT) && qs_job_state(job, bad_flags)) return;
 	int b0 = (tile - job->tile_begin) * 32;
 	int nb = min(32, job->nblocks - b0);
 	uint32_t *sw = sm[warp];
@@ -333,6 +450,8 @@ __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_ke
 		}
 	}
 }
+
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * K2: the smoothing pass.
@@ -756,7 +875,7 @@ __device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, 
 template <bool DIAG, int SYNC>
 __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(const QsJob *__restrict__ jobs,
 		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
-		int flags, int clamp_out) {
+		int flags, int clamp_out, const int *__restrict__ bad) {
 	extern __shared__ __align__(16) uint32_t smem[];
 	__shared__ int s_tile[16];
 	__shared__ int s_sig[32];
@@ -844,7 +963,9 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 		int nblocks = job->nblocks;
 		int b = (tile - job->tile_begin) * 32 + lane;
-		bool valid = active && b < nblocks;
+		/* a stopped component walks through the passes like any other (the barrier sequence of
+		 * its lock-step group must not change) but never writes anything back */
+		bool valid = active && b < nblocks && !qs_job_state(job, bad);
 		if (b >= nblocks) b = nblocks - 1;              /* idle lanes shadow the last block */
 		int W = job->wblk, stride = job->stride;
 		int by = b / W, bx = b - by * W;
@@ -1007,14 +1128,14 @@ __device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, int *
 }
 
 __global__ void __launch_bounds__(128) qs_lowq_kernel(const QsJob *__restrict__ jobs, int njobs, int total_tiles,
-		int flags, int clamp_out) {
+		int flags, int clamp_out, const int *__restrict__ bad) {
 	__shared__ uint32_t sm[4 * 32 * 32];
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int tile = blockIdx.x * 4 + warp;
 	if (tile >= total_tiles) return;
 	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
 	int b = (tile - job->tile_begin) * 32 + lane;
-	if (b >= job->nblocks) return;
+	if (b >= job->nblocks || qs_job_state(job, bad)) return;
 	uint32_t *cw = sm + warp * 1024 + lane;
 	uint16_t *cs = (uint16_t *)(sm + warp * 1024) + lane * 2;
 	int W = job->wblk, stride = job->stride;
@@ -1188,6 +1309,99 @@ __global__ void qs_fdct_plane_kernel(const uint8_t *__restrict__ px, int pstride
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Sharded runs (one image cut into MCU-row slabs over several GPUs, qs_cuda.cu run_slab).
+ *
+ * qs_stop_fixup_kernel: the component whose coefficients overflowed is "clamped only"
+ * (quantsmooth.h:2602-2610 + 2670-2689): decided on the device from the run's flags.
+ *
+ * qs_xchg_push_kernel / qs_xchg_pull_kernel: the one neighbour exchange of the path
+ * (SURVEY.md 8e).  After an IDCT pass every rank stores its first / last pixel row of every
+ * plane straight into the neighbours' mailboxes - peer memory over NVLink (P2P mapping inside a
+ * process, CUDA IPC between processes) - then publishes a sequence number there; the pull
+ * kernel waits for its own mailbox's sequence numbers and moves the rows into the halo rows of
+ * the planes.  No host thread, no stream event and no NCCL call sits between the IDCT pass and
+ * the smoothing pass; mailboxes are double buffered by sequence parity, which is all the
+ * write-after-read protection the stream order of the neighbours leaves to do.  The first
+ * exchange of a phase also carries the "coefficient out of range" masks to every rank (OR).
+ * ------------------------------------------------------------------------------------------ */
+__global__ void qs_stop_fixup_kernel(const QsJob *__restrict__ jobs, int njobs, const int *__restrict__ bad) {
+	for (int j = 0; j < njobs; j++) {
+		const QsJob *job = jobs + j;
+		if (qs_job_state(job, bad) != 1) continue;
+		size_t n = (size_t)job->nblocks * 32;               /* coefficient pairs */
+		uint32_t *p = (uint32_t *)job->coef;
+		for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+			uint32_t w = p[i];
+			int a = (short)(w & 0xffff), c = (int)w >> 16;
+			a = min(max(a, -1023), 1023); c = min(max(c, -1023), 1023);
+			p[i] = (uint32_t)(a & 0xffff) | ((uint32_t)c << 16);
+		}
+	}
+}
+
+__device__ __forceinline__ void qs_copy_row(const uint8_t *src, uint8_t *dst, uint32_t bytes) {
+	/* plane rows start 8-byte aligned and are a multiple of 8 bytes long (QS_PLANE_STRIDE) */
+	const uint2 *s = (const uint2 *)src; uint2 *d = (uint2 *)dst;
+	for (uint32_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) d[i] = s[i];
+}
+
+__global__ void __launch_bounds__(512) qs_xchg_push_kernel(const __grid_constant__ QsXchgPush a) {
+	for (int r = 0; r < a.nrows; r++) qs_copy_row(a.rows[r].src, a.rows[r].dst, a.rows[r].bytes);
+	for (int i = threadIdx.x; i < a.bad_n * a.npeers; i += blockDim.x)
+		a.bad_dst[i / a.bad_n][i % a.bad_n] = (uint32_t)a.bad_src[i % a.bad_n];
+	__threadfence_system();                                  /* every thread: its own peer stores first */
+	__syncthreads();
+	if (threadIdx.x < 2 && a.flag[threadIdx.x]) *(volatile uint32_t *)a.flag[threadIdx.x] = a.seq;
+	if (threadIdx.x >= 32 && threadIdx.x < 32 + a.npeers && a.bad_n)
+		*(volatile uint32_t *)a.bad_flag[threadIdx.x - 32] = a.seq;
+	__threadfence_system();
+}
+
+__device__ __forceinline__ bool qs_wait_seq(const uint32_t *flag, uint32_t seq) {
+	unsigned long long t0 = 0, t; int spins = 0;
+	for (;;) {
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+		if ((int32_t)(v - seq) >= 0) return true;
+		if (++spins < 64) continue;
+		spins = 0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+		if (!t0) t0 = t;
+		if (t - t0 > 10000000000ull) return false;          /* 10 s: the peer is gone */
+		__nanosleep(200);
+	}
+}
+
+__global__ void __launch_bounds__(512) qs_xchg_pull_kernel(const __grid_constant__ QsXchgPull a) {
+	__shared__ int ok;
+	if (threadIdx.x == 0) ok = 1;
+	__syncthreads();
+	if (threadIdx.x < 2 && a.flag[threadIdx.x] && !qs_wait_seq(a.flag[threadIdx.x], a.seq)) ok = 0;
+	if (threadIdx.x >= 32 && threadIdx.x < 32 + a.npeers && a.bad_n && !qs_wait_seq(a.bad_flag[threadIdx.x - 32], a.seq)) ok = 0;
+	__syncthreads();
+	if (!ok) { if (threadIdx.x == 0 && a.timeout_flag) { *(volatile int *)a.timeout_flag = 1; __threadfence_system(); } return; }
+	for (int r = 0; r < a.nrows; r++) qs_copy_row(a.rows[r].src, a.rows[r].dst, a.rows[r].bytes);
+	for (int i = threadIdx.x; i < a.bad_n; i += blockDim.x) {
+		int v = a.bad_io[i];
+		for (int p = 0; p < a.npeers; p++) v |= (int)*(const volatile uint32_t *)&a.bad_in[p][i];
+		a.bad_io[i] = v;
+	}
+}
+
+cudaError_t qs_launch_stop_fixup(const QsJob *jobs_dev, int njobs, const int *bad, cudaStream_t st) {
+	if (njobs <= 0) return cudaSuccess;
+	qs_stop_fixup_kernel<<<148 * 4, 256, 0, st>>>(jobs_dev, njobs, bad);
+	return cudaGetLastError();
+}
+cudaError_t qs_launch_xchg(const QsXchgPush *push, const QsXchgPull *pull, cudaStream_t st) {
+	qs_xchg_push_kernel<<<1, 512, 0, st>>>(*push);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	qs_xchg_pull_kernel<<<1, 512, 0, st>>>(*pull);
+	return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------
  * Control-data movers.  Job lists and the "coefficient out of range" flags are a few hundred
  * bytes, but as cudaMemcpyAsync they queue on the copy engines BEHIND the bulk coefficient
  * transfers of the host entry points (measured: a 4-byte flag read waited 1.2 ms for a 66 MB
@@ -1212,7 +1426,7 @@ cudaError_t qs_set_chunks(const QsChunk *chunks, int n) {
 	return cudaMemcpyToSymbol(d_nchunks, &n, sizeof(int));
 }
 
-typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int);
+typedef void (*qs_smooth_fn)(const QsJob *, int, int, const float *, int *, int, int, const int *);
 #define QS_V(d, lvl, wps, gs) qs_smooth_kernel<d, QS_SYNC(lvl, wps, gs)>
 #ifdef QS_EXPERIMENTS
 static qs_smooth_fn qs_smooth_variant_x2(int diag, int sync) {
@@ -1287,7 +1501,7 @@ cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tile
 	int grid = (total_tiles + 15) / 16;
 	if (grid > num_sms) grid = num_sms;
 	qs_smooth_variant_x2(diag, sync == 1 ? 1 : 2)<<<grid, 512, qs_smooth_smem_bytes_x2(diag, nslots), st>>>(
-			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out, NULL);
 	return cudaGetLastError();
 }
 #endif
@@ -1301,7 +1515,7 @@ cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tile
 }
 
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st) {
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, const int *bad, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), st);
 	if (e != cudaSuccess) return e;
@@ -1316,14 +1530,14 @@ cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, 
 	int grid = (total_tiles + warps - 1) / warps;
 	if (grid > num_sms) grid = num_sms;
 	qs_smooth_variant(diag, sync, wpg)<<<grid, wpg * 128, qs_smooth_smem_bytes(diag, wpg), st>>>(
-			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out);
+			jobs_dev, njobs, total_tiles, tables_dev, tile_counter, flags, clamp_out, bad);
 	return cudaGetLastError();
 }
 
 cudaError_t qs_launch_lowq(const QsJob *jobs_dev, int njobs, int total_tiles, int flags, int clamp_out,
-		cudaStream_t st) {
+		const int *bad, cudaStream_t st) {
 	if (total_tiles <= 0) return cudaSuccess;
-	qs_lowq_kernel<<<(total_tiles + 3) / 4, 128, 0, st>>>(jobs_dev, njobs, total_tiles, flags, clamp_out);
+	qs_lowq_kernel<<<(total_tiles + 3) / 4, 128, 0, st>>>(jobs_dev, njobs, total_tiles, flags, clamp_out, bad);
 	return cudaGetLastError();
 }
 

@@ -16,9 +16,11 @@ cudaError_t qs_launch_smooth_x2(const QsJob *jobs_dev, int njobs, int total_tile
 cudaError_t qs_launch_idct_pass(const QsJob *jobs_dev, int njobs, int total_tiles, int mode,
 		int *bad_flags, cudaStream_t st);
 cudaError_t qs_launch_smooth(const QsJob *jobs_dev, int njobs, int total_tiles, const float *tables_dev,
-		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, cudaStream_t st);
+		int *tile_counter, int flags, int clamp_out, int num_sms, int sync, int wpg, const int *bad, cudaStream_t st);
 cudaError_t qs_launch_lowq(const QsJob *jobs_dev, int njobs, int total_tiles, int flags, int clamp_out,
-		cudaStream_t st);
+		const int *bad, cudaStream_t st);
+cudaError_t qs_launch_stop_fixup(const QsJob *jobs_dev, int njobs, const int *bad, cudaStream_t st);
+cudaError_t qs_launch_xchg(const QsXchgPush *push, const QsXchgPull *pull, cudaStream_t st);
 cudaError_t qs_launch_scale_clamp(int16_t *coef, size_t n, const QsQuantDev *qd, int dequant, int clamp,
 		cudaStream_t st);
 cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, uint8_t *dst, int dstride,

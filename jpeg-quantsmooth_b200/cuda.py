@@ -49,6 +49,11 @@ class _Job(C.Structure):
                 ("luma", C.c_int32), ("top_edge", C.c_int32), ("bottom_edge", C.c_int32)]
 
 
+class _Slab(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
+                ("row0", C.c_uint32 * MAX_COMP), ("hblk_total", C.c_uint32 * MAX_COMP)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int)
 PASS_DEQUANT, PASS_CLAMP = 1, 2
 
@@ -101,6 +106,22 @@ def load():
     lib.jpegqs_cuda_kernel_stats.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                              C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.jpegqs_cuda_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.jpegqs_cuda_link_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.jpegqs_cuda_link_destroy.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_link_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.jpegqs_cuda_link_connect_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    lib.jpegqs_cuda_link_connect_local.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.jpegqs_cuda_run_slab.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_Image), C.POINTER(_Slab), C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p]
+    lib.jpegqs_cuda_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    lib.jpegqs_cuda_multi_destroy.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_multi_devices.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    lib.jpegqs_cuda_multi_ctx.restype = C.c_void_p
+    lib.jpegqs_cuda_multi_last_error.argtypes = [C.c_void_p]
+    lib.jpegqs_cuda_multi_last_error.restype = C.c_char_p
+    lib.jpegqs_cuda_multi_plan.argtypes = [C.c_void_p, C.POINTER(_Image)]
+    lib.jpegqs_cuda_run_host_multi.argtypes = [C.c_void_p, C.POINTER(_Image), C.c_int, C.c_int]
     lib.jpegqs_cuda_tables.argtypes = [C.c_int, C.c_void_p]
     lib.jpegqs_cuda_orig_coef.argtypes = [C.c_int, C.c_int]
     _lib = lib
@@ -340,6 +361,42 @@ class QsContext:
                                                    C.c_void_p(stream or None)))
         return list(rets), [bool(a.upsampled) for a in arr]
 
+    # ---- one slab of a sharded image (include/jpegqs_cuda.h "one image sharded by MCU rows") ----
+    def run_slab(self, link, slab: CoefImage, rank: int, world: int, row0: Sequence[int],
+                 hblk_total: Sequence[int], flags: int, niter: int, coef_ptrs=None, up_ptrs=None, stream: int = 0):
+        """slab: CoefImage whose components hold this rank's block rows (width / height = the
+        WHOLE image's).  Host arrays (coef_ptrs None: slab.comps[].coef, modified IN PLACE, results
+        for UPSAMPLE_UV in the returned arrays) or device pointers (coef_ptrs / up_ptrs).
+        Returns (ret, upsampled, up_arrays)."""
+        on_device = coef_ptrs is not None
+        up_arrays = []
+        if not on_device:
+            coef_ptrs, up_ptrs = [], []
+            for c in slab.comps:
+                c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+                coef_ptrs.append(c.coef.ctypes.data)
+            if len(slab.comps) >= 3:
+                y = slab.comps[0]
+                up_ptrs.append(None)
+                for _ in range(2):
+                    a = np.zeros((y.hblk, y.wblk, 64), dtype=np.int16)
+                    up_arrays.append(a)
+                    up_ptrs.append(a.ctypes.data)
+        ci = _Image()
+        _fill_image(ci, slab, coef_ptrs, up_ptrs or [])
+        g = _Slab()
+        g.rank, g.world = rank, world
+        for k in range(len(slab.comps)):
+            g.row0[k], g.hblk_total[k] = int(row0[k]), int(hblk_total[k])
+        ret = self._check(self.lib.jpegqs_cuda_run_slab(self.h, link.h if link is not None else None, C.byref(ci),
+                                                       C.byref(g), flags & 0x7f, niter, int(on_device),
+                                                       C.c_void_p(stream or None)))
+        if not on_device:
+            for i, c in enumerate(slab.comps):
+                if c.quant is not None:
+                    c.quant = np.array(list(ci.comp[i].quant), dtype=np.uint16)
+        return ret, bool(ci.upsampled), up_arrays
+
     # ---- pass level (multi-GPU slabs) ----
     @staticmethod
     def make_job(coef_ptr, plane_ptr, plane2_ptr, wblk, hblk, quant, luma, top_edge, bottom_edge) -> _Job:
@@ -384,6 +441,99 @@ class QsContext:
 
     def plane_pad(self) -> int:
         return int(self.lib.jpegqs_cuda_plane_pad())
+
+
+class QsLink:
+    """This rank's mailbox + its view of the other ranks' (jpegqs_cuda_link)."""
+
+    def __init__(self, ctx: QsContext, rank: int, world: int, max_wblk: int):
+        self.ctx, self.lib, self.rank, self.world = ctx, ctx.lib, rank, world
+        h = C.c_void_p()
+        ctx._check(self.lib.jpegqs_cuda_link_create(ctx.h, rank, world, max_wblk, C.byref(h)))
+        self.h = h
+
+    def export(self) -> bytes:
+        n = self.lib.jpegqs_cuda_link_handle_bytes()
+        buf = C.create_string_buffer(n)
+        self.ctx._check(self.lib.jpegqs_cuda_link_export(self.h, buf))
+        return buf.raw
+
+    def connect_ipc(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        self.ctx._check(self.lib.jpegqs_cuda_link_connect_ipc(self.h, blob))
+
+    @staticmethod
+    def connect_local(links: Sequence["QsLink"]):
+        arr = (C.c_void_p * len(links))(*[l.h for l in links])
+        links[0].ctx._check(links[0].lib.jpegqs_cuda_link_connect_local(arr, len(links)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jpegqs_cuda_link_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class QsMulti:
+    """Several devices of this process behind one call (jpegqs_cuda_multi): what the C entry
+    point do_quantsmooth uses when JPEGQS_GPUS is set."""
+
+    def __init__(self, devices):
+        self.lib = load()
+        if isinstance(devices, int):
+            n, arr = devices, None
+        else:
+            n, arr = len(devices), (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.jpegqs_cuda_multi_create(n, arr, C.byref(h))
+        if rc:
+            raise QsError(f"jpegqs_cuda_multi_create failed ({rc}): {self.lib.jpegqs_cuda_last_error(None).decode()}")
+        self.h = h
+
+    def _image(self, out: CoefImage):
+        ptrs, ups, up_arrays = [], [], []
+        for c in out.comps:
+            c.coef = np.ascontiguousarray(c.coef, dtype=np.int16)
+            ptrs.append(c.coef.ctypes.data)
+        if len(out.comps) >= 3:
+            y = out.comps[0]
+            ups.append(None)
+            for _ in range(2):
+                a = np.zeros((y.hblk, y.wblk, 64), dtype=np.int16)
+                up_arrays.append(a)
+                ups.append(a.ctypes.data)
+        ci = _Image()
+        _fill_image(ci, out, ptrs, ups)
+        return ci, up_arrays
+
+    def plan(self, image: CoefImage) -> int:
+        ci, _ = self._image(image.clone())
+        return int(self.lib.jpegqs_cuda_multi_plan(self.h, C.byref(ci)))
+
+    def do_quantsmooth(self, image: CoefImage, flags: int, niter: int):
+        out = image.clone()
+        ci, up_arrays = self._image(out)
+        rc = self.lib.jpegqs_cuda_run_host_multi(self.h, C.byref(ci), flags & 0x7f, niter)
+        if rc < 0:
+            raise QsError(f"CUDA back end error {rc}: {self.lib.jpegqs_cuda_multi_last_error(self.h).decode()}")
+        QsContext._collect(out, ci, up_arrays)
+        return rc, out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.jpegqs_cuda_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default_ctx = {}

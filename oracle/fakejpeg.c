@@ -1,8 +1,8 @@
 /*
  * TEST INFRASTRUCTURE - not part of the product.
  *
- * A fake libjpeg front end: builds a jpeg_decompress_struct (compat layout,
- * include/compat/jpeglib.h) plus an in-memory jpeg_memory_mgr around flat
+ * A fake libjpeg front end: builds a jpeg_decompress_struct (the real libjpeg 6.2
+ * layout, include/libjpeg62/jpeglib.h) plus an in-memory jpeg_memory_mgr around flat
  * coefficient arrays, calls a do_quantsmooth-shaped function (the reference's,
  * the C restatement's, or the product's) and copies the results back out.
  * This is how the parity tests drive every implementation through the SAME

@@ -3,7 +3,7 @@
  *
  * Compiles the UNMODIFIED reference hot path (reference quantsmooth.h + idct.h,
  * included from where they lie under $(REF), never copied) into a shared
- * object under oracle/_ref/, against the minimal include/compat/jpeglib.h.
+ * object under oracle/_ref/, against include/libjpeg62/jpeglib.h (libjpeg API 6.2).
  * Built twice by oracle/Makefile:
  *   libqsref_scalar.so  gcc -O2 -DNO_SIMD -ffp-contract=off       (parity oracle)
  *   libqsref_avx512.so  gcc -O2 -mavx512f -mavx512dq -mavx512bw -mfma -fopenmp

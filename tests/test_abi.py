@@ -55,7 +55,7 @@ int main(void) {
 ''')
     exe = tmp_path / "t"
     lib = os.path.dirname(qs.cuda.lib_path())
-    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"),
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include", "libjpeg62"), "-I", os.path.join(ROOT, "include"),
                     str(src), "-o", str(exe), "-L", lib, "-ljpegqs_b200", f"-Wl,-rpath,{lib}"], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
     assert out[0].split() == [str(v) for v in (100, 1, 2, 4, 8, 16, 32, 64, 0x7f, 12, 15, 16, 1, 2, 4, 8, 16)]

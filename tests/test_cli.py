@@ -241,7 +241,7 @@ def test_codec_survives_corrupt_input(jpegs, tmp_path):
                     " { (void)a; (void)b; (void)c; return 0; }\n")
     csrc = os.path.join(ROOT, "jpeg-quantsmooth_b200", "csrc")
     r = subprocess.run(["/usr/bin/gcc", "-O1", "-g", "-fsanitize=address,undefined", "-DJPEGQS_NO_CUDA_RENDER",
-                        "-I", os.path.join(ROOT, "include", "compat"), "-I", os.path.join(ROOT, "include"), "-I", csrc,
+                        "-I", os.path.join(ROOT, "include", "libjpeg62"), "-I", os.path.join(ROOT, "include"), "-I", csrc,
                         "-o", exe, os.path.join(csrc, "jpegqs.c"), os.path.join(csrc, "jpegcoef.c"), str(stub), "-lpthread"],
                        capture_output=True, text=True)
     if r.returncode:
@@ -265,4 +265,5 @@ def test_codec_survives_corrupt_input(jpegs, tmp_path):
         f = tmp_path / "f.jpg"
         f.write_bytes(bytes(d))
         r = subprocess.run([exe, "-n", "0", "-i", "0", str(f), str(tmp_path / "o.jpg")], capture_output=True, timeout=60)
-        assert r.returncode in (0, 1), (it, r.returncode, r.stderr.decode()[-800:])
+        # 0 decoded, 1 rejected, 2 decoded with recoverable damage (the reference's warning status)
+        assert r.returncode in (0, 1, 2), (it, r.returncode, r.stderr.decode()[-800:])
