@@ -80,6 +80,10 @@ typedef struct jpegqs_control {
 JPEGQS_ATTR int do_quantsmooth(j_decompress_ptr srcinfo, jvirt_barray_ptr *coef_arrays,
 		jpegqs_control_t *opts);
 
+/* extension: create the CUDA context do_quantsmooth(flags) will use (device from the CPU field),
+ * e.g. on a second thread while the caller still decodes its file; returns 0 or a negative value */
+JPEGQS_ATTR int jpegqs_warmup(int flags);
+
 #ifndef TRANSCODE_ONLY
 /* decode helpers; replace reference libjpegqs.h:50-55 / quantsmooth.h:2880-2904 */
 JPEGQS_ATTR boolean jpegqs_start_decompress(j_decompress_ptr cinfo, jpegqs_control_t *opts);

@@ -118,6 +118,20 @@ static jpegqs_cuda_ctx *get_ctx(int ordinal_plus1) {
 	return g_ctx[slot];
 }
 
+/* Extension (include/libjpegqs.h): create the context do_quantsmooth(flags) will use.  CUDA
+ * initialisation + loading the kernels take a few hundred ms in a fresh process - as long as
+ * decoding a large file - so a tool can run this on a second thread while it parses its input
+ * (csrc/jpegqs.c does).  Silent on failure: the real call reports. */
+JPEGQS_ATTR
+int jpegqs_warmup(int flags) {
+	int slot = (flags >> JPEGQS_CPU_SHIFT) & JPEGQS_CPU_MASK, ok;
+	pthread_mutex_lock(&g_lock);
+	if (!g_ctx[slot] && jpegqs_cuda_create(slot ? slot - 1 : -1, &g_ctx[slot])) g_ctx[slot] = NULL;
+	ok = g_ctx[slot] != NULL;
+	pthread_mutex_unlock(&g_lock);
+	return ok ? 0 : JPEGQS_ERR_CUDA;
+}
+
 /* Block-row table of one virtual array: libjpeg keeps a whole-image coefficient array in memory
  * as separately allocated row groups (jmemmgr.c alloc_barray), and access_virt_barray returns
  * pointers into them.  The reference calls it once per row from inside its OpenMP loops

@@ -31,7 +31,11 @@
 #include "jpegcoef.h"
 #ifndef JPEGQS_NO_CUDA_RENDER      /* the reference-linked test build (oracle/Makefile) has no CUDA back end */
 #include "jpegqs_cuda.h"
+#include <pthread.h>
+static void *warmup_thread(void *arg) { jpegqs_warmup(*(int*)arg); return NULL; }
 #endif
+#include <sys/time.h>
+static double now_ms(void) { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec * 1e3 + tv.tv_usec * 1e-3; }
 
 static unsigned char *load_all(FILE *f, size_t *len) {
 	size_t cap = 1 << 20, n = 0, r; unsigned char *p = (unsigned char*)malloc(cap);
@@ -62,7 +66,11 @@ static int usage(const char *prog) {
 
 int main(int argc, char **argv) {
 	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
-	int i, ret, flags = 0, ppm = 0, io_err = 0, warnings;
+	int i, ret, flags = 0, ppm = 0, io_err = 0, warnings, warm = 0;
+	double t_start, t_read, t_smooth, t_write;
+#ifndef JPEGQS_NO_CUDA_RENDER
+	pthread_t warm_th;
+#endif
 	const char *in_name, *out_name;
 	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
 	jq_image im; char err[256]; jpegqs_control_t opts;
@@ -111,6 +119,12 @@ int main(int argc, char **argv) {
 	opts.threads = threads;
 	if (threads > 0) jq_set_threads(threads);
 
+	t_start = now_ms();
+#ifndef JPEGQS_NO_CUDA_RENDER
+	/* CUDA start-up (context + kernel image, a few hundred ms in a fresh process) overlaps with
+	 * reading and Huffman-decoding the input */
+	if (opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
+#endif
 	f = strcmp(in_name, "-") ? fopen(in_name, "rb") : stdin;
 	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", argv[0], in_name); return 1; }
 	data = load_all(f, &len);
@@ -123,8 +137,14 @@ int main(int argc, char **argv) {
 				im.cinfo.image_height, im.cinfo.num_components, im.progressive ? "progressive" : "sequential",
 				im.restart_interval);
 
+	t_read = now_ms();
 	ret = do_quantsmooth(&im.cinfo, im.coef_arrays, &opts);
+#ifndef JPEGQS_NO_CUDA_RENDER
+	if (warm) pthread_join(warm_th, NULL);
+#endif
+	(void)warm;
 	if (ret < 0) { jq_free(&im); return 2; }
+	t_smooth = now_ms();
 
 #ifdef JPEGQS_NO_CUDA_RENDER
 	if (ppm) { fprintf(stderr, "%s: --ppm needs the CUDA back end\n", argv[0]); jq_free(&im); return 1; }
@@ -182,6 +202,9 @@ int main(int argc, char **argv) {
 	if (fwrite(out, 1, outlen, f) != outlen) io_err = 1;
 	if (f != stdout ? fclose(f) != 0 : fflush(f) != 0) io_err = 1;      /* ENOSPC shows up at the flush */
 	if (io_err) fprintf(stderr, "%s: error writing \"%s\"\n", argv[0], out_name);
+	t_write = now_ms();
+	if (verbose) fprintf(stderr, "wall time: read + decode %.1f ms, do_quantsmooth %.1f ms (includes waiting for CUDA start-up), "
+			"encode + write %.1f ms\n", t_read - t_start, t_smooth - t_read, t_write - t_smooth);
 	warnings = im.warnings;
 	free(out); jq_free(&im);
 	/* the reference's exit status (quantsmooth.c:626): 2 when the codec met recoverable damage

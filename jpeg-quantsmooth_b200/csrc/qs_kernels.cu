@@ -219,11 +219,15 @@ __device__ __forceinline__ float qs_regress(const uint8_t *__restrict__ A, const
 	return scale;
 }
 
-#ifdef QS_IDCT_PRIVATE
-/* measurement variant (make variant DEFS=-DQS_IDCT_PRIVATE): round 1's IDCT pass with
- * thread-private int4 loads at a 128-byte lane stride, for A/B runs against the coalesced one */
+#ifndef QS_IDCT_COALESCED
+/* K1 as shipped: thread-private int4 loads at a 128-byte lane stride (the eight loads of a lane
+ * walk one 128-byte line, which L1 keeps), register cap raised occupancy.  Measured per 8K
+ * launch (average of the de-quantizing and the two plain passes of a step, profiles/README.md
+ * round 2): 179 registers / 8 warps per SM (round 1) 83.8 us, 128 registers / 16 warps 67.1 us;
+ * the shared-memory-transposed variant below (make variant DEFS=-DQS_IDCT_COALESCED) 151 / 97 /
+ * 78 us at 8 / 16 / 24 warps: the transposition costs more than the uncoalesced requests. */
 #ifndef QS_IDCT_MINB
-#define QS_IDCT_MINB 1
+#define QS_IDCT_MINB 2
 #endif
 #define QS_IDCT_THREADS 256
 /* ------------------------------------------------------------------------------------------
@@ -1127,7 +1131,10 @@ __device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, int *
 	for (int k = 0; k < 4; k++) { r[1 + k] = (w.x >> (8 * k)) & 0xff; r[5 + k] = (w.y >> (8 * k)) & 0xff; }
 }
 
-__global__ void __launch_bounds__(128) qs_lowq_kernel(const QsJob *__restrict__ jobs, int njobs, int total_tiles,
+#ifndef QS_LOWQ_MINB
+#define QS_LOWQ_MINB 4
+#endif
+__global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob *__restrict__ jobs, int njobs, int total_tiles,
 		int flags, int clamp_out, const int *__restrict__ bad) {
 	__shared__ uint32_t sm[4 * 32 * 32];
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1157,7 +1164,7 @@ __global__ void __launch_bounds__(128) qs_lowq_kernel(const QsJob *__restrict__ 
 		qs_joint_predict(img, img2, stride, qd, cs);
 	} else {
 		float range = 0.0f; int sum = 0;
-#pragma unroll 1
+#pragma unroll 7
 		for (int x = 1; x < 64; x++) {
 			int a = (short)cs[(x >> 1) * 64 + (x & 1)]; a = a < 0 ? -a : a;
 			range = FA(range, (float)((int)__ldg(&qd->q[x]) * a)); sum += a;

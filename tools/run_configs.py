@@ -96,18 +96,34 @@ def batch(cfg, n, flags, niter):
           "launches": ctx.last_launches})
 
 
+_link = {}
+
+
+def get_link(max_wblk):
+    """This rank's mailbox, connected to the other ranks' through CUDA IPC handles (the C slab
+    engine of include/jpegqs_cuda.h; torch.distributed only carries the handles)."""
+    if world == 1:
+        return None
+    if "l" not in _link or _link["w"] < max_wblk:
+        l = qs.cuda.QsLink(ctx, rank, world, max_wblk)
+        handles = [None] * world
+        dist.all_gather_object(handles, l.export())
+        l.connect_ipc(handles)
+        _link["l"], _link["w"] = l, max_wblk
+    return _link["l"]
+
+
 def sharded(cfg, size, flags, niter, check):
     total = (size + 15) // 16
     rng = mg.split_mcu_rows(total, world)[rank]
     slab = qs.synth.make_image_torch(size, size, "420", mcu_rows=rng, device=dev)
-    geom = mg.SlabGeom(True, size, size)
     fullh = [qs.blocks_for(size, c.v_samp, 2) for c in slab.comps]
+    row0 = [mg.comp_block_rows(rng, c.v_samp, fullh[k])[0] for k, c in enumerate(slab.comps)]
     src = [c.coef for c in slab.comps]
     work = [torch.empty_like(t) for t in src]
-    planes = [torch.empty((c.hblk * 8 + 2, mg.plane_stride(c.wblk)), dtype=torch.uint8, device=dev) for c in slab.comps]
-    passes = mg.CudaPasses(ctx, stream)
-    allreduce_flag = mg.make_flag_allreduce(dist, dev) if dist is not None else None
-
+    y = slab.comps[0]
+    ups = [torch.empty((y.hblk, y.wblk, 64), dtype=torch.int16, device=dev) for _ in range(2)] if flags & 4 else []
+    link = get_link(max(c.wblk for c in slab.comps))
     state = {}
 
     def copy_only():
@@ -116,16 +132,17 @@ def sharded(cfg, size, flags, niter, check):
 
     def fn():
         copy_only()
-        comps = [mg.SlabComp(work[k], planes[k], c.wblk, c.hblk, c.quant, k == 0, c.h_samp, c.v_samp,
-                             mg.comp_block_rows(rng, c.v_samp, fullh[k])[0], fullh[k]) for k, c in enumerate(slab.comps)]
-        state["ups"] = mg.run_slab(passes, comps, flags, niter, rank, world, dist, allreduce_flag, geom)[1]
-        state["comps"] = comps
+        ret, upsampled, _ = ctx.run_slab(link, slab, rank, world, row0, fullh, flags, niter,
+                                         coef_ptrs=[t.data_ptr() for t in work],
+                                         up_ptrs=([None] + [t.data_ptr() for t in ups]) if ups else [], stream=stream)
+        state["ups"] = upsampled
     ms = timed(fn, args.reps) - timed(copy_only, args.reps)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     res = {"config": cfg, "shape": f"{size}x{size} 4:2:0", "flags": flags, "niter": niter, "n_gpus": world,
+           "engine": "jpegqs_cuda_run_slab (kernel-side exchange over CUDA IPC mailboxes)",
            "ms": round(ms, 3), "mpix_s": round(size * size / 1e6 / (ms / 1e3), 1)}
     if check:
         # the sharded result of every rank's slab must equal the same rows of a single-GPU run
@@ -133,15 +150,15 @@ def sharded(cfg, size, flags, niter, check):
         torch.cuda.synchronize()
         full = qs.synth.make_image_torch(size, size, "420", device=dev)
         fw = [c.coef.clone() for c in full.comps]
-        y = full.comps[0]
-        fup = [torch.empty((y.hblk, y.wblk, 64), dtype=torch.int16, device=dev) for _ in range(2)]
+        yf = full.comps[0]
+        fup = [torch.empty((yf.hblk, yf.wblk, 64), dtype=torch.int16, device=dev) for _ in range(2)]
         _, ups1 = ctx.run_device(full, [t.data_ptr() for t in fw], [None] + [t.data_ptr() for t in fup], flags, niter, stream)
         torch.cuda.synchronize()
         bad = int(ups1 != state["ups"])
         for k, c in enumerate(full.comps):
             if ups1 and k in (1, 2):
-                r0, r1 = mg.comp_block_rows(rng, 2, y.hblk)
-                bad += int((fup[k - 1][r0:r1] != state["comps"][k].coef_up).sum().item())
+                r0, r1 = mg.comp_block_rows(rng, 2, yf.hblk)
+                bad += int((fup[k - 1][r0:r1] != ups[k - 1]).sum().item())
             else:
                 r0, r1 = mg.comp_block_rows(rng, c.v_samp, c.hblk)
                 bad += int((fw[k][r0:r1] != work[k]).sum().item())
@@ -150,6 +167,34 @@ def sharded(cfg, size, flags, niter, check):
             dist.all_reduce(b)
         res["mismatches_vs_single_gpu"] = int(b.item())
     emit(res)
+
+
+def lowq(w, h):
+    """LOW_QUALITY (-q 0..2): the one-shot 8-neighbour filter (quantsmooth.h:924-938, 1162-1178).
+    Reports the kernel's own time (CUDA events around the launches) next to the q4 time of the
+    same image - the reference's README claims 'about 10x faster'."""
+    im = qs.synth.make_image_torch(w, h, "420", device=dev)
+    src = [c.coef for c in im.comps]
+    work = [torch.empty_like(t) for t in src]
+    ctx.set_profiling(True)
+    out = {}
+    for name, flags, niter in (("q0 (flags 9)", 9, 3), ("q1 (flags 11)", 11, 3), ("q4 (flags 1)", 1, 3)):
+        tot, ker, n = 0.0, 0.0, 0
+        for rep in range(args.reps + 1):
+            for a, b in zip(work, src):
+                a.copy_(b)
+            torch.cuda.synchronize()
+            ctx.run_device(im, [t.data_ptr() for t in work], [], flags, niter, stream)
+            if rep:
+                _, _, sm, sn = ctx.kernel_stats()
+                tot += ctx.last_device_ms; ker += sm; n += sn
+        out[name] = {"ms_whole_run": round(tot / args.reps, 3), "smooth_kernel_ms_per_launch": round(ker / max(n, 1), 4)}
+    ctx.set_profiling(False)
+    nb = im.num_blocks
+    k0 = out["q0 (flags 9)"]["smooth_kernel_ms_per_launch"]
+    emit({"config": "lowq", "shape": f"{w}x{h} 4:2:0", "blocks": nb, "runs": out,
+          "lowq_kernel_algorithmic_GBps": round(nb * 256 / (k0 / 1e3) / 1e9, 1),
+          "speedup_q0_over_q4": round(out["q4 (flags 1)"]["ms_whole_run"] / out["q0 (flags 9)"]["ms_whole_run"], 2)})
 
 
 for cfg in [int(x) for x in args.configs.split(",")]:
@@ -165,5 +210,7 @@ for cfg in [int(x) for x in args.configs.split(",")]:
         sharded(5, args.size, 1, 5, args.check)
     elif cfg == 6:                      # q6 sharded (JOINT_YUV + UPSAMPLE_UV across slabs)
         sharded("6 (q6 sharded)", args.size, 7, 3, args.check)
+    elif cfg == 7:                      # LOW_QUALITY kernel
+        lowq(7680, 4320)
 if dist is not None:
     dist.destroy_process_group()
