@@ -123,7 +123,7 @@ int main(int argc, char **argv) {
 #ifndef JPEGQS_NO_CUDA_RENDER
 	/* CUDA start-up (context + kernel image, a few hundred ms in a fresh process) overlaps with
 	 * reading and Huffman-decoding the input */
-	if (opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
+	if ((opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) && !getenv("JPEGQS_NO_WARMUP")) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
 #endif
 	f = strcmp(in_name, "-") ? fopen(in_name, "rb") : stdin;
 	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", argv[0], in_name); return 1; }

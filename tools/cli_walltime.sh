@@ -1,0 +1,24 @@
+#!/bin/bash
+# wall-time breakdown of the jpegqs tool on an 8K file: each run is a fresh
+# process, so CUDA start-up is in; with and without the start-up overlap (JPEGQS_NO_WARMUP=1)
+cd "$(dirname "$0")/.."
+T=$(mktemp -d)
+python - "$T" <<'PY'
+import sys, numpy as np
+from PIL import Image
+rng = np.random.RandomState(5)
+h, w = 4320, 7680
+y, x = np.mgrid[0:h, 0:w]
+a = (128 + 60 * np.sin(x / 97.0) + 50 * np.cos(y / 131.0)).astype(np.float32)
+img = np.stack([a + rng.randint(-12, 12, (h, w)), a[::-1] + rng.randint(-12, 12, (h, w)), a.T[:h, :w] if False else a[:, ::-1]], -1).clip(0, 255).astype(np.uint8)
+Image.fromarray(img, "RGB").save(sys.argv[1] + "/in.jpg", quality=75)
+PY
+ls -la $T/in.jpg
+E=jpeg-quantsmooth_b200/csrc/jpegqs
+for mode in warm nowarm; do
+  for i in 1 2 3; do
+    if [ $mode = nowarm ]; then export JPEGQS_NO_WARMUP=1; else unset JPEGQS_NO_WARMUP; fi
+    /usr/bin/time -f "$mode run $i: total %e s" $E -v 1 -i 8 -q 3 $T/in.jpg $T/out.jpg 2>&1 | grep -v "^$T\|component\|quant\|^0" | tr '\n' ' '; echo
+  done
+done
+rm -rf $T

@@ -21,7 +21,11 @@ ap.add_argument("--height", type=int, default=4320)
 ap.add_argument("--reps", type=int, default=8)
 ap.add_argument("--threads", type=int, default=0)
 ap.add_argument("--contiguous", action="store_true")
+ap.add_argument("--gpus", type=int, default=0, help="JPEGQS_GPUS for do_quantsmooth; the image is stacked that many times (weak scaling)")
 a = ap.parse_args()
+if a.gpus > 1:
+    os.environ["JPEGQS_GPUS"] = str(a.gpus)
+    a.height *= a.gpus
 ol.ensure_built()
 lib = qs.cuda.load()
 im = qs.synth.make_image(a.width, a.height, "420")
