@@ -29,7 +29,8 @@ extern "C" {
 /* error codes (all negative); >= 0 return values are the reference's `stop` value */
 #define JPEGQS_ERR_CUDA  (-1)          /* CUDA runtime failure, see jpegqs_cuda_last_error */
 #define JPEGQS_ERR_ARG   (-2)          /* malformed arguments */
-#define JPEGQS_ERR_UNSUPPORTED (-3)    /* reserved (every JPEGQS_* flag combination is implemented) */
+#define JPEGQS_ERR_UNSUPPORTED (-3)    /* a knob of a measurement build asked of the shipped library */
+#define JPEGQS_ERR_TIMEOUT (-4)        /* sharded run: a peer rank did not answer (see last_error) */
 
 typedef struct jpegqs_cuda_ctx jpegqs_cuda_ctx;
 

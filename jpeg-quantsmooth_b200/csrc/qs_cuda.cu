@@ -1243,12 +1243,12 @@ extern "C" int jpegqs_cuda_link_create(jpegqs_cuda_ctx *ctx, int rank, int world
 	l->box_bytes = QS_BOX_ROWS + (size_t)2 * 2 * QS_XCHG_SLOTS * l->row_bytes;
 	cudaError_t e = cudaMalloc((void **)&l->box, l->box_bytes);
 	if (e == cudaSuccess) e = cudaMemset(l->box, 0, l->box_bytes);
-	if (e == cudaSuccess) e = cudaHostAlloc((void **)&l->timeout_host, sizeof(int), cudaHostAllocMapped);
+	if (e == cudaSuccess) e = cudaHostAlloc((void **)&l->timeout_host, 4 * sizeof(int), cudaHostAllocMapped);
 	if (e != cudaSuccess) {
 		snprintf(ctx->err, sizeof(ctx->err), "link_create: %s", cudaGetErrorString(e));
 		cudaFree(l->box); delete l; return JPEGQS_ERR_CUDA;
 	}
-	*l->timeout_host = 0;
+	memset(l->timeout_host, 0, 4 * sizeof(int));
 	l->peer[rank] = l->box;
 	l->connected = world == 1;
 	*out = l;
@@ -1490,7 +1490,7 @@ static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_im
 		if (ngroups == 2) { *c0 = g ? 1 : 0; *c1 = g ? nc : 1; } else { *c0 = 0; *c1 = nc; }
 	};
 	HostIo io(ctx);
-	int unit_of_group[2] = { -1, -1 };
+	int unit_of_group[2] = { -1, -1 }, nbands[2] = { 1, 1 };
 	auto seg_of = [&](const CompWork &w, int r0, int r1) {
 		IoSeg sg; sg.dev = w.coef_dev; sg.pin = w.pin; sg.rows = w.rows; sg.wblk = w.W; sg.r0 = r0; sg.r1 = r1;
 		return sg;
@@ -1499,11 +1499,24 @@ static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_im
 		while ((int)ctx->sync_ev.size() < 2 * ngroups) {
 			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->sync_ev.push_back(e);
 		}
+		/* a phase travels in bands of ~8 MB: the H2D copy of band k runs while band k+1 is being
+		 * gathered (and, on the way back, band k is scattered while band k+1 is still in flight) */
+		while ((int)ctx->slab_ev.size() < 2 * ngroups * QS_MAX_SLABS) {
+			cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->slab_ev.push_back(e);
+		}
 		for (int g = 0; g < ngroups; g++) {
 			int c0, c1; group_range(g, &c0, &c1);
-			std::vector<IoSeg> segs;
-			for (int ci = c0; ci < c1; ci++) if (W[ci].W && W[ci].H) segs.push_back(seg_of(W[ci], 0, W[ci].H));
-			unit_of_group[g] = io.add_unit(std::move(segs), ctx->sync_ev[2 * g]);
+			size_t gb = 0;
+			for (int ci = c0; ci < c1; ci++) gb += (size_t)W[ci].W * W[ci].H * 128;
+			nbands[g] = (int)std::min<size_t>(QS_MAX_SLABS, std::max<size_t>(1, gb >> 23));
+			for (int k = 0; k < nbands[g]; k++) {
+				std::vector<IoSeg> segs;
+				for (int ci = c0; ci < c1; ci++) {
+					int r0 = (int)((long)k * W[ci].H / nbands[g]), r1 = (int)((long)(k + 1) * W[ci].H / nbands[g]);
+					if (W[ci].W && r1 > r0) segs.push_back(seg_of(W[ci], r0, r1));
+				}
+				unit_of_group[g] = io.add_unit(std::move(segs), k == nbands[g] - 1 ? ctx->sync_ev[2 * g] : ctx->slab_ev[(2 * g) * QS_MAX_SLABS + k]);
+			}
 		}
 		if (io.start()) return JPEGQS_ERR_CUDA;
 	}
@@ -1631,19 +1644,23 @@ static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_im
 				}
 			}
 		}
-		if (!on_device) {                                                  /* downloads of this phase */
+		if (!on_device) {                                                  /* downloads of this phase, band by band */
 			CK(cudaEventRecord(ctx->sync_ev[2 * g + 1], st));
-			std::vector<IoSeg> segs;
-			for (int ci = c0; ci < c1; ci++) {
-				CompWork &w = W[ci];
-				if (w.W && w.H) segs.push_back(seg_of(w, 0, w.H));
-				if (image1 && ci >= 1 && ci <= 2) {
-					IoSeg sg; sg.dev = coef_up_dev[ci - 1]; sg.pin = w.pin_up; sg.rows = w.rows_up;
-					sg.wblk = im->comp[0].wblk; sg.r0 = 0; sg.r1 = im->comp[0].hblk;
-					segs.push_back(sg);
+			for (int k = 0; k < nbands[g]; k++) {
+				std::vector<IoSeg> segs;
+				for (int ci = c0; ci < c1; ci++) {
+					CompWork &w = W[ci];
+					int r0 = (int)((long)k * w.H / nbands[g]), r1 = (int)((long)(k + 1) * w.H / nbands[g]);
+					if (w.W && r1 > r0) segs.push_back(seg_of(w, r0, r1));
+					if (image1 && ci >= 1 && ci <= 2) {
+						int H0 = (int)im->comp[0].hblk;
+						IoSeg sg; sg.dev = coef_up_dev[ci - 1]; sg.pin = w.pin_up; sg.rows = w.rows_up;
+						sg.wblk = im->comp[0].wblk; sg.r0 = (int)((long)k * H0 / nbands[g]); sg.r1 = (int)((long)(k + 1) * H0 / nbands[g]);
+						if (sg.r1 > sg.r0) segs.push_back(sg);
+					}
 				}
+				if (io.download(std::move(segs), ctx->sync_ev[2 * g + 1])) return JPEGQS_ERR_CUDA;
 			}
-			if (io.download(std::move(segs), ctx->sync_ev[2 * g + 1])) return JPEGQS_ERR_CUDA;
 		}
 	}
 	CK(cudaEventRecord(ctx->ev1, st));
@@ -1651,9 +1668,12 @@ static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_im
 	CK(cudaStreamSynchronize(st));
 	if (!on_device && io.finish()) return JPEGQS_ERR_CUDA;
 	if (link && *link->timeout_host) {
-		*link->timeout_host = 0;
-		snprintf(ctx->err, sizeof(ctx->err), "sharded run: a peer rank did not answer within 10 s");
-		return JPEGQS_ERR_CUDA;
+		int *t = link->timeout_host;
+		snprintf(ctx->err, sizeof(ctx->err), "sharded run: rank %d of %d waited 10 s for %s %d: sequence %d expected, %d found "
+				"(its own count: %u)", rank, world, t[1] > 32 ? "the mask message of peer" : "the halo rows of neighbour", 
+				t[1] > 32 ? t[1] - 33 : t[1] - 1, t[2], t[3], link->seq);
+		memset(t, 0, 4 * sizeof(int));
+		return JPEGQS_ERR_TIMEOUT;
 	}
 	int stop = static_stop_ci < (1 << 30) ? 1 : 0;
 	for (int ci = 0; ci < nc; ci++) if (W[ci].iterate && ctx->flags_host[ci]) stop = 1;
@@ -1813,10 +1833,12 @@ extern "C" int jpegqs_cuda_run_host_multi(jpegqs_cuda_multi *m, jpegqs_cuda_imag
 	rc[0] = jpegqs_cuda_run_slab(m->ctx[0], m->link[0], &slab[0], &geom[0], flags, niter, 0, NULL);
 	for (std::thread &t : th) t.join();
 	int out = 0;
-	for (int r = 0; r < use; r++) {
-		if (rc[r] < 0 && out >= 0) { out = rc[r]; snprintf(m->err, sizeof(m->err), "device %d: %s", r, jpegqs_cuda_last_error(m->ctx[r])); }
-		else if (out >= 0 && rc[r] > out) out = rc[r];
-	}
+	for (int pass = 0; pass < 2 && out >= 0; pass++)            /* a timeout is usually the echo of another rank's error */
+		for (int r = 0; r < use; r++)
+			if (rc[r] < 0 && out >= 0 && (pass == 1 || rc[r] != JPEGQS_ERR_TIMEOUT)) {
+				out = rc[r]; snprintf(m->err, sizeof(m->err), "rank %d: %s", r, jpegqs_cuda_last_error(m->ctx[r]));
+			}
+	for (int r = 0; r < use && out >= 0; r++) if (rc[r] > out) out = rc[r];
 	if (out < 0) { multi_drop_links(m); return out; }               /* sequence numbers may be out of step */
 	for (int c = 0; c < img->ncomp; c++) memcpy(img->comp[c].quant, slab[0].comp[c].quant, sizeof(img->comp[c].quant));
 	img->upsampled = slab[0].upsampled;

@@ -160,7 +160,7 @@ __device__ __forceinline__ void qs_pair_sections(const uint2 *pw, const float *c
 
 template <int NP, bool DIAG>
 __device__ __forceinline__ void qs_chunk_pairs(const QsChunk2 &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, long long *msum) {
 	const float *tab[NP]; float Rs[2 * NP]; qs_u64 a2[NP], a3[NP];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -178,8 +178,8 @@ __device__ __forceinline__ void qs_chunk_pairs(const QsChunk2 &ch, const float *
 	for (int c = 0; c < NP; c++) {
 		float x2a, x2b, x3a, x3b;
 		qs_unpk(a2[c], x2a, x2b); qs_unpk(a3[c], x3a, x3b);
-		if (ch.idx[2 * c] < 64) qs_coef_update<1>(&x2a, &x3a, &ch.idx[2 * c], qd, cs);
-		if (ch.idx[2 * c + 1] < 64) qs_coef_update<1>(&x2b, &x3b, &ch.idx[2 * c + 1], qd, cs);
+		if (ch.idx[2 * c] < 64) qs_coef_update<1>(&x2a, &x3a, &ch.idx[2 * c], qd, cs, msum);
+		if (ch.idx[2 * c + 1] < 64) qs_coef_update<1>(&x2b, &x3b, &ch.idx[2 * c + 1], qd, cs, msum);
 	}
 }
 

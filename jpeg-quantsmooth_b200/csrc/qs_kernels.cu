@@ -105,8 +105,7 @@ __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	z2 = in[2]; z3 = in[6];
 	z1 = (z2 + z3) * 4433;
 	a = z1 - z3 * 15137; b = z1 + z2 * 6270;
-	t0 = (in[0] + in[4]) * 8192 + RND; t1 = (in[0] - in[4]) * 8192 + RND;
-	e0 = t0 + b; e3 = t0 - b; e1 = t1 + a; e2 = t1 - a;
+	e0 = (in[0] + in[4]) * 8192 + RND; e1 = (in[0] - in[4]) * 8192 + RND;
 	t0 = in[7]; t1 = in[5]; t2 = in[3]; t3 = in[1];
 	z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;
 	z5 = (z3 + z4) * 9633;
@@ -114,8 +113,11 @@ __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	z1 *= 7373; z2 *= 20995; z3 *= 16069; z4 *= 3196;
 	z3 = z5 - z3; z4 = z5 - z4;
 	t0 += z3 - z1; t1 += z4 - z2; t2 += z3 - z2; t3 += z4 - z1;
-	out[0] = e0 + t3; out[7] = e0 - t3; out[1] = e1 + t2; out[6] = e1 - t2;
-	out[2] = e2 + t1; out[5] = e2 - t1; out[3] = e3 + t0; out[4] = e3 - t0;
+	/* three-input sums (one IADD3 each, on the ALU pipe the butterflies' IMADs leave idle)
+	 * instead of forming the even part first: wrap-around integer sums, same values */
+	out[0] = e0 + b + t3; out[7] = e0 + b - t3; out[1] = e1 + a + t2; out[6] = e1 + a - t2;
+	out[2] = e1 - a + t1; out[5] = e1 - a - t1; out[3] = e0 - b + t0; out[4] = e0 - b - t0;
+	(void)e2; (void)e3;
 }
 
 /* four int32 -> four saturated bytes b0 | b1<<8 | b2<<16 | b3<<24 */
@@ -332,42 +334,34 @@ __global__ void __launch_bounds__(256, QS_IDCT_MINB) qs_idct_pass_kernel(const Q
 
 #else
 /* ------------------------------------------------------------------------------------------
- * K1: IDCT pass (HBM bound: 128 B of coefficients in, 64 B of pixels out per block, + 128 B
- * back in the de-quantizing / clamping modes).  One thread per block, a warp owns 32
- * consecutive blocks = 4 KB of contiguous coefficients.  The warp moves those 4 KB with eight
- * fully coalesced 512-byte requests and transposes them through shared memory ([word][block],
- * row stride 33 words: conflict free both ways), so a request touches 4 cache lines instead of
- * the 32 that per-thread int4 loads at a 128-byte lane stride touch, and the coefficients live
- * in shared memory instead of 64 registers: 2 CTAs per SM keep 16 warps x 4 KB of loads in
- * flight (round 1: thread-private loads, 169 registers, 8 warps per SM, 0.33 of HBM peak).
- * The eight 8-byte row stores of a warp cover 256 contiguous bytes per pixel row.
+ * K1, coalesced variant: a warp owns 32 consecutive blocks = 4 KB of contiguous coefficients and
+ * moves them with eight fully coalesced 512-byte requests (4 cache lines per request instead of
+ * the 32 that per-thread loads at a 128-byte lane stride touch: no LSU queue pressure), staged in
+ * shared memory as 16-byte chunks in 128-byte rows with the chunk index XOR-ed by the row
+ * number - the 8 lanes of a quarter warp then hit 8 different chunk columns both when the tile is
+ * stored (one row, chunks 0..7) and when every lane fetches its own block (8 rows, one chunk
+ * each): conflict-free 128-bit shared accesses, 8 STS.128 + 8 LDS.128 per thread.
  * ------------------------------------------------------------------------------------------ */
 #ifndef QS_IDCT_MINB
 #define QS_IDCT_MINB 2
 #endif
 #define QS_IDCT_THREADS 256
-#define QS_IDCT_SROW 33
 __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_kernel(const QsJob *__restrict__ jobs,
 		int njobs, int total_tiles, int mode, int *__restrict__ bad_flags) {
-	__shared__ uint32_t sm[QS_IDCT_THREADS / 32][32 * QS_IDCT_SROW];
+	__shared__ int4 sm[QS_IDCT_THREADS / 32][32 * 8];
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int tile = blockIdx.x * (QS_IDCT_THREADS / 32) + warp;
 	if (tile >= total_tiles) return;                    /* whole warps leave: only __syncwarp below */
 	const QsJob *job = jobs + qs_find_job(jobs, njobs, tile);
-	/* a stopped component is only ever de-quantized (iteration 0); nothing else may touch it */
 	if (!(mode & QS_IDCT_DEQUANT) && qs_job_state(job, bad_flags)) return;
 	int b0 = (tile - job->tile_begin) * 32;
 	int nb = min(32, job->nblocks - b0);
-	uint32_t *sw = sm[warp];
+	int4 *sw = sm[warp];
 	int4 *g = (int4 *)(job->coef + (size_t)b0 * 64);
 #pragma unroll
 	for (int j = 0; j < 8; j++) {
-		int P = j * 32 + lane;                          /* 16-byte piece P of the tile: block P/8, words 4*(P%8).. */
-		if ((P >> 3) < nb) {
-			int4 v = g[P];
-			uint32_t *d = sw + (4 * (P & 7)) * QS_IDCT_SROW + (P >> 3);
-			d[0] = v.x; d[QS_IDCT_SROW] = v.y; d[2 * QS_IDCT_SROW] = v.z; d[3 * QS_IDCT_SROW] = v.w;
-		}
+		int P = j * 32 + lane, blk = P >> 3;            /* 16-byte chunk P of the tile: block P/8, chunk P%8 */
+		if (blk < nb) sw[blk * 8 + ((P & 7) ^ (blk & 7))] = g[P];
 	}
 	__syncwarp();
 	const bool valid = lane < nb;
@@ -375,34 +369,38 @@ __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_ke
 	int b = b0 + (valid ? lane : 0);
 	int by = b / W, bx = b - by * W;
 	const QsQuantDev *qd = job->quant;
-	uint32_t *cwp = sw + lane;                          /* coefficient pair p of this lane's block: cwp[p * SROW] */
 
 	if (valid) {
-		int ws[64], val = 0;
+		int c[64];
 #pragma unroll
-		for (int xp = 0; xp < 4; xp++) {
-			int a[8], c[8], oa[8], oc[8];
-#pragma unroll
-			for (int k = 0; k < 8; k++) {
-				uint32_t w = cwp[(k * 4 + xp) * QS_IDCT_SROW];
-				a[k] = (short)(w & 0xffff); c[k] = (int)w >> 16;
-				if (mode & QS_IDCT_DEQUANT) {               /* quantsmooth.h:2596-2603 */
-					int t0 = a[k] * (int)__ldg(&qd->qraw[k * 8 + 2 * xp]);
-					int t1 = c[k] * (int)__ldg(&qd->qraw[k * 8 + 2 * xp + 1]);
-					val |= (t0 + 0x800) | (t1 + 0x800);
-					a[k] = (short)t0; c[k] = (short)t1;
-					cwp[(k * 4 + xp) * QS_IDCT_SROW] = (uint32_t)(a[k] & 0xffff) | ((uint32_t)c[k] << 16);
-				}
-			}
-			if (!(mode & QS_IDCT_NOPLANE)) {
-				qs_islow_1d<1024>(a, oa); qs_islow_1d<1024>(c, oc);
-#pragma unroll
-				for (int k = 0; k < 8; k++) { ws[k * 8 + 2 * xp] = oa[k] >> 11; ws[k * 8 + 2 * xp + 1] = oc[k] >> 11; }
-			}
+		for (int j = 0; j < 8; j++) {
+			int4 v = sw[lane * 8 + (j ^ (lane & 7))];
+			c[j * 8 + 0] = (short)(v.x & 0xffff); c[j * 8 + 1] = v.x >> 16;
+			c[j * 8 + 2] = (short)(v.y & 0xffff); c[j * 8 + 3] = v.y >> 16;
+			c[j * 8 + 4] = (short)(v.z & 0xffff); c[j * 8 + 5] = v.z >> 16;
+			c[j * 8 + 6] = (short)(v.w & 0xffff); c[j * 8 + 7] = v.w >> 16;
 		}
-		if ((mode & QS_IDCT_DEQUANT) && (val >> 12)) atomicOr(&bad_flags[job->bad_slot], 1);
-
+		if (mode & QS_IDCT_DEQUANT) {                       /* quantsmooth.h:2596-2603 */
+			int val = 0;
+#pragma unroll
+			for (int k = 0; k < 64; k++) {
+				int t = c[k] * (int)__ldg(&qd->qraw[k]);
+				val |= t + 0x800;
+				c[k] = (short)t;
+			}
+			if (val >> 12) atomicOr(&bad_flags[job->bad_slot], 1);
+		}
 		if (!(mode & QS_IDCT_NOPLANE)) {
+			int ws[64];
+#pragma unroll
+			for (int x = 0; x < 8; x++) {
+				int in[8], o[8];
+#pragma unroll
+				for (int k = 0; k < 8; k++) in[k] = c[k * 8 + x];
+				qs_islow_1d<1024>(in, o);
+#pragma unroll
+				for (int k = 0; k < 8; k++) ws[k * 8 + x] = o[k] >> 11;
+			}
 			uint32_t lo[8], hi[8];
 			qs_islow_rows(ws, lo, hi);
 			uint8_t *p = job->plane + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
@@ -431,30 +429,31 @@ __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_ke
 				if (right) r[8] = (uint8_t)(hi[7] >> 24);
 			}
 		}
-		if (mode & QS_IDCT_CLAMP) {                         /* quantsmooth.h:2670-2689 */
+		if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {
+			if (mode & QS_IDCT_CLAMP) {                     /* quantsmooth.h:2670-2689 */
 #pragma unroll
-			for (int p2 = 0; p2 < 32; p2++) {
-				uint32_t w = cwp[p2 * QS_IDCT_SROW];
-				int a = (short)(w & 0xffff), c = (int)w >> 16;
-				a = min(max(a, -1023), 1023); c = min(max(c, -1023), 1023);
-				cwp[p2 * QS_IDCT_SROW] = (uint32_t)(a & 0xffff) | ((uint32_t)c << 16);
+				for (int k = 0; k < 64; k++) c[k] = min(max(c[k], -1023), 1023);
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int4 v;
+				v.x = (c[j * 8 + 0] & 0xffff) | (c[j * 8 + 1] << 16);
+				v.y = (c[j * 8 + 2] & 0xffff) | (c[j * 8 + 3] << 16);
+				v.z = (c[j * 8 + 4] & 0xffff) | (c[j * 8 + 5] << 16);
+				v.w = (c[j * 8 + 6] & 0xffff) | (c[j * 8 + 7] << 16);
+				sw[lane * 8 + (j ^ (lane & 7))] = v;
 			}
 		}
 	}
-
 	if (mode & (QS_IDCT_DEQUANT | QS_IDCT_CLAMP)) {         /* coefficients back, coalesced */
 		__syncwarp();
 #pragma unroll
 		for (int j = 0; j < 8; j++) {
-			int P = j * 32 + lane;
-			if ((P >> 3) < nb) {
-				const uint32_t *d = sw + (4 * (P & 7)) * QS_IDCT_SROW + (P >> 3);
-				g[P] = make_int4((int)d[0], (int)d[QS_IDCT_SROW], (int)d[2 * QS_IDCT_SROW], (int)d[3 * QS_IDCT_SROW]);
-			}
+			int P = j * 32 + lane, blk = P >> 3;
+			if (blk < nb) g[P] = sw[blk * 8 + ((P & 7) ^ (blk & 7))];
 		}
 	}
 }
-
 #endif
 
 /* ------------------------------------------------------------------------------------------
@@ -478,7 +477,8 @@ __global__ void __launch_bounds__(QS_IDCT_THREADS, QS_IDCT_MINB) qs_idct_pass_ke
  * after the division.  Per (term, coefficient): 1 FADD.SAT + 5 FMUL + 2 FADD, no FMA.
  * ------------------------------------------------------------------------------------------ */
 #define QS_SMOOTH_THREADS 512               /* default: 4 warps per sub-partition */
-#define QS_WARP_WORDS (32 * 32 + 14 * 32 * 2)     /* uint32 words per warp region */
+#define QS_WARP_MSUM (32 * 32 + 14 * 32 * 2)      /* word offset of the rebalance sums: 2 x int64 per lane */
+#define QS_WARP_WORDS (QS_WARP_MSUM + 4 * 32)     /* uint32 words per warp region */
 
 __device__ __forceinline__ float qs_px(uint32_t w, int j) {
 	return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | (uint32_t)(j << 4)));
@@ -696,11 +696,18 @@ __device__ __forceinline__ void qs_section_sync(int grp) {
 /* division, rounding and clamped update of the N coefficients of a chunk, quantsmooth.h:1548-1564.
  * Written without control flow (the reference's `if (r)` becomes a select, and the store is
  * unconditional) so that the N dependent chains - divide, round, quant constants, exact
- * division, clamp - interleave; in lock step nothing else could hide their latencies. */
+ * division, clamp - interleave; in lock step nothing else could hide their latencies.
+ * It also keeps the two sums of the rebalance step (quantsmooth.h:1823-1832: m0 = sum coef*a0,
+ * m1 = sum a0*a0 over the AC coefficients) up to date: every AC coefficient passes through here
+ * exactly once per iteration, its new value stays inside the quantization interval of a0 (that
+ * is what the clamp does), so a0 - already at hand - is also the a0 the rebalance step would
+ * recompute from the final value.  The sums live in shared memory (msum[0] = m0, msum[32] = m1).
+ */
 template <int N>
 __device__ __forceinline__ void qs_coef_update(const float *a2s, const float *a3, const uint8_t *idx,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, long long *msum) {
 	int q[N], c[N], r[N]; uint32_t m31[N]; uint16_t *slot[N];
+	long long m0 = msum[0], m1 = msum[32];
 #pragma unroll
 	for (int k = 0; k < N; k++) {
 		int i = idx[k];
@@ -720,13 +727,16 @@ __device__ __forceinline__ void qs_coef_update(const float *a2s, const float *a3
 		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
 		int add = (int)((unsigned)c[k] - (unsigned)r[k]);
 		add = min(add, dh); add = max(add, dl);
-		*slot[k] = (uint16_t)(r[k] ? add : c[k]);
+		add = r[k] ? add : c[k];
+		*slot[k] = (uint16_t)add;
+		m0 += add * a0; m1 += a0 * a0;
 	}
+	msum[0] = m0; msum[32] = m1;
 }
 
 template <int N, bool DIAG, int SYNC, bool UNI>
 __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h, long long *msum) {
 	const float *tab[N]; float Rs[N], a2[N], a3[N];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -748,7 +758,7 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
 	QS_PH_MARK(ph, 8);
 	/* the next chunk's header travels while the divisions below are in flight */
 	h[0] = __ldg(nh); h[1] = __ldg(nh + 1); h[2] = __ldg(nh + 2);
-	qs_coef_update<N>(a2, a3, ch.idx, qd, cs);
+	qs_coef_update<N>(a2, a3, ch.idx, qd, cs, msum);
 	QS_PH_MARK(ph, 9);
 }
 
@@ -756,7 +766,7 @@ __device__ __forceinline__ void qs_chunk_full(const QsChunk &ch, const float *ta
  * terms), idx[1] in column 0 (i & 7 == 0: no horizontal terms) */
 template <bool DIAG, int SYNC>
 __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *tabs, const uint2 *pw,
-		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h) {
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h, long long *msum) {
 	const float *tab[2]; float Rs[2], a2[2], a3[2];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #pragma unroll
@@ -777,7 +787,7 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 	qs_section_sync<SYNC>(grp);
 	QS_PH_MARK(ph, 8);
 	h[0] = __ldg(nh); h[1] = __ldg(nh + 1); h[2] = __ldg(nh + 2);
-	qs_coef_update<2>(a2, a3, ch.idx, qd, cs);
+	qs_coef_update<2>(a2, a3, ch.idx, qd, cs, msum);
 	QS_PH_MARK(ph, 9);
 }
 
@@ -849,15 +859,19 @@ __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, c
 }
 
 /* rebalance, quantsmooth.h:1566-1568, 1823-1848 */
-__device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs) {
+template <bool HAVE_SUMS>
+__device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs, const long long *msum) {
 	long long m0 = 0, m1 = 0;
-	/* both loops: 63 independent iterations, latency bound when rolled (LDS -> LDG -> IMAD.HI);
-	 * unrolled by 7 the loads of seven coefficients are in flight together */
+	if (HAVE_SUMS) { m0 = msum[0]; m1 = msum[32]; }
+	else {
+		/* 63 independent iterations, latency bound when rolled (LDS -> LDG -> IMAD.HI); unrolled
+		 * by 7 the loads of seven coefficients are in flight together */
 #pragma unroll 7
-	for (int k = 1; k < 64; k++) {
-		int c = (short)cs[(k >> 1) * 64 + (k & 1)];
-		int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
-		m0 += c * a0; m1 += a0 * a0;
+		for (int k = 1; k < 64; k++) {
+			int c = (short)cs[(k >> 1) * 64 + (k & 1)];
+			int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
+			m0 += c * a0; m1 += a0 * a0;
+		}
 	}
 	if (m1 > m0 && m0 != 0) {
 		int mul = (int)(((m1 << 13) + (m0 >> 1)) / m0);
@@ -881,7 +895,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		int njobs, int total_tiles, const float *__restrict__ tables_g, int *__restrict__ tile_counter,
 		int flags, int clamp_out, const int *__restrict__ bad) {
 	extern __shared__ __align__(16) uint32_t smem[];
-	__shared__ int s_tile[16];
+	__shared__ int s_tile[16], s_next[16];
 	__shared__ int s_sig[32];
 	const int TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
 #ifdef QS_EXPERIMENTS
@@ -921,6 +935,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	uint32_t *cw = wbase + lane;                        /* coefficient pair p at cw[p * 32] */
 	uint16_t *cs = (uint16_t *)wbase + lane * 2;        /* coefficient i at cs[(i>>1)*64 + (i&1)] */
 	uint2 *pw = (uint2 *)(wbase + 32 * 32) + lane;      /* pixel word j at pw[j * 32] */
+	long long *msum = (long long *)(wbase + QS_WARP_MSUM) + lane;   /* rebalance sums: msum[0], msum[32] */
 
 	/* Tile schedule of the lock-step groups: first `a_tiles` group tiles of WPG warp tiles
 	 * each (dynamic, one atomic per group tile); then the left-over warp tiles are spread
@@ -939,14 +954,22 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 	ph.start(s_ph[warp]);
 #endif
 
+	/* The group tile after the current one is known one tile ahead (its atomic ran during the
+	 * previous tile), so the group can ask L2 for its coefficients and pixel rows while it still
+	 * works on the current tile: the prologue's DRAM round trips leave the critical path. */
+	if (QS_SYNC_LEVEL(SYNC) && wig == 0 && lane == 0) {
+		s_tile[grp] = atomicAdd(tile_counter, 1);
+		s_next[grp] = atomicAdd(tile_counter, 1);
+	}
 	for (;;) {
-		int tile = 0;
+		int tile = 0, gnext = 0, gnext2 = 0;
 		if (QS_SYNC_LEVEL(SYNC)) {
 			if (last) break;
-			if (wig == 0 && lane == 0) s_tile[grp] = atomicAdd(tile_counter, 1);
 			qs_group_sync<SYNC>(gbar);
 			int gt = *(volatile int *)&s_tile[grp];
-			qs_group_sync<SYNC>(gbar);                  /* s_tile may be rewritten from here on */
+			gnext = *(volatile int *)&s_next[grp];
+			qs_group_sync<SYNC>(gbar);                  /* s_tile / s_next may be rewritten from here on */
+			if (wig == 0 && lane == 0) gnext2 = atomicAdd(tile_counter, 1);    /* consumed at the end of this tile */
 			if (gt < a_tiles) tile = gt * WPG + wig;
 			else {
 				int j = blockIdx.x * NG + grp;          /* this group's left-over share */
@@ -1007,6 +1030,20 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		/* The first refresh of a block would re-render exactly what the IDCT pass just wrote to
 		 * the plane (same coefficients, deterministic IDCT), so those 64 pixels are loaded
 		 * instead of computed - unless the JOINT_YUV predictor changed the coefficients. */
+		msum[0] = 0; msum[32] = 0;
+		if (QS_SYNC_LEVEL(SYNC) && gnext < a_tiles) {
+			/* next group tile, if it lies in the same component: one coefficient line per lane
+			 * (32 blocks x 128 B), the ten pixel rows the prologue reads (3 lines each) */
+			int nb0 = ((gnext * WPG + wig) - job->tile_begin) * 32;
+			if (nb0 >= 0 && nb0 + 32 <= nblocks) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(job->coef + ((size_t)nb0 + lane) * 64));
+				int nby = nb0 / W, nbx = nb0 - nby * W;
+				if (lane < 30 && nbx * 8 + (lane % 3) * 128 < W * 8) {          /* stay inside the row */
+					const uint8_t *np = job->plane + (size_t)(nby * 8 + lane / 3) * stride + QS_PLANE_PAD + nbx * 8 + (lane % 3) * 128;
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(np));
+				}
+			}
+		}
 		const bool fresh_px = job->plane2 == NULL;
 		/* Warps of a lock-step group may sit in different components (a group tile or the
 		 * balanced tail can straddle jobs).  Their barrier sequences must be identical, so a
@@ -1041,8 +1078,8 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 				QsChunk2 ch = c_chunks2[ci];
 				qs_group_sync<SYNC>(gsync);
 				if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
-				if (ch.np == 2) qs_chunk_pairs<2, DIAG>(ch, tabs, pw, qd, cs);
-				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs);
+				if (ch.np == 2) qs_chunk_pairs<2, DIAG>(ch, tabs, pw, qd, cs, msum);
+				else qs_chunk_pairs<1, DIAG>(ch, tabs, pw, qd, cs, msum);
 			}
 		}
 #endif
@@ -1064,21 +1101,21 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			 * unconditional refresh at each anti-diagonal start is value-identical */
 			if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 			QS_PH_MARK(ph, 3);
-			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
 			else if (ch.type == 2) {
-				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
-				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
-				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+				else qs_chunk_full<2, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
 			}
-			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
-			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
-			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
-			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h);
+			else if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+			else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+			else if (ch.n == 2) qs_chunk_full<2, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+			else qs_chunk_full<1, DIAG, SYNC, false>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
 		}
 		QS_PH_MARK(ph, 10);
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
-			qs_rebalance(qd, cs);
+			qs_rebalance<true>(qd, cs, msum);
 		QS_PH_MARK(ph, 11);
 
 		if (valid) {
@@ -1099,6 +1136,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			}
 		}
 		__syncwarp();
+		if (QS_SYNC_LEVEL(SYNC) && wig == 0 && lane == 0) { s_tile[grp] = gnext; s_next[grp] = gnext2; }
 		QS_PH_MARK(ph, 12);
 	}
 #ifdef QS_PHASE_CLOCKS
@@ -1197,7 +1235,7 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 		qs_fdct_clamp(f, qd, cs);
 	}
 	if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
-		qs_rebalance(qd, cs);
+		qs_rebalance<false>(qd, cs, NULL);
 	{
 		int4 *p = (int4 *)cptr;
 #pragma unroll
@@ -1383,8 +1421,17 @@ __global__ void __launch_bounds__(512) qs_xchg_pull_kernel(const __grid_constant
 	__shared__ int ok;
 	if (threadIdx.x == 0) ok = 1;
 	__syncthreads();
-	if (threadIdx.x < 2 && a.flag[threadIdx.x] && !qs_wait_seq(a.flag[threadIdx.x], a.seq)) ok = 0;
-	if (threadIdx.x >= 32 && threadIdx.x < 32 + a.npeers && a.bad_n && !qs_wait_seq(a.bad_flag[threadIdx.x - 32], a.seq)) ok = 0;
+	/* on a timeout the mapped host words say which wait it was: [0] = 1, [1] = 1 + waiter (0/1 = halo
+	 * flag from the upper / lower neighbour, 32 + p = mask message of the p-th peer), [2] = the
+	 * sequence number expected, [3] = the one found */
+	if (threadIdx.x < 2 && a.flag[threadIdx.x] && !qs_wait_seq(a.flag[threadIdx.x], a.seq)) {
+		ok = 0;
+		if (a.timeout_flag) { a.timeout_flag[1] = 1 + threadIdx.x; a.timeout_flag[2] = (int)a.seq; a.timeout_flag[3] = (int)*(const volatile uint32_t *)a.flag[threadIdx.x]; }
+	}
+	if (threadIdx.x >= 32 && threadIdx.x < 32 + a.npeers && a.bad_n && !qs_wait_seq(a.bad_flag[threadIdx.x - 32], a.seq)) {
+		ok = 0;
+		if (a.timeout_flag) { a.timeout_flag[1] = 1 + threadIdx.x; a.timeout_flag[2] = (int)a.seq; a.timeout_flag[3] = (int)*(const volatile uint32_t *)a.bad_flag[threadIdx.x - 32]; }
+	}
 	__syncthreads();
 	if (!ok) { if (threadIdx.x == 0 && a.timeout_flag) { *(volatile int *)a.timeout_flag = 1; __threadfence_system(); } return; }
 	for (int r = 0; r < a.nrows; r++) qs_copy_row(a.rows[r].src, a.rows[r].dst, a.rows[r].bytes);

@@ -1,6 +1,14 @@
 import os
 import sys
 
+# Several ranks of the slab engine may share one device in these tests (a one-GPU box still runs
+# the whole exchange).  Their pull kernels spin until a peer's push kernel has run, so kernels of
+# different streams must really be able to run side by side: with more streams than hardware
+# work queues (default 8) two streams can share a queue and a spinning kernel would then sit in
+# front of the very kernel it waits for.  Must be set before CUDA initialises.  Production runs
+# one rank per device and never needs it.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
