@@ -406,15 +406,32 @@ def main():
                     "share_of_step": round(smooth_ms / (ms_total if ms_total else 1), 4),
                     "note": "the path is FP32-issue bound, not HBM bound (SURVEY.md 8d, DESIGN.md 4); "
                             "see roofline_fp32"}
-        # FP32-issue roofline: 8 FP32 pipe instructions per (term, coefficient), 8288 terms per block
-        fp_inst = 8288 * 8 * nblocks_rank / 32.0                       # warp instructions per launch
+        # FP32-issue roofline.  Minimum FP32-pipe instructions of the order-exact arithmetic per
+        # block-iteration, from the chunk schedule the kernel really runs for each component's quant
+        # table: a coefficient has 56 horizontal (if not in column 0) + 32 border + 56 vertical (if not
+        # in row 0) terms (+98 with DIAGONALS); 8 instructions per term, except in "uniform" chunks
+        # (equal quant values) where the n coefficients share t and d*t: 3 + 5n per term.
+        def min_fp_per_block(quant, diag):
+            total = 0
+            for typ, _first, idx in qs.cuda.chunk_schedule(quant):
+                if typ == 2:
+                    total += (144 + (98 if diag else 0)) * (3 + 5 * len(idx))
+                else:
+                    for i in idx:
+                        terms = 32 + (56 if i & 7 else 0) + (56 if i > 7 else 0) + (98 if diag else 0)
+                        total += 8 * terms
+            return total
+        fp_inst = sum(min_fp_per_block(c.quant, bool(FLAGS & 1)) * c.wblk * c.hblk for c in im.comps) / 32.0
+        fp_inst_plain = 8288 * 8 * nblocks_rank / 32.0                  # without the uniform-chunk sharing
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = 148 * 4 * sm_mhz * 1e6                            # warp-instr/s at 1 per SMSP per clock
         roofline_fp32 = {"bound": "fp32-issue", "achieved": round(fp_inst / (avg_ms / 1e3) / 1e12, 4),
                          "peak": round(issue_peak / 1e12, 4), "unit": "T warp-instr/s",
                          "frac": round(fp_inst / (avg_ms / 1e3) / issue_peak, 4),
-                         "note": "minimum FP32-pipe instructions of the order-exact arithmetic / (148 SM x 4 "
-                                 "sub-partitions x measured SM clock)"}
+                         "frac_counting_8_per_term": round(fp_inst_plain / (avg_ms / 1e3) / issue_peak, 4),
+                         "note": "minimum FP32-pipe instructions of the order-exact arithmetic for the chunk schedules in "
+                                 "use (uniform chunks: 3 + 5n per term) / (148 SM x 4 sub-partitions x measured SM clock); "
+                                 "frac_counting_8_per_term is round 1's figure (8 per term everywhere)"}
     else:
         roofline_fp32 = None
 

@@ -105,7 +105,8 @@ __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	z2 = in[2]; z3 = in[6];
 	z1 = (z2 + z3) * 4433;
 	a = z1 - z3 * 15137; b = z1 + z2 * 6270;
-	e0 = (in[0] + in[4]) * 8192 + RND; e1 = (in[0] - in[4]) * 8192 + RND;
+	t0 = (in[0] + in[4]) * 8192 + RND; t1 = (in[0] - in[4]) * 8192 + RND;
+	e0 = t0 + b; e3 = t0 - b; e1 = t1 + a; e2 = t1 - a;
 	t0 = in[7]; t1 = in[5]; t2 = in[3]; t3 = in[1];
 	z1 = t0 + t3; z2 = t1 + t2; z3 = t0 + t2; z4 = t1 + t3;
 	z5 = (z3 + z4) * 9633;
@@ -113,11 +114,10 @@ __device__ __forceinline__ void qs_islow_1d(const int *in, int *out) {
 	z1 *= 7373; z2 *= 20995; z3 *= 16069; z4 *= 3196;
 	z3 = z5 - z3; z4 = z5 - z4;
 	t0 += z3 - z1; t1 += z4 - z2; t2 += z3 - z2; t3 += z4 - z1;
-	/* three-input sums (one IADD3 each, on the ALU pipe the butterflies' IMADs leave idle)
-	 * instead of forming the even part first: wrap-around integer sums, same values */
-	out[0] = e0 + b + t3; out[7] = e0 + b - t3; out[1] = e1 + a + t2; out[6] = e1 + a - t2;
-	out[2] = e1 - a + t1; out[5] = e1 - a - t1; out[3] = e0 - b + t0; out[4] = e0 - b - t0;
-	(void)e2; (void)e3;
+	/* (forming the outputs as three-input sums e0 +- b +- t3 - fewer instructions, IADD3 on the
+	 * ALU pipe - measured slower: the refresh went from 60.8k to 65.1k cycles per warp tile) */
+	out[0] = e0 + t3; out[7] = e0 - t3; out[1] = e1 + t2; out[6] = e1 - t2;
+	out[2] = e2 + t1; out[5] = e2 - t1; out[3] = e3 + t0; out[4] = e3 - t0;
 }
 
 /* four int32 -> four saturated bytes b0 | b1<<8 | b2<<16 | b3<<24 */

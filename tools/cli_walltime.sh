@@ -18,7 +18,10 @@ E=jpeg-quantsmooth_b200/csrc/jpegqs
 for mode in warm nowarm; do
   for i in 1 2 3; do
     if [ $mode = nowarm ]; then export JPEGQS_NO_WARMUP=1; else unset JPEGQS_NO_WARMUP; fi
-    /usr/bin/time -f "$mode run $i: total %e s" $E -v 1 -i 8 -q 3 $T/in.jpg $T/out.jpg 2>&1 | grep -v "^$T\|component\|quant\|^0" | tr '\n' ' '; echo
+    t0=$(date +%s.%N)
+    $E -v 1 -i 8 -q 3 $T/in.jpg $T/out.jpg 2>&1 | grep "wall time\|quantsmooth" | tr '\n' ' '
+    t1=$(date +%s.%N)
+    echo " | $mode run $i: process total $(python3 -c "print(round($t1 - $t0, 3))") s"
   done
 done
 rm -rf $T

@@ -9,7 +9,8 @@ import sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0          # which captured launch
+hdr, units, vals = rows[0], rows[1], rows[2 + which]
 m = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
@@ -33,7 +34,10 @@ tot, samp = collections.Counter(), collections.Counter()
 for r in rows[2:]:
     f = r[ia].split()
     op = (f[1] if f[0].startswith("@") else f[0]).split(".")[0]
-    tot[op] += int(r[ie]); samp[op] += int(r[isamp])
+    try:
+        tot[op] += int(r[ie]); samp[op] += int(r[isamp])
+    except (ValueError, IndexError):
+        continue
 T, S = sum(tot.values()), sum(samp.values())
 print(f"-- dynamic opcode mix: {T} warp instructions, {len(rows) - 2} static ({(len(rows) - 2) * 16} B) --")
 for op, c in tot.most_common(22):
