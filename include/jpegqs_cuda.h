@@ -84,16 +84,14 @@ void jpegqs_cuda_set_profiling(jpegqs_cuda_ctx *ctx, int on);
 void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *idct_launches,
 		float *smooth_ms, int *smooth_launches);
 
-/* kernel-variant knobs for tuning runs; results are bit-identical for every setting.
- * key 0: lock-step execution of the warps sharing an SM sub-partition (0 = off, 1 = barrier
- *        per section (default), 2 = barrier per chunk)
- * key 1: maximum coefficients per accumulation chunk (1..7, default 4)
- * key 2: warps per SM sub-partition (4 or 6, default 4; 6 = 80 registers per thread)
- * key 3: (retired experiment, ignored)
+/* knobs for tuning runs and tests; results are bit-identical for every setting.
+ * key 1: maximum coefficients per accumulation chunk (1..4, default 4)
  * key 5: uniform-quant chunks share t and d*t (default 1)
- * key 6: slab-pipelined upload/download in the host entry points (default 1)
+ * key 6: slab-pipelined upload / download in the host entry points (default 1)
  * key 7: blocks per slab wave for key 6; 0 = SM count x resident warps x 32 (tests force small values)
- * key 4: 1 = packed FP32x2 pair path (FMUL2/FFMA2; exact, but measured slower), 0 = scalar (default) */
+ * keys 0, 2, 4 (lock-step level, warps per sub-partition, packed FP32x2 path) only exist in the
+ * measurement build (make -C csrc experiments); the shipped library accepts their default values
+ * and answers JPEGQS_ERR_UNSUPPORTED otherwise.  key 3: retired, ignored. */
 int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value);
 
 /* pinned host memory for coefficient arrays: the copy engines read / write it directly.  Plain

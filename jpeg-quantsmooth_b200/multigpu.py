@@ -1,4 +1,9 @@
-"""MCU-row sharding of one image across the GPUs of a box.
+"""MCU-row sharding of one image across the GPUs of a box - the round-1 Python
+orchestration over the pass-level C ABI.  Since round 2 the product path is the C slab engine
+(csrc/qs_cuda.cu run_slab, include/jpegqs_cuda.h "one image sharded by MCU rows": kernel-side
+exchange over peer mailboxes, device-side stop logic); this module stays as the CPU-testable
+statement of the shard geometry and schedule (tests/test_multigpu_gloo.py drives it with oracle
+passes over gloo) and provides split_mcu_rows / comp_block_rows to bench.py and the tools.
 
 One process per GPU (torch.distributed, NCCL over NVLink).  Every rank owns a contiguous
 range of MCU rows of every component.  Within an iteration blocks only need the
@@ -155,7 +160,8 @@ def exchange_rows(planes: Sequence[Tuple[object, int]], rank: int, world: int, d
     ops = []
     for plane, rows in planes:
         if not rows:
-            continue
+            raise ValueError("sharded run: a rank holds no block row of a component (more ranks than MCU rows); "
+                             "use fewer ranks - the C engine's jpegqs_cuda_multi_plan does")
         h = rows * 8
         if rank > 0:
             ops.append(dist.P2POp(dist.isend, plane[1], rank - 1, group))
