@@ -13,6 +13,9 @@
  *     -p, --cpu n        CUDA device ordinal + 1 (0 = current device); the reference's SIMD cap
  *     -f, --flags n      raw JPEGQS_* flag bits instead of -q
  *     -c, --copy n       0 = no markers, 1 = comments, 2 = comments + APPn (default)
+ *     --batch            (extension) any number of "input output" pairs follow: one process, CUDA
+ *                        start-up paid once (it is 1-2 s in a fresh process, 100x the smoothing
+ *                        of an 8K image); exit status = the worst of the pairs
  *     --ppm              (extension) write the decoded RGB image as binary PPM/PGM instead of a
  *                        JPEG: the device-side equivalent of the reference's example.c
  *                        (JPEG -> pixels through jpegqs_start_decompress)
@@ -60,70 +63,30 @@ static int usage(const char *prog) {
 		"  -i, --info n      Print quantsmooth debug messages (default is 15)\n"
 		"  -p, --cpu n       CUDA device ordinal + 1 (0 = current device)\n"
 		"  -f, --flags n     Raw flag bits\n"
-		"  -c, --copy n      Markers to copy: 0 none, 1 comments, 2 all (default)\n", prog);
+		"  -c, --copy n      Markers to copy: 0 none, 1 comments, 2 all (default)\n"
+		"      --batch       Process several \"input output\" pairs in one process\n"
+		"      --ppm         Write the decoded image (PPM/PGM) instead of a JPEG\n", prog);
 	return 1;
 }
 
-int main(int argc, char **argv) {
-	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
-	int i, ret, flags = 0, ppm = 0, io_err = 0, warnings, warm = 0;
+/* one input -> one output; returns the process exit status for this pair */
+static int run_one(const char *prog, const char *in_name, const char *out_name, jpegqs_control_t *optsp,
+		int copy, int optimize, int verbose, int ppm, int cpu, int warm_ok) {
+	jpegqs_control_t opts = *optsp;
+	char *const *argv = (char *const *)&prog;            /* argv[0] in the messages below */
+	int i, ret, io_err = 0, warnings, warm = 0;
 	double t_start, t_read, t_smooth, t_write;
+	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
+	jq_image im; char err[256];
 #ifndef JPEGQS_NO_CUDA_RENDER
 	pthread_t warm_th;
 #endif
-	const char *in_name, *out_name;
-	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
-	jq_image im; char err[256]; jpegqs_control_t opts;
-	static const struct { char s; const char *l; int has_arg; } O[] = {
-		{ 'o', "--optimize", 0 }, { 'v', "--verbose", 1 }, { 'i', "--info", 1 }, { 'n', "--niter", 1 },
-		{ 'q', "--quality", 1 }, { 't', "--threads", 1 }, { 'f', "--flags", 1 }, { 'p', "--cpu", 1 }, { 'c', "--copy", 1 } };
-
-	for (i = 1; i < argc; i++) {
-		const char *a = argv[i], *val = NULL; int k, which = -1;
-		if (a[0] != '-' || !a[1]) break;
-		if (!strcmp(a, "--")) { i++; break; }
-		if (!strcmp(a, "--ppm")) { ppm = 1; continue; }
-		for (k = 0; k < (int)(sizeof(O) / sizeof(O[0])); k++) {
-			if (a[1] != '-' && a[1] == O[k].s) { which = k; if (a[2]) val = a + 2; break; }
-			if (!strcmp(a, O[k].l)) { which = k; break; }
-		}
-		if (which < 0) return usage(argv[0]);
-		if (O[which].has_arg) {
-			if (!val) { if (++i >= argc) return usage(argv[0]); val = argv[i]; }
-			if ((unsigned)(val[0] - '0') > 9) return usage(argv[0]);
-		} else if (val) return usage(argv[0]);
-		switch (O[which].s) {
-			case 'o': optimize = 1; break;
-			case 'v': verbose = atoi(val); break;
-			case 'i': info = atoi(val); break;
-			case 'n': niter = atoi(val); break;
-			case 'q': quality = atoi(val); break;
-			case 't': threads = atoi(val); break;
-			case 'f': cmd_flags = atoi(val) & JPEGQS_FLAGS_MASK; break;
-			case 'p': cpu = atoi(val); if (cpu > JPEGQS_CPU_MASK) cpu = JPEGQS_CPU_MASK; break;
-			case 'c': copy = atoi(val); break;
-		}
-	}
-	if (argc - i != 2) return usage(argv[0]);
-	in_name = argv[i]; out_name = argv[i + 1];
-
-	if (quality < 3) { flags |= JPEGQS_LOW_QUALITY; quality += 4; }      /* quantsmooth.c:380-393 */
-	if (quality >= 4) flags |= JPEGQS_DIAGONALS;
-	if (quality >= 5) flags |= JPEGQS_JOINT_YUV;
-	if (quality >= 6) flags |= JPEGQS_UPSAMPLE_UV;
-	memset(&opts, 0, sizeof(opts));
-	opts.niter = niter >= 0 ? niter : 3;
-	opts.flags = (cmd_flags >= 0 ? cmd_flags : flags) | JPEGQS_TRANSCODE;
-	opts.flags |= cpu << JPEGQS_CPU_SHIFT;
-	opts.flags |= info << JPEGQS_INFO_SHIFT;
-	opts.threads = threads;
-	if (threads > 0) jq_set_threads(threads);
-
+	(void)i; (void)cpu; (void)warm_ok;
 	t_start = now_ms();
 #ifndef JPEGQS_NO_CUDA_RENDER
 	/* CUDA start-up (context + kernel image, a few hundred ms in a fresh process) overlaps with
 	 * reading and Huffman-decoding the input */
-	if ((opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) && !getenv("JPEGQS_NO_WARMUP")) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
+	if (warm_ok && (opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) && !getenv("JPEGQS_NO_WARMUP")) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
 #endif
 	f = strcmp(in_name, "-") ? fopen(in_name, "rb") : stdin;
 	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", argv[0], in_name); return 1; }
@@ -210,4 +173,62 @@ int main(int argc, char **argv) {
 	/* the reference's exit status (quantsmooth.c:626): 2 when the codec met recoverable damage
 	 * (libjpeg's num_warnings), else 0 - do_quantsmooth's "stopped early" value is not an error */
 	return io_err ? 1 : warnings ? 2 : 0;
+}
+
+int main(int argc, char **argv) {
+	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
+	int i, flags = 0, ppm = 0, batch = 0, status = 0;
+	jpegqs_control_t opts;
+	static const struct { char s; const char *l; int has_arg; } O[] = {
+		{ 'o', "--optimize", 0 }, { 'v', "--verbose", 1 }, { 'i', "--info", 1 }, { 'n', "--niter", 1 },
+		{ 'q', "--quality", 1 }, { 't', "--threads", 1 }, { 'f', "--flags", 1 }, { 'p', "--cpu", 1 }, { 'c', "--copy", 1 } };
+
+	for (i = 1; i < argc; i++) {
+		const char *a = argv[i], *val = NULL; int k, which = -1;
+		if (a[0] != '-' || !a[1]) break;
+		if (!strcmp(a, "--")) { i++; break; }
+		if (!strcmp(a, "--ppm")) { ppm = 1; continue; }
+		if (!strcmp(a, "--batch")) { batch = 1; continue; }
+		for (k = 0; k < (int)(sizeof(O) / sizeof(O[0])); k++) {
+			if (a[1] != '-' && a[1] == O[k].s) { which = k; if (a[2]) val = a + 2; break; }
+			if (!strcmp(a, O[k].l)) { which = k; break; }
+		}
+		if (which < 0) return usage(argv[0]);
+		if (O[which].has_arg) {
+			if (!val) { if (++i >= argc) return usage(argv[0]); val = argv[i]; }
+			if ((unsigned)(val[0] - '0') > 9) return usage(argv[0]);
+		} else if (val) return usage(argv[0]);
+		switch (O[which].s) {
+			case 'o': optimize = 1; break;
+			case 'v': verbose = atoi(val); break;
+			case 'i': info = atoi(val); break;
+			case 'n': niter = atoi(val); break;
+			case 'q': quality = atoi(val); break;
+			case 't': threads = atoi(val); break;
+			case 'f': cmd_flags = atoi(val) & JPEGQS_FLAGS_MASK; break;
+			case 'p': cpu = atoi(val); if (cpu > JPEGQS_CPU_MASK) cpu = JPEGQS_CPU_MASK; break;
+			case 'c': copy = atoi(val); break;
+		}
+	}
+	if (batch ? (argc - i < 2 || ((argc - i) & 1)) : argc - i != 2) return usage(argv[0]);
+
+	if (quality < 3) { flags |= JPEGQS_LOW_QUALITY; quality += 4; }      /* quantsmooth.c:380-393 */
+	if (quality >= 4) flags |= JPEGQS_DIAGONALS;
+	if (quality >= 5) flags |= JPEGQS_JOINT_YUV;
+	if (quality >= 6) flags |= JPEGQS_UPSAMPLE_UV;
+	memset(&opts, 0, sizeof(opts));
+	opts.niter = niter >= 0 ? niter : 3;
+	opts.flags = (cmd_flags >= 0 ? cmd_flags : flags) | JPEGQS_TRANSCODE;
+	opts.flags |= cpu << JPEGQS_CPU_SHIFT;
+	opts.flags |= info << JPEGQS_INFO_SHIFT;
+	opts.threads = threads;
+	if (threads > 0) jq_set_threads(threads);
+
+	/* --batch: any number of "input output" pairs in one process, so that CUDA start-up (1-2 s in a
+	 * fresh process, profiles/README.md) is paid once; the exit status is the worst of the pairs */
+	for (; i + 1 < argc; i += 2) {
+		int rc = run_one(argv[0], argv[i], argv[i + 1], &opts, copy, optimize, verbose, ppm, cpu, status == 0);
+		if (rc > status) status = rc;
+	}
+	return status;
 }

@@ -1308,20 +1308,37 @@ __global__ void qs_upsample_kernel(const uint8_t *__restrict__ C, const uint8_t 
 		const uint8_t *__restrict__ Yf, int ystride, uint8_t *__restrict__ out, int ostride,
 		int w1, int h1, int ws, int hs, int ww, int hh, int oy0) {
 	/* oy0 = first output (luma) pixel row of this slab inside the whole component: planes and
-	 * `out` are slab-local, w1/h1 are whole-image quantities (0 for a single-GPU run) */
-	int ox = blockIdx.x * blockDim.x + threadIdx.x;     /* output pixel */
-	int oy = blockIdx.y * blockDim.y + threadIdx.y;
-	if (ox >= ww || oy >= hh) return;
-	int sx = min(ox, w1 * ws - 1), sy = min(oy + oy0, h1 * hs - 1) - oy0;
-	int x = sx / ws, y = (sy + oy0) / hs - oy0 / hs;
+	 * `out` are slab-local, w1/h1 are whole-image quantities (0 for a single-GPU run).
+	 * One thread per CELL of ws x hs output pixels: the 3x3 regression of its chroma pixel
+	 * (scale, offset) is computed once and applied to the cell's luma pixels, like the reference's
+	 * loop nest; cells beyond (w1, h1) replicate the last column / row (all their pixels read the
+	 * last valid luma column / row and the last chroma pixel, exactly what clamping every output
+	 * coordinate gives). */
+	int cx = blockIdx.x * blockDim.x + threadIdx.x;     /* cell */
+	int cy = blockIdx.y * blockDim.y + threadIdx.y;
+	if (cx * ws >= ww || cy * hs >= hh) return;
+	int sx0 = min(cx * ws, w1 * ws - 1);
+	int x = sx0 / ws;                                   /* chroma pixel of this cell */
+	int sy0 = min(cy * hs + oy0, h1 * hs - 1) - oy0;
+	int y = (sy0 + oy0) / hs - oy0 / hs;
 	const uint8_t *pc = C + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
 	const uint8_t *pd = Yd + (size_t)(y + 1) * cstride + QS_PLANE_PAD + x;
 	int sA, sB;
 	float scale = qs_regress(pd, pc, cstride, sA, sB);
 	float offset = FA(FS((float)pc[0], FM((float)pd[0], scale)), 0.5f);
-	float yv = (float)Yf[(size_t)(sy + 1) * ystride + QS_PLANE_PAD + sx];
-	int a = qs_cvtt_x86(FA(FM(yv, scale), offset));
-	out[(size_t)oy * ostride + ox] = (uint8_t)min(max(a, 0), 255);
+	for (int j = 0; j < hs; j++) {
+		int oy = cy * hs + j;
+		if (oy >= hh) break;
+		int sy = min(oy + oy0, h1 * hs - 1) - oy0;
+		for (int i = 0; i < ws; i++) {
+			int ox = cx * ws + i;
+			if (ox >= ww) break;
+			int sx = min(ox, w1 * ws - 1);
+			float yv = (float)Yf[(size_t)(sy + 1) * ystride + QS_PLANE_PAD + sx];
+			int a = qs_cvtt_x86(FA(FM(yv, scale), offset));
+			out[(size_t)oy * ostride + ox] = (uint8_t)min(max(a, 0), 255);
+		}
+	}
 }
 
 /* FDCT of the up-sampled plane into new coefficient arrays, quantsmooth.h:2735-2750 */
@@ -1616,7 +1633,8 @@ cudaError_t qs_launch_downsample(const uint8_t *src, int sstride, int w, int h, 
 
 cudaError_t qs_launch_upsample(const uint8_t *C, const uint8_t *Yd, int cstride, const uint8_t *Yf, int ystride,
 		uint8_t *out, int ostride, int w1, int h1, int ws, int hs, int ww, int hh, int oy0, cudaStream_t st) {
-	dim3 blk(64, 4), grd((ww + 63) / 64, (hh + 3) / 4);
+	int wc = (ww + ws - 1) / ws, hc = (hh + hs - 1) / hs;          /* cells of ws x hs output pixels */
+	dim3 blk(64, 4), grd((wc + 63) / 64, (hc + 3) / 4);
 	qs_upsample_kernel<<<grd, blk, 0, st>>>(C, Yd, cstride, Yf, ystride, out, ostride, w1, h1, ws, hs, ww, hh, oy0);
 	return cudaGetLastError();
 }

@@ -165,6 +165,20 @@ def test_exit_status_follows_the_reference(jpegs, tmp_path):
         assert r.returncode == 1
 
 
+def test_batch_mode_equals_single_runs(jpegs, tmp_path):
+    """--batch: several "input output" pairs in one process (CUDA start-up paid once)."""
+    names = ["base420", "prog420", "gray"]
+    args = [EXE, "-n", "0", "-i", "0", "--batch"]
+    for n in names:
+        args += [jpegs[n], str(tmp_path / f"b_{n}.jpg")]
+    assert subprocess.run(args).returncode == 0
+    for n in names:
+        single = str(tmp_path / f"s_{n}.jpg")
+        assert subprocess.run([EXE, "-n", "0", "-i", "0", jpegs[n], single]).returncode == 0
+        assert open(single, "rb").read() == open(tmp_path / f"b_{n}.jpg", "rb").read()
+    assert subprocess.run([EXE, "--batch", jpegs["gray"]], capture_output=True).returncode == 1     # odd count: usage
+
+
 def test_bad_input_and_usage(tmp_path):
     bad = tmp_path / "bad.jpg"
     bad.write_bytes(b"this is not a jpeg")

@@ -24,4 +24,10 @@ for mode in warm nowarm; do
     echo " | $mode run $i: process total $(python3 -c "print(round($t1 - $t0, 3))") s"
   done
 done
+# one process, four files: start-up amortised
+t0=$(date +%s.%N)
+$E -v 1 -i 0 -q 3 --batch $T/in.jpg $T/o1.jpg $T/in.jpg $T/o2.jpg $T/in.jpg $T/o3.jpg $T/in.jpg $T/o4.jpg 2>&1 | grep "wall time" | sed 's/^/  batch: /'
+t1=$(date +%s.%N)
+echo "batch of 4 files in one process: total $(python3 -c "print(round($t1 - $t0, 3))") s"
+cmp $T/out.jpg $T/o4.jpg && echo "batch output identical to the single-file run"
 rm -rf $T
