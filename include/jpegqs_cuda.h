@@ -89,6 +89,8 @@ void jpegqs_cuda_kernel_stats(const jpegqs_cuda_ctx *ctx, float *idct_ms, int *i
  * key 5: uniform-quant chunks share t and d*t (default 1)
  * key 6: slab-pipelined upload / download in the host entry points (default 1)
  * key 7: blocks per slab wave for key 6; 0 = SM count x resident warps x 32 (tests force small values)
+ * key 8: the two edge coefficients of an anti-diagonal ride along with up to two of its full
+ *        coefficients in one "mixed" chunk instead of forming their own
  * keys 0, 2, 4 (lock-step level, warps per sub-partition, packed FP32x2 path) only exist in the
  * measurement build (make -C csrc experiments); the shipped library accepts their default values
  * and answers JPEGQS_ERR_UNSUPPORTED otherwise.  key 3: retired, ignored. */
@@ -231,8 +233,9 @@ int jpegqs_cuda_orig_coef(int coef, int q);
  * AC coefficients in the reference's anti-diagonal visiting order (quantsmooth.h:313-322,
  * 1403-1409), grouped into chunks.  out: 12 bytes per chunk = {type, n, first, 0, idx[8]} with
  * type 0 = plain, 1 = the diagonal's two edge coefficients, 2 = equal quant values (shared
- * threshold work); idx = natural-order coefficient indices.  quant == NULL or uniform == 0
- * gives the table-independent schedule.  Returns the chunk count (<= 64), or JPEGQS_ERR_ARG. */
+ * threshold work), 3 = mixed (n full coefficients, then the row-0 and the column-0 one: n + 2
+ * indices); idx = natural-order coefficient indices.  uniform: bit 0 = uniform chunks, bit 1 =
+ * mixed chunks; quant == NULL gives the table-independent schedule.  Returns the chunk count (<= 64), or JPEGQS_ERR_ARG. */
 int jpegqs_cuda_chunk_schedule(const uint16_t *quant, int max_coefs, int uniform, uint8_t *out);
 
 #ifdef __cplusplus

@@ -35,8 +35,10 @@
  * pixel-difference work.  type 1 = the group's two edge coefficients (row 0: no vertical
  * terms; column 0: no horizontal terms; quantsmooth.h:1527, 1531); type 2 = a chunk whose
  * coefficients all have the same quant value, so t = max(R-|d|,0)^2 and a0 = d*t are
- * computed once per term and shared (3 + 5n FP ops per term instead of 8n).  The schedule is
- * built per quant table on the host (qs_cuda.cu::build_chunks). */
+ * computed once per term and shared (3 + 5n FP ops per term instead of 8n); type 3 = "mixed":
+ * n (1 or 2) full coefficients idx[0..n-1] plus the group's two edge coefficients idx[n] (row 0)
+ * and idx[n+1] (column 0) in one chunk.  The schedule is built per quant table on the host
+ * (qs_cuda.cu::build_chunks). */
 typedef struct {
 	uint8_t type, n, first, pad;
 	uint8_t idx[8];

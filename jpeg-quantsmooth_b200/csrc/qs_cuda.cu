@@ -82,7 +82,7 @@ static int build_tables(int flags, float *out, float prescale) {
  * reference's visiting order (reverse zig-zag, quantsmooth.h:1403 + zigzag_refresh 313-322).
  * Inside an anti-diagonal the coefficients are independent, so they may be regrouped: runs of
  * equal quant value become "uniform" chunks (type 2) that share t and d*t per term. */
-static int build_chunks(QsChunk *ch, int maxn, const uint16_t *q, int uniform) {
+static int build_chunks(QsChunk *ch, int maxn, const uint16_t *q, int uniform, int merge = 0) {
 	int n = 0;
 	for (int s = 14; s >= 1; s--) {
 		int full[8], nf = 0; bool first = true;
@@ -91,14 +91,43 @@ static int build_chunks(QsChunk *ch, int maxn, const uint16_t *q, int uniform) {
 			if (v < 0 || v > 7 || u == 0 || v == 0) continue;
 			full[nf++] = v * 8 + u;
 		}
+		bool used[8] = { false };
 		if (s <= 7) {
+			/* merge: the diagonal's two edge coefficients ride along with (up to) two of its full
+			 * coefficients in one "mixed" chunk (type 3) instead of forming a chunk of their own
+			 * with single-coefficient horizontal / vertical passes.  Not when those full
+			 * coefficients would otherwise share their threshold work in a uniform chunk. */
+			int take = 0;
+			if (merge && maxn >= 4 && nf >= 1) {
+				take = nf < 2 ? nf : 2;
+				if (nf - take == 1) take = 1;              /* do not leave one full coefficient on its own */
+				if (uniform && q) {
+					/* keep uniform runs whole: only coefficients whose quant value is unique on this diagonal */
+					int pick[2], np = 0;
+					for (int a = 0; a < nf && np < take; a++) {
+						bool tie = false;
+						for (int b = 0; b < nf; b++) tie = tie || (b != a && q[full[b]] == q[full[a]]);
+						if (!tie) pick[np++] = a;
+					}
+					if (np < take) take = 0;
+					else for (int k = 0; k < take; k++) used[pick[k]] = true;
+				} else for (int k = 0; k < take; k++) used[k] = true;
+			}
 			QsChunk c; memset(&c, 0, sizeof(c));
-			c.type = 1; c.n = 2; c.first = 1; first = false;
-			c.idx[0] = (uint8_t)s;          /* row 0:    horizontal + border (+diag) */
-			c.idx[1] = (uint8_t)(s * 8);    /* column 0: border + vertical   (+diag) */
+			c.first = 1; first = false;
+			if (take) {
+				int k = 0;
+				c.type = 3; c.n = (uint8_t)take;
+				for (int a = 0; a < nf; a++) if (used[a]) c.idx[k++] = (uint8_t)full[a];
+				c.idx[k++] = (uint8_t)s; c.idx[k++] = (uint8_t)(s * 8);
+			} else {
+				c.type = 1; c.n = 2;
+				c.idx[0] = (uint8_t)s;          /* row 0:    horizontal + border (+diag) */
+				c.idx[1] = (uint8_t)(s * 8);    /* column 0: border + vertical   (+diag) */
+			}
 			ch[n++] = c;
 		}
-		int rest[8], nr = 0; bool used[8] = { false };
+		int rest[8], nr = 0;
 		if (uniform && q && maxn >= 2) {
 			for (int a = 0; a < nf; a++) {
 				if (used[a]) continue;
@@ -203,7 +232,7 @@ struct jpegqs_cuda_ctx {
 	float last_ms; int launches;
 	/* optional per-kernel timing (bench.py's roofline line): event pairs around launches */
 	int profiling;
-	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2, tune_uni, tune_slabs, tune_wave;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
+	int tune_sync, tune_maxn, tune_wpg, tune_gs, tune_x2, tune_uni, tune_slabs, tune_wave, tune_merge;              /* kernel variant knobs (jpegqs_cuda_set_tuning) */
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used;
 	std::vector<int> ev_kind;              /* 0 = idct pass, 1 = smoothing pass, per pair */
 	float kernel_ms[2]; int kernel_launches[2];
@@ -287,7 +316,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_slabs = 1; ctx->tune_wave = 0; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_merge = 0; ctx->tune_slabs = 1; ctx->tune_wave = 0; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -304,7 +333,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 		CK(cudaMemcpy(ctx->tab_diag, t.data(), 64 * QS_TAB_DIAG * sizeof(float), cudaMemcpyHostToDevice));
 		{
 			QsChunk ch[QS_MAX_CHUNKS * 2];
-			int n = build_chunks(ch, ctx->tune_maxn, NULL, 0);
+			int n = build_chunks(ch, ctx->tune_maxn, NULL, 0, ctx->tune_merge);
 			CK(qs_set_chunks(ch, n));
 		}
 #ifdef QS_EXPERIMENTS
@@ -497,7 +526,7 @@ struct HostIo {
 	}
 };
 
-static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int maxn = 4, int uniform = 1) {
+static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int maxn = 4, int uniform = 1, int merge = 0) {
 	int val = 0;
 	for (int i = 0; i < 64; i++) {
 		int v = raw[i]; val |= v;
@@ -508,7 +537,7 @@ static void quant_prepare(const uint16_t *raw, QsQuantDev *q, int *val_out, int 
 	}
 	{
 		QsChunk tmp[QS_MAX_CHUNKS * 2];
-		int n = build_chunks(tmp, maxn, q->q, uniform);
+		int n = build_chunks(tmp, maxn, q->q, uniform, merge);
 		if (n > QS_MAX_CHUNKS) n = build_chunks(tmp, maxn, NULL, 0);   /* cannot happen for maxn 1..4 */
 		memset(q->chunks, 0, sizeof(q->chunks));
 		memcpy(q->chunks, tmp, (size_t)n * sizeof(QsChunk));
@@ -619,13 +648,23 @@ extern "C" int jpegqs_cuda_set_tuning(jpegqs_cuda_ctx *ctx, int key, int value) 
 		CK(cudaStreamSynchronize(ctx->stream));
 		CK(cudaDeviceSynchronize());
 		QsChunk ch[QS_MAX_CHUNKS * 2];
-		int n = build_chunks(ch, value, NULL, 0);
+		int n = build_chunks(ch, value, NULL, 0, ctx->tune_merge);
 		if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
 		CK(qs_set_chunks(ch, n));                  /* the table-independent schedule */
 		ctx->tune_maxn = value;                    /* per-table schedules follow with the next upload */
 		return 0;
 	}
 	if (key == 5) { ctx->tune_uni = value ? 1 : 0; return 0; }
+	if (key == 8) {                                    /* edge coefficients merged into mixed chunks */
+		CK(cudaSetDevice(ctx->device));
+		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaDeviceSynchronize());
+		ctx->tune_merge = value ? 1 : 0;
+		QsChunk ch[QS_MAX_CHUNKS * 2];
+		int n = build_chunks(ch, ctx->tune_maxn, NULL, 0, ctx->tune_merge);
+		CK(qs_set_chunks(ch, n));
+		return 0;
+	}
 	if (key == 6) { ctx->tune_slabs = value ? 1 : 0; return 0; }
 	if (key == 7) { if (value < 0) return JPEGQS_ERR_ARG; ctx->tune_wave = value; return 0; }
 	return JPEGQS_ERR_ARG;
@@ -635,7 +674,7 @@ extern "C" int jpegqs_cuda_chunk_schedule(const uint16_t *quant, int max_coefs, 
 	uint16_t q[64];
 	if (quant) for (int i = 0; i < 64; i++) q[i] = quant[i] ? quant[i] : 1;       /* as quant_prepare */
 	QsChunk tmp[QS_MAX_CHUNKS * 2];
-	int n = build_chunks(tmp, max_coefs, quant ? q : NULL, quant ? uniform : 0);
+	int n = build_chunks(tmp, max_coefs, quant ? q : NULL, quant ? (uniform & 1) : 0, (uniform >> 1) & 1);
 	if (n > QS_MAX_CHUNKS) return JPEGQS_ERR_ARG;
 	memcpy(out, tmp, (size_t)n * sizeof(QsChunk));
 	return n;
@@ -784,7 +823,7 @@ static int run_images(jpegqs_cuda_ctx *ctx, int nimg, jpegqs_cuda_image *imgs, i
 			}
 			w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
 			w.qslot = (int)qhost.size();
-			QsQuantDev q; quant_prepare(c->quant, &q, &qval[n][ci], ctx->tune_maxn, ctx->tune_uni); qhost.push_back(q);
+			QsQuantDev q; quant_prepare(c->quant, &q, &qval[n][ci], ctx->tune_maxn, ctx->tune_uni, ctx->tune_merge); qhost.push_back(q);
 		}
 		bool sub = s.need_downsample && !(im->comp[0].h_samp == 1 && im->comp[0].v_samp == 1);
 		if (sub) {
@@ -1463,7 +1502,7 @@ static int run_slab(jpegqs_cuda_ctx *ctx, jpegqs_cuda_link *link, jpegqs_cuda_im
 			else { w.rows = flat_rows(c->coef, c->wblk, c->hblk); w.pin = stage_take(cb); }
 		}
 		w.plane = (uint8_t *)arena_take(ctx, QS_PLANE_BYTES(c->wblk, c->hblk));
-		quant_prepare(c->quant, &qhost[ci], &qval[ci], ctx->tune_maxn, ctx->tune_uni);
+		quant_prepare(c->quant, &qhost[ci], &qval[ci], ctx->tune_maxn, ctx->tune_uni, ctx->tune_merge);
 	}
 	uint8_t *image2_buf = NULL, *mem_buf[2] = { NULL, NULL }; int16_t *coef_up_dev[2] = { NULL, NULL };
 	if (sub) {
@@ -1855,7 +1894,7 @@ static int stage_jobs(jpegqs_cuda_ctx *ctx, int njobs, const jpegqs_cuda_job *jo
 	if (quant_reserve(ctx, QS_MAX_JOBS)) return JPEGQS_ERR_CUDA;
 	std::vector<QsQuantDev> q(njobs); std::vector<QsJob> v(njobs);
 	for (int i = 0; i < njobs; i++) {
-		int val; quant_prepare(jobs[i].quant, &q[i], &val, ctx->tune_maxn, ctx->tune_uni);
+		int val; quant_prepare(jobs[i].quant, &q[i], &val, ctx->tune_maxn, ctx->tune_uni, ctx->tune_merge);
 		QsJob &j = v[i]; memset(&j, 0, sizeof(j));
 		j.coef = jobs[i].coef; j.plane = jobs[i].plane; j.plane2 = jobs[i].plane2;
 		j.quant = ctx->quant_dev + i;

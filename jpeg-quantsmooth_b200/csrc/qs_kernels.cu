@@ -791,6 +791,48 @@ __device__ __forceinline__ void qs_chunk_edge(const QsChunk &ch, const float *ta
 	QS_PH_MARK(ph, 9);
 }
 
+/* "mixed" chunk (schedule type 3): NF (1 or 2) full coefficients of an anti-diagonal together with
+ * its two edge coefficients - idx[NF] lies in row 0 (no vertical terms), idx[NF+1] in column 0
+ * (no horizontal terms; quantsmooth.h:1527, 1531).  The edge coefficients share the pixel
+ * expansion, the differences and the table-load slots of the full ones instead of paying for
+ * single-coefficient horizontal / vertical passes of their own, and the diagonal has one chunk
+ * (one barrier, one header, one update batch) less. */
+template <int NF, bool DIAG, int SYNC>
+__device__ __forceinline__ void qs_chunk_mixed(const QsChunk &ch, const float *tabs, const uint2 *pw,
+		const QsQuantDev *__restrict__ qd, uint16_t *cs, int grp, QsPh &ph, const uint32_t *nh, uint32_t *h, long long *msum) {
+	const int NT = NF + 2, TS = DIAG ? QS_TAB_DIAG : QS_TAB_PLAIN;
+	const float *tab[NT]; float Rs[NT], a2[NT], a3[NT];
+#pragma unroll
+	for (int c = 0; c < NT; c++) {
+		int i = ch.idx[c];
+		tab[c] = tabs + i * TS; Rs[c] = __ldg(&qd->Rs[i]); a2[c] = 0.0f; a3[c] = 0.0f;
+	}
+	QS_PH_MARK(ph, 4);
+	qs_sec_h<NF + 1, false>(pw, tab, Rs, a2, a3);           /* full coefficients + the row-0 one */
+	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 5);
+	qs_sec_border<NT, false>(pw, tab, Rs, a2, a3);
+	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 6);
+	{                                                       /* full coefficients + the column-0 one */
+		const float *tv[NF + 1]; float Rv[NF + 1], v2[NF + 1], v3[NF + 1];
+#pragma unroll
+		for (int c = 0; c < NF; c++) { tv[c] = tab[c]; Rv[c] = Rs[c]; v2[c] = a2[c]; v3[c] = a3[c]; }
+		tv[NF] = tab[NF + 1]; Rv[NF] = Rs[NF + 1]; v2[NF] = a2[NF + 1]; v3[NF] = a3[NF + 1];
+		qs_sec_v<NF + 1, false>(pw, tv, Rv, v2, v3);
+#pragma unroll
+		for (int c = 0; c < NF; c++) { a2[c] = v2[c]; a3[c] = v3[c]; }
+		a2[NF + 1] = v2[NF]; a3[NF + 1] = v3[NF];
+	}
+	QS_PH_MARK(ph, 7);
+	if (DIAG) { qs_section_sync<SYNC>(grp); qs_sec_diag<NT, false>(pw, tab, Rs, a2, a3); }
+	qs_section_sync<SYNC>(grp);
+	QS_PH_MARK(ph, 8);
+	h[0] = __ldg(nh); h[1] = __ldg(nh + 1); h[2] = __ldg(nh + 2);
+	qs_coef_update<NT>(a2, a3, ch.idx, qd, cs, msum);
+	QS_PH_MARK(ph, 9);
+}
+
 #ifdef QS_EXPERIMENTS
 #include "qs_experiments.cuh"
 #endif
@@ -1102,6 +1144,10 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 			if (ch.first && !(ci == 0 && skip0)) { qs_refresh(cw, pw); qs_group_sync<SYNC>(gsync); }
 			QS_PH_MARK(ph, 3);
 			if (ch.type == 1) qs_chunk_edge<DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+			else if (ch.type == 3) {
+				if (ch.n == 2) qs_chunk_mixed<2, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+				else qs_chunk_mixed<1, DIAG, SYNC>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
+			}
 			else if (ch.type == 2) {
 				if (ch.n == 4) qs_chunk_full<4, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);
 				else if (ch.n == 3) qs_chunk_full<3, DIAG, SYNC, true>(ch, tabs, pw, qd, cs, gsync, ph, nh, h, msum);

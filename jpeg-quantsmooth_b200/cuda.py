@@ -140,7 +140,7 @@ def orig_coef(coef: int, q: int) -> int:
     return load().jpegqs_cuda_orig_coef(coef, q)
 
 
-def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True):
+def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True, merge: bool = False):
     """The smoothing kernel's chunk schedule for a quant table (or the table-independent one
     for quant=None): list of (type, first, [natural-order coefficient indices]).  Host-only."""
     lib = load()
@@ -150,10 +150,11 @@ def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True):
     if quant is not None:
         qa = np.ascontiguousarray(quant, dtype=np.uint16).reshape(64)
         qp = qa.ctypes.data
-    n = lib.jpegqs_cuda_chunk_schedule(qp, max_coefs, int(uniform), out.ctypes.data)
+    n = lib.jpegqs_cuda_chunk_schedule(qp, max_coefs, int(uniform) | (2 if merge else 0), out.ctypes.data)
     if n < 0:
         raise QsError(f"jpegqs_cuda_chunk_schedule: {n}")
-    return [(int(r[0]), int(r[2]), [int(x) for x in r[4:4 + r[1]]]) for r in out[:n]]
+    # type 3 ("mixed"): n full coefficients followed by the row-0 and the column-0 coefficient
+    return [(int(r[0]), int(r[2]), [int(x) for x in r[4:4 + r[1] + (2 if r[0] == 3 else 0)]]) for r in out[:n]]
 
 
 class PinnedArray:

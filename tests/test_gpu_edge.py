@@ -184,6 +184,9 @@ def test_run_slab_pass_level_luma_chroma_handover(ctx, flags, ss, w, h):
         assert got.shape == o.coef.shape and np.array_equal(got, o.coef), k
 
 
+DEFAULT_MERGE = 0        # csrc/qs_cuda.cu tune_merge
+
+
 def test_tuning_variants_are_bit_identical(ctx):
     """The shipped library carries one lock-step configuration (the others live behind
     -DQS_EXPERIMENTS); what can still vary is the chunk schedule: 1..4 coefficients per chunk,
@@ -191,16 +194,24 @@ def test_tuning_variants_are_bit_identical(ctx):
     im = qs.synth.make_image(320, 240, "420")
     want = {f: ol.run_oracle(im, f, 2)[1] for f in (0, 1)}
     try:
-        for uni in (0, 1):
-            for maxn in (1, 2, 3, 4):
-                ctx.set_tuning(1, maxn); ctx.set_tuning(5, uni)
-                for f in (0, 1):
-                    _, out = ctx.do_quantsmooth(im, f, 2)
-                    assert ol.images_equal(out, want[f]), (uni, maxn, f)
+        for merge in (0, 1):                          # key 8: edge coefficients in "mixed" chunks
+            ctx.set_tuning(8, merge)
+            for uni in (0, 1):
+                for maxn in (1, 2, 3, 4):
+                    ctx.set_tuning(1, maxn); ctx.set_tuning(5, uni)
+                    for f in (0, 1):
+                        _, out = ctx.do_quantsmooth(im, f, 2)
+                        assert ol.images_equal(out, want[f]), (merge, uni, maxn, f)
+        ctx.set_tuning(8, 1); ctx.set_tuning(1, 4); ctx.set_tuning(5, 1)
+        for w, h, ss, f in ((250, 130, "444", 7), (160, 400, "gray", 1), (136, 120, "422", 3), (200, 136, "420", 0)):
+            im2 = qs.synth.make_image(w, h, ss)
+            ret, out = ctx.do_quantsmooth(im2, f, 2)
+            oret, o = ol.run_oracle(im2, f, 2)
+            assert ret == oret and ol.images_equal(out, o), (w, h, ss, f)
         with pytest.raises(qs.cuda.QsError):
             ctx.set_tuning(0, 0)                      # free-running warps: experiments build only
     finally:
-        ctx.set_tuning(1, 4); ctx.set_tuning(5, 1)
+        ctx.set_tuning(1, 4); ctx.set_tuning(5, 1); ctx.set_tuning(8, DEFAULT_MERGE)
 
 
 # ---- full BASELINE sizes: size-independent properties (the oracle would take minutes) ----

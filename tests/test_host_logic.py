@@ -60,11 +60,24 @@ def test_torch_generator_matches_numpy():
 
 
 # ---- chunk schedule of the smoothing kernel (host side of DESIGN.md 3.3) ---------------------
+uniform_flag = [True]
+
+
 def _check_schedule(sched, quant, max_coefs):
     seen = []
     diag_order = []
     for typ, first, idx in sched:
         assert 1 <= len(idx) <= (2 if typ == 1 else max_coefs)
+        if typ == 3:                                  # mixed: 1-2 full coefficients, then row-0, then column-0
+            assert max_coefs >= 4 and 3 <= len(idx) <= 4 and first
+            s3 = (idx[0] >> 3) + (idx[0] & 7)
+            assert idx[-2:] == [s3, s3 * 8] and all((i >> 3) and (i & 7) for i in idx[:-2])
+            if quant is not None:                     # a mixed chunk never breaks up a uniform run
+                others = [j for t2, _, ix in sched for j in ix if (j >> 3) + (j & 7) == s3 and (j >> 3) and (j & 7) and j not in idx]
+                for i in idx[:-2]:
+                    assert all((int(quant[i]) or 1) != (int(quant[j]) or 1) for j in others) or not uniform_flag[0]
+            diag_order.append(s3); seen += idx
+            continue
         s = {(i >> 3) + (i & 7) for i in idx}
         assert len(s) == 1, "a chunk never crosses an anti-diagonal (refresh points, quantsmooth.h:313-322)"
         s = s.pop()
@@ -97,9 +110,13 @@ def test_chunk_schedule_covers_every_coefficient_once():
     for quant in tables:
         for max_coefs in (1, 2, 3, 4):
             for uniform in (False, True):
-                _check_schedule(cuda.chunk_schedule(quant, max_coefs, uniform), quant, max_coefs)
+                for merge in (False, True):
+                    uniform_flag[0] = uniform
+                    _check_schedule(cuda.chunk_schedule(quant, max_coefs, uniform, merge), quant, max_coefs)
     # the Annex-K chroma table: 46 of the 49 inner coefficients sit in shared-threshold chunks
     shared = sum(len(idx) for typ, _, idx in cuda.chunk_schedule(im.comps[1].quant) if typ == 2)
     assert shared == 46
     assert all(typ != 2 for typ, _, _ in cuda.chunk_schedule(im.comps[1].quant, 4, False))
     assert len(cuda.chunk_schedule(None)) == 25
+    merged = cuda.chunk_schedule(None, 4, False, True)
+    assert sum(typ == 3 for typ, _, _ in merged) == 6 and sum(typ == 1 for typ, _, _ in merged) == 1   # s = 2..7 merged, s = 1 has no full coefficient

@@ -19,12 +19,15 @@ ap.add_argument("--niter", type=int, default=3)
 ap.add_argument("--width", type=int, default=7680)
 ap.add_argument("--height", type=int, default=4320)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--merge", type=int, default=-1, help="tuning key 8 (mixed chunks), -1 = library default")
 a = ap.parse_args()
 NAMES = ["tile fetch (atomic + barriers)", "tile prologue (job, coef/pixel loads, mixed check)",
          "chunk header + chunk barrier", "refresh IDCT (+ barrier)", "chunk set-up (Rs, table ptrs)",
          "section h", "section border", "section v", "section diag", "coefficient update (div, clamp)",
          "chunk loop exit", "rebalance", "write-back", "-", "-", "-"]
 ctx = qs.cuda.QsContext(0)
+if a.merge >= 0:
+    ctx.set_tuning(8, a.merge)
 lib = qs.cuda.load()
 if not hasattr(lib, "qs_read_phase_clocks"):
     raise SystemExit("not a phase build: set JPEGQS_B200_LIB to libjpegqs_b200_phase.so")

@@ -34,12 +34,17 @@ for v in args.variants.split(","):
     sync, maxn, wpg, gs = f[0], f[1], (f[2] if len(f) > 2 else 4), (f[3] if len(f) > 3 else 1)
     x2 = f[4] if len(f) > 4 else 0
     uni = f[5] if len(f) > 5 else 1
-    ctx.set_tuning(4, x2)
+    merge = f[6] if len(f) > 6 else None
+    if x2:
+        ctx.set_tuning(4, x2)
     ctx.set_tuning(5, uni)
-    ctx.set_tuning(0, sync)
+    if merge is not None:
+        ctx.set_tuning(8, merge)
+    if sync != 2:
+        ctx.set_tuning(0, sync)
     ctx.set_tuning(1, maxn)
-    ctx.set_tuning(2, wpg)
-    ctx.set_tuning(3, gs)
+    if wpg != 4:
+        ctx.set_tuning(2, wpg)
     sm, n, tot, idm, idn = 0.0, 0, 0.0, 0.0, 0
     for i in range(args.steps + 1):
         bufs = [h.to(dev) for h in host]
@@ -55,5 +60,5 @@ for v in args.variants.split(","):
     h = hashlib.sha1(b"".join(t.cpu().numpy().tobytes() for t in bufs)).hexdigest()
     if ref_hash is None:
         ref_hash = h
-    print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs} x2={x2} uni={uni}: smooth {sm / n:.3f} ms/launch, idct pass {1e3 * idm / max(idn, 1):.1f} us/launch, whole run {tot / args.steps:.3f} ms, "
+    print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs} x2={x2} uni={uni} merge={merge}: smooth {sm / n:.3f} ms/launch, idct pass {1e3 * idm / max(idn, 1):.1f} us/launch, whole run {tot / args.steps:.3f} ms, "
           f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
