@@ -416,7 +416,7 @@ def main():
             for typ, _first, idx in qs.cuda.chunk_schedule(quant):
                 if typ == 2:
                     total += (144 + (98 if diag else 0)) * (3 + 5 * len(idx))
-                else:
+                else:                                  # plain, edge and mixed chunks: 8 per term
                     for i in idx:
                         terms = 32 + (56 if i & 7 else 0) + (56 if i > 7 else 0) + (98 if diag else 0)
                         total += 8 * terms

@@ -316,7 +316,7 @@ extern "C" int jpegqs_cuda_create(int device, jpegqs_cuda_ctx **out) {
 	ctx->jobs_dev = NULL; ctx->flags_dev = NULL; ctx->flags_host = NULL;
 	ctx->arena = NULL; ctx->arena_cap = ctx->arena_pos = 0; ctx->ev0 = ctx->ev1 = NULL;
 	ctx->last_ms = 0; ctx->launches = 0;
-	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_merge = 0; ctx->tune_slabs = 1; ctx->tune_wave = 0; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
+	ctx->profiling = 0; ctx->ev_used = 0; ctx->tune_sync = 2; ctx->tune_maxn = 4; ctx->tune_wpg = 4; ctx->tune_gs = 1; ctx->tune_uni = 1; ctx->tune_merge = 1; ctx->tune_slabs = 1; ctx->tune_wave = 0; ctx->tune_x2 = 0;   /* packed FP32x2 measured slower: profiles/README.md */
 	ctx->kernel_ms[0] = ctx->kernel_ms[1] = 0; ctx->kernel_launches[0] = ctx->kernel_launches[1] = 0;
 	int rc = [&]() -> int {
 		CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

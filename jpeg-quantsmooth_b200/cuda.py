@@ -140,7 +140,7 @@ def orig_coef(coef: int, q: int) -> int:
     return load().jpegqs_cuda_orig_coef(coef, q)
 
 
-def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True, merge: bool = False):
+def chunk_schedule(quant, max_coefs: int = 4, uniform: bool = True, merge: bool = True):
     """The smoothing kernel's chunk schedule for a quant table (or the table-independent one
     for quant=None): list of (type, first, [natural-order coefficient indices]).  Host-only."""
     lib = load()

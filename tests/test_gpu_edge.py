@@ -184,7 +184,7 @@ def test_run_slab_pass_level_luma_chroma_handover(ctx, flags, ss, w, h):
         assert got.shape == o.coef.shape and np.array_equal(got, o.coef), k
 
 
-DEFAULT_MERGE = 0        # csrc/qs_cuda.cu tune_merge
+DEFAULT_MERGE = 1        # csrc/qs_cuda.cu tune_merge
 
 
 def test_tuning_variants_are_bit_identical(ctx):

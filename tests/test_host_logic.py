@@ -114,9 +114,11 @@ def test_chunk_schedule_covers_every_coefficient_once():
                     uniform_flag[0] = uniform
                     _check_schedule(cuda.chunk_schedule(quant, max_coefs, uniform, merge), quant, max_coefs)
     # the Annex-K chroma table: 46 of the 49 inner coefficients sit in shared-threshold chunks
-    shared = sum(len(idx) for typ, _, idx in cuda.chunk_schedule(im.comps[1].quant) if typ == 2)
+    shared = sum(len(idx) for typ, _, idx in cuda.chunk_schedule(im.comps[1].quant, 4, True, False) if typ == 2)
     assert shared == 46
+    shared = sum(len(idx) for typ, _, idx in cuda.chunk_schedule(im.comps[1].quant) if typ == 2)
+    assert shared == 46                                # mixed chunks never break a uniform run
     assert all(typ != 2 for typ, _, _ in cuda.chunk_schedule(im.comps[1].quant, 4, False))
-    assert len(cuda.chunk_schedule(None)) == 25
+    assert len(cuda.chunk_schedule(None, 4, False, False)) == 25
     merged = cuda.chunk_schedule(None, 4, False, True)
     assert sum(typ == 3 for typ, _, _ in merged) == 6 and sum(typ == 1 for typ, _, _ in merged) == 1   # s = 2..7 merged, s = 1 has no full coefficient

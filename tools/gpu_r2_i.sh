@@ -4,7 +4,7 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-OUT=gpurun_out
+OUT=gpurun_out/final; mkdir -p gpurun_out/final
 timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/i_pytest.log 2>&1; echo "rc=$?" >> $OUT/i_pytest.log
 timeout 300 python __graft_entry__.py smoke > $OUT/i_smoke.log 2>&1
 timeout 600 python bench.py > $OUT/i_bench.json 2> $OUT/i_bench.err
