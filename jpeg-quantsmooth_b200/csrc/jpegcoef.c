@@ -11,6 +11,9 @@
 #include <stdint.h>
 #include <pthread.h>
 #include <unistd.h>
+#ifdef __SSE2__
+#include <emmintrin.h>
+#endif
 #include "jpegcoef.h"
 
 /* zig-zag index -> natural (row-major) index, T.81 figure A.6 */
@@ -79,7 +82,12 @@ typedef struct {
 	unsigned char bits[17], val[256];
 	uint16_t look[512];                  /* 9-bit prefix -> (length << 8) | symbol, 0 = longer */
 	int32_t maxcode[18], valptr[17], mincode[17];
+	/* AC symbols whose code AND value bits fit in FAST_BITS: prefix -> (coefficient << 16) | (run << 4)
+	 * | total bits, 0 = take the two-step path (long codes, EOB, ZRL).  One table read per symbol
+	 * instead of code look-up -> value bits -> sign extension. */
+	int32_t fast[1 << 10];
 } jq_dhuff;
+#define FAST_BITS 10
 
 static int dhuff_build(jq_dhuff *h) {
 	int code = 0, k = 0, l, i;
@@ -99,6 +107,15 @@ static int dhuff_build(jq_dhuff *h) {
 		code <<= 1;
 	}
 	h->maxcode[17] = 0x7fffffff;
+	for (i = 0; i < (1 << FAST_BITS); i++) {
+		unsigned e = h->look[i >> (FAST_BITS - 9)]; int len = (int)(e >> 8), r = (int)(e >> 4) & 15, sz = (int)e & 15;
+		h->fast[i] = 0;
+		if (e && sz && len + sz <= FAST_BITS) {
+			int v = (i >> (FAST_BITS - len - sz)) & ((1 << sz) - 1);
+			if (v < (1 << (sz - 1))) v += 1 - (1 << sz);             /* F.2.2.1 EXTEND */
+			h->fast[i] = (int32_t)((uint32_t)v << 16 | (uint32_t)r << 4 | (uint32_t)(len + sz));
+		}
+	}
 	h->present = 1;
 	return 0;
 }
@@ -156,7 +173,11 @@ static inline int huff_decode(jq_bits *b, const jq_dhuff *h) {
 	b->nbits -= 16; b->warn++;
 	return 0;                            /* corrupt data: keep going like libjpeg's JWRN_HUFF_BAD_CODE path */
 }
-static inline int extend(unsigned v, int s) { return s && v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v; }
+/* F.2.2.1 EXTEND without a branch (the sign of a coefficient is a coin toss): v < 2^(s-1) means negative */
+static inline int extend(unsigned v, int s) {
+	int neg = ((int)v - (1 << s >> 1)) >> 31;                /* all ones if v is in the lower half (and for s = 0) */
+	return (int)v + (neg & (1 - (1 << s)));
+}
 
 /* ---------------------------------------------------------------- the reader */
 typedef struct {
@@ -173,27 +194,35 @@ typedef struct {
 
 static void dec_block_seq(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFPTR blk) {
 	int c = s->ci[k], t, i;
+	const jq_dhuff *h = &d->ac[s->ta[k]];
+	uint64_t buf; int nbits;
 	t = huff_decode(b, &d->dc[s->td[k]]);
 	d->pred[c] += extend(bits_get(b, t & 15), t & 15);
 	blk[0] = (JCOEF)d->pred[c];
-	{
-		const jq_dhuff *h = &d->ac[s->ta[k]];
-		for (i = 1; i < 64; ) {
-			/* one refill check per symbol: a code (<= 16 bits) and its value bits (<= 15) fit in 32 */
-			unsigned look, e, v; int rs, r, sz;
-			if (b->nbits < 32) bits_fill(b);
-			look = (unsigned)(b->buf >> (b->nbits - 16)) & 0xFFFF;
-			e = h->look[look >> 7];
-			if (e) { b->nbits -= (int)(e >> 8); rs = (int)(e & 255); }
-			else rs = huff_decode(b, h);
-			r = rs >> 4; sz = rs & 15;
-			if (!sz) { if (r != 15) break; i += 16; continue; }
-			i += r;
-			v = (unsigned)(b->buf >> (b->nbits - sz)) & ((1u << sz) - 1); b->nbits -= sz;
-			blk[zz_nat[i]] = (JCOEF)extend(v, sz);
+	buf = b->buf; nbits = b->nbits;                     /* the bit window lives in registers inside the loop */
+	for (i = 1; i < 64; ) {
+		/* one refill check per symbol: a code (<= 16 bits) and its value bits (<= 15) fit in 32 */
+		unsigned look, e, v; int rs, r, sz, f;
+		if (nbits < 32) { b->buf = buf; b->nbits = nbits; bits_fill(b); buf = b->buf; nbits = b->nbits; }
+		look = (unsigned)(buf >> (nbits - 16)) & 0xFFFF;
+		f = h->fast[look >> (16 - FAST_BITS)];
+		if (f) {                                        /* code and value in one step */
+			i += (f >> 4) & 15; nbits -= f & 15;
+			blk[zz_nat[i]] = (JCOEF)(f >> 16);
 			i++;
+			continue;
 		}
+		e = h->look[look >> 7];
+		if (e) { nbits -= (int)(e >> 8); rs = (int)(e & 255); }
+		else { b->buf = buf; b->nbits = nbits; rs = huff_decode(b, h); nbits = b->nbits; }
+		r = rs >> 4; sz = rs & 15;
+		if (!sz) { if (r != 15) break; i += 16; continue; }
+		i += r;
+		v = (unsigned)(buf >> (nbits - sz)) & ((1u << sz) - 1); nbits -= sz;
+		blk[zz_nat[i]] = (JCOEF)extend(v, sz);
+		i++;
 	}
+	b->buf = buf; b->nbits = nbits;
 }
 
 static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFPTR blk) {
@@ -471,7 +500,12 @@ static void out_bits(jq_out *o, unsigned code, int n) {
 }
 static void out_flush(jq_out *o) { if (o->nacc) out_bits(o, 0x7F, 8 - o->nacc); o->acc = 0; o->nacc = 0; }
 
-typedef struct { unsigned char bits[17], val[256]; int nval; unsigned code[256]; unsigned char size[256]; long freq[257]; } jq_ehuff;
+typedef struct {
+	unsigned char bits[17], val[256]; int nval;
+	unsigned code[256]; unsigned char size[256];
+	uint32_t cs[256];                    /* (code << 8) | size: one load per symbol in the block coder */
+	long freq[257];
+} jq_ehuff;
 
 /* T.81 K.3.3 example tables */
 static const unsigned char std_dc_l_bits[17] = { 0, 0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0 };
@@ -510,6 +544,7 @@ static void ehuff_codes(jq_ehuff *h) {                  /* T.81 C.2 */
 		for (i = 0; i < h->bits[l]; i++, k++) { h->code[h->val[k]] = code++; h->size[h->val[k]] = (unsigned char)l; }
 		code <<= 1;
 	}
+	for (i = 0; i < 256; i++) h->cs[i] = h->size[i] ? (uint32_t)h->code[i] << 8 | h->size[i] : 0;
 }
 /* optimal code lengths limited to 16 bits, T.81 K.2 (figures K.1 - K.4) */
 static void ehuff_optimal(jq_ehuff *h) {
@@ -557,7 +592,7 @@ static inline int bit_size(int v) { unsigned a = (unsigned)(v < 0 ? -v : v); ret
 
 typedef struct {
 	unsigned char *p; size_t n, cap;     /* whole bytes, unstuffed */
-	uint64_t acc; int nacc;              /* pending bits (< 8 after a block) */
+	uint64_t acc; int nacc;              /* pending bits: < 32 after a block, < 8 after seg_finish */
 	int fail;
 	char pad[128];                       /* workers write neighbouring entries: keep them on separate cache lines */
 } jq_seg;
@@ -572,51 +607,93 @@ typedef struct {
 	volatile int range_error;
 } jq_enc;
 
-#define SEG_PUT(code, size) do { acc = (acc << (size)) | (uint64_t)(code); nacc += (size); } while (0)
-#define SEG_DRAIN() do { while (nacc >= 8) { nacc -= 8; *w++ = (unsigned char)(acc >> nacc); } } while (0)
+/* code bits go to a 64-bit accumulator that is emptied four bytes at a time: at most 31 bits are
+ * pending before a put, a put adds at most 27 (a 16-bit code + 11 value bits) */
+#define SEG_PUT(code, size) do { acc = (acc << (size)) | (uint64_t)(code); nacc += (size); \
+	if (nacc >= 32) { uint32_t x_ = __builtin_bswap32((uint32_t)(acc >> (nacc - 32))); memcpy(w, &x_, 4); w += 4; nacc -= 32; } } while (0)
+
+/* Which coefficients of a block are not zero, as a bit mask in ZIG-ZAG order (bit k = k-th
+ * coefficient of the scan): the block coder then walks the set bits instead of testing 63
+ * coefficients.  Natural-order mask by 16-bit compares (SSE2 when the target has it), turned
+ * into zig-zag order with one table look-up per block row. */
+static uint64_t zz_mask_tab[8][256];
+static pthread_once_t zz_mask_once = PTHREAD_ONCE_INIT;
+static void zz_mask_init(void) {
+	int r, b, c, k; unsigned char nat_zz[64];
+	for (k = 0; k < 64; k++) nat_zz[zz_nat[k]] = (unsigned char)k;
+	for (r = 0; r < 8; r++) for (b = 0; b < 256; b++) {
+		uint64_t m = 0;
+		for (c = 0; c < 8; c++) if (b >> c & 1) m |= 1ULL << nat_zz[r * 8 + c];
+		zz_mask_tab[r][b] = m;
+	}
+}
+static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
+	uint64_t m = 0; int r;
+#ifdef __SSE2__
+	const __m128i z = _mm_setzero_si128();
+	for (r = 0; r < 8; r += 2) {
+		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
+		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
+		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));     /* bit set = coefficient not zero */
+		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
+	}
+#else
+	for (r = 0; r < 8; r++) {
+		unsigned k = 0; int c;
+		for (c = 0; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
+		m |= zz_mask_tab[r][k];
+	}
+#endif
+	return m;
+}
 
 /* one block: counts symbols (sg == NULL) or appends its code bits to the segment */
 static inline int enc_block(jq_seg *sg, const JCOEF *blk, int *pred, const jq_ehuff *dc, const jq_ehuff *ac,
 		long *fdc, long *fac) {
-	int diff = blk[0] - *pred, s = bit_size(diff), i, run = 0;
+	int diff = blk[0] - *pred, s = bit_size(diff), k, prev = 0, run;
+	uint64_t zm = nonzero_mask_zz(blk) & ~1ULL;
 	*pred = blk[0];
 	if (s > 11) return -1;
 	if (!sg) {
 		fdc[s]++;
-		for (i = 1; i < 64; i++) {
-			int v = blk[zz_nat[i]];
-			if (!v) { run++; continue; }
+		while (zm) {
+			k = __builtin_ctzll(zm); zm &= zm - 1;
+			run = k - prev - 1; prev = k;
 			for (; run > 15; run -= 16) fac[0xF0]++;
-			s = bit_size(v);
+			s = bit_size(blk[zz_nat[k]]);
 			if (s > 10) return -1;
 			fac[run << 4 | s]++;
-			run = 0;
 		}
-		if (run) fac[0]++;
+		if (prev != 63) fac[0]++;
 		return 0;
 	}
 	{
 		uint64_t acc = sg->acc; int nacc = sg->nacc;
 		unsigned char *w = sg->p + sg->n;            /* the caller reserved room for a whole block */
-		SEG_PUT(dc->code[s], dc->size[s]);
-		if (s) SEG_PUT((unsigned)(diff < 0 ? diff - 1 : diff) & ((1u << s) - 1), s);
-		SEG_DRAIN();
-		for (i = 1; i < 64; i++) {
-			int v = blk[zz_nat[i]], rs;
-			if (!v) { run++; continue; }
-			for (; run > 15; run -= 16) { SEG_PUT(ac->code[0xF0], ac->size[0xF0]); SEG_DRAIN(); }
+		uint32_t cs = dc->cs[s];
+		SEG_PUT((uint64_t)(cs >> 8) << s | ((unsigned)(diff + (diff >> 31)) & ((1u << s) - 1)), (int)(cs & 255) + s);
+		while (zm) {
+			int v;
+			k = __builtin_ctzll(zm); zm &= zm - 1;
+			run = k - prev - 1; prev = k;
+			v = blk[zz_nat[k]];
+			for (; run > 15; run -= 16) SEG_PUT(ac->cs[0xF0] >> 8, (int)(ac->cs[0xF0] & 255));
 			s = bit_size(v);
 			if (s > 10) return -1;
-			rs = run << 4 | s;
-			SEG_PUT(ac->code[rs], ac->size[rs]);
-			SEG_PUT((unsigned)(v < 0 ? v - 1 : v) & ((1u << s) - 1), s);
-			SEG_DRAIN();
-			run = 0;
+			cs = ac->cs[run << 4 | s];
+			/* value bits: v for v > 0, v - 1 for v < 0 (F.1.2.1), the low s bits of it */
+			SEG_PUT((uint64_t)(cs >> 8) << s | ((unsigned)(v + (v >> 31)) & ((1u << s) - 1)), (int)(cs & 255) + s);
 		}
-		if (run) { SEG_PUT(ac->code[0], ac->size[0]); SEG_DRAIN(); }
-		sg->acc = acc & 0xFF; sg->nacc = nacc; sg->n = (size_t)(w - sg->p);
+		if (prev != 63) SEG_PUT(ac->cs[0] >> 8, (int)(ac->cs[0] & 255));
+		sg->acc = acc; sg->nacc = nacc; sg->n = (size_t)(w - sg->p);
 	}
 	return 0;
+}
+
+/* whole bytes of the pending bits to the buffer: fewer than 8 stay (room: see enc_rows) */
+static void seg_finish(jq_seg *sg) {
+	while (sg->nacc >= 8) { sg->nacc -= 8; sg->p[sg->n++] = (unsigned char)(sg->acc >> sg->nacc); }
+	sg->acc &= 0xFF;
 }
 
 /* MCU rows [y0, y1): walk = 1 only tracks the DC predictors (used for the row above a segment) */
@@ -670,6 +747,7 @@ static void *enc_worker(void *arg) {
 		if (y0 > 0) enc_rows(e, y0 - 1, y0, pred, NULL, NULL, 1);
 		if (enc_rows(e, y0, y1, pred, e->dc ? &e->seg[i] : NULL, e->dc ? NULL : e->freq[i], 0) &&
 				!(e->dc && e->seg[i].fail)) e->range_error = 1;
+		if (e->dc && e->seg[i].p) seg_finish(&e->seg[i]);
 	}
 	return NULL;
 }
@@ -684,12 +762,38 @@ static int enc_thread_count(JDIMENSION mcuy) {
 	return n < 1 ? 1 : n;
 }
 
-/* appends a segment's bits at the output's current bit position, stuffing FF bytes */
+/* appends a segment's bits at the output's current bit position, stuffing FF bytes.  Eight
+ * bytes at a time: shifted to the output's bit phase, tested for an FF byte with one
+ * arithmetic expression, stored whole when there is none. */
 static void out_segment(jq_out *o, const jq_seg *sg) {
-	size_t i = 0;
-	if (o->nacc == 0) {
-		for (; i < sg->n; i++) { unsigned b = sg->p[i]; out_byte(o, b); if (b == 0xFF) out_byte(o, 0); }
-	} else for (; i < sg->n; i++) out_bits(o, sg->p[i], 8);
+	size_t i = 0, need = o->n + 2 * sg->n + 32;
+	int k = o->nacc;                                    /* 0..7 bits already pending in o->acc */
+	if (need > o->cap) {
+		size_t nc = o->cap ? o->cap : 1 << 16; unsigned char *q;
+		while (nc < need) nc *= 2;
+		q = (unsigned char*)realloc(o->p, nc);
+		if (!q) { o->fail = 1; return; }
+		o->p = q; o->cap = nc;
+	}
+	{
+		unsigned char *w = o->p + o->n;
+		uint64_t carry = k ? o->acc & ((1ULL << k) - 1) : 0;
+		for (; i + 8 <= sg->n; i += 8) {
+			uint64_t x, v; int j;
+			memcpy(&x, sg->p + i, 8); x = __builtin_bswap64(x);      /* first byte on top */
+			v = k ? carry << (64 - k) | x >> k : x;
+			carry = x;                                               /* its low k bits are the new pending bits */
+			if (!((~v - 0x0101010101010101ULL) & v & 0x8080808080808080ULL)) {
+				uint64_t be = __builtin_bswap64(v); memcpy(w, &be, 8); w += 8;
+			} else for (j = 56; j >= 0; j -= 8) {
+				unsigned c = (unsigned)(v >> j) & 255;
+				*w++ = (unsigned char)c; if (c == 0xFF) *w++ = 0;
+			}
+		}
+		o->n = (size_t)(w - o->p);
+		o->acc = k ? carry & ((1ULL << k) - 1) : 0;
+	}
+	for (; i < sg->n; i++) out_bits(o, sg->p[i], 8);
 	if (sg->nacc) out_bits(o, (unsigned)sg->acc & ((1u << sg->nacc) - 1), sg->nacc);
 }
 
@@ -703,6 +807,7 @@ static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff 
 	e.mcux = (ci->image_width + 8 * maxh - 1) / (8 * maxh); e.mcuy = (ci->image_height + 8 * maxv - 1) / (8 * maxv);
 	if (!e.mcuy || !e.mcux) return 0;
 	for (k = 0; k < ci->num_components; k++) if (ci->comp_info[k].v_samp_factor > 4) return -1;
+	pthread_once(&zz_mask_once, zz_mask_init);
 	nthr = enc_thread_count(e.mcuy);
 	e.nseg = nthr == 1 ? 1 : nthr * 4;
 	if ((JDIMENSION)e.nseg > e.mcuy) e.nseg = (int)e.mcuy;

@@ -550,6 +550,23 @@ __device__ __forceinline__ void qs_prep_slice(uint2 w, float *f, int c) {
  * between the coefficients and differenced afterwards, so neither the LDS latency nor the
  * PRMT->FADD chain sits in front of the FP work. */
 
+/* unroll factors of the row loops of the sections.  Measurement knobs: unrolling by 2 removes 2-4 %
+ * of a loop's instructions (address arithmetic, the fp = fn copies) and is SLOWER - 2.507 ms per 8K
+ * q3 launch rolled, 2.551 / 2.541 / 2.534 with the h / border / v loop unrolled by 2, 2.556 with
+ * all three (profiles/README.md, GPU call M): the loop bodies (260-310 instructions at N = 4) stop
+ * fitting the instruction cache the four lock-step warps share. */
+#ifndef QS_UNROLL_H
+#define QS_UNROLL_H 1
+#endif
+#ifndef QS_UNROLL_B
+#define QS_UNROLL_B 1
+#endif
+#ifndef QS_UNROLL_V
+#define QS_UNROLL_V 1
+#endif
+#define QS_PRAGMA_(x) _Pragma(#x)
+#define QS_PRAGMA(x) QS_PRAGMA_(x)
+
 /* horizontal pairs, quantsmooth.h:1527 */
 template <int N, bool UNI>
 __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *tab, const float *Rs,
@@ -561,7 +578,7 @@ __device__ __forceinline__ void qs_sec_h(const uint2 *pw, const float *const *ta
 #pragma unroll
 		for (int x = 0; x < 7; x++) d[x] = FS(f[x], f[x + 1]);
 	}
-#pragma unroll 1
+QS_PRAGMA(unroll QS_UNROLL_H)
 	for (int y = 0; y < 8; y++) {
 		uint2 wn = pw[((y + 1) & 7) * 32];              /* next row (wraps on the last pass) */
 		float f[8];
@@ -583,7 +600,7 @@ __device__ __forceinline__ void qs_sec_border(const uint2 *pw, const float *cons
 #pragma unroll
 		for (int x = 0; x < 8; x++) d[x] = FS(fa[x], fb[x]);
 	}
-#pragma unroll 1
+QS_PRAGMA(unroll QS_UNROLL_B)
 	for (int s = 0; s < 4; s++) {
 		int sn = (s + 1) & 3;
 		int wi = sn == 0 ? 0 : sn == 1 ? 7 : 6 + sn;     /* word of the block edge for step sn */
@@ -607,7 +624,7 @@ __device__ __forceinline__ void qs_sec_v(const uint2 *pw, const float *const *ta
 #pragma unroll
 		for (int x = 0; x < 8; x++) d[x] = FS(f0[x], fp[x]);
 	}
-#pragma unroll 1
+QS_PRAGMA(unroll QS_UNROLL_V)
 	for (int y = 0; y < 7; y++) {
 		uint2 wn = pw[min(y + 2, 7) * 32];
 		float fn[8];
@@ -881,6 +898,33 @@ __device__ __forceinline__ void qs_fdct_clamp(float *f, const QsQuantDev *__rest
 	}
 }
 
+/* the same for the LOW_QUALITY kernel: the transformed block is parked in shared memory
+ * (fs[k * 32]) and the clamp loop is rolled - that kernel's top stall was instruction fetch
+ * (profiles/README.md) - and, like qs_coef_update, it leaves the two sums of the rebalance step
+ * (m0 = sum coef*a0, m1 = sum a0*a0 over the AC coefficients; the clamp keeps the new value in
+ * the quantization interval of a0, so a0 is what the rebalance step would recompute) */
+__device__ __forceinline__ void qs_fdct_clamp_rolled(float *f, float *fs, const QsQuantDev *__restrict__ qd, uint16_t *cs,
+		long long &m0, long long &m1) {
+	qs_fdct_8x8(f);
+#pragma unroll
+	for (int x = 0; x < 64; x++) fs[x * 32] = f[x];
+	long long s0 = 0, s1 = 0;
+#pragma unroll 8
+	for (int x = 0; x < 64; x++) {
+		uint16_t *slot = cs + (x >> 1) * 64 + (x & 1);
+		int c = (short)*slot;
+		int q = __ldg(&qd->q[x]);
+		int a0 = qs_orig_coef(c, q, __ldg(&qd->m31[x]));
+		int d0 = (q - 1) >> 1, d1 = q >> 1;
+		int dh = a0 + (a0 < 0 ? d1 : d0), dl = a0 - (a0 > 0 ? d1 : d0);
+		int add = qs_cvtt_x86(roundf(fs[x * 32]));
+		add = min(add, dh); add = max(add, dl);
+		*slot = (uint16_t)add;
+		if (x) { s0 += add * a0; s1 += a0 * a0; }
+	}
+	m0 = s0; m1 = s1;
+}
+
 /* JOINT_YUV chroma predictor + fdct_clamp, quantsmooth.h:577-579, 894-921, 551-561 */
 __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, const uint8_t *__restrict__ img2,
 		int stride, const QsQuantDev *__restrict__ qd, uint16_t *cs) {
@@ -900,21 +944,22 @@ __device__ __noinline__ void qs_joint_predict(const uint8_t *__restrict__ img, c
 	qs_fdct_clamp(f, qd, cs);
 }
 
-/* rebalance, quantsmooth.h:1566-1568, 1823-1848 */
-template <bool HAVE_SUMS>
-__device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs, const long long *msum) {
-	long long m0 = 0, m1 = 0;
-	if (HAVE_SUMS) { m0 = msum[0]; m1 = msum[32]; }
-	else {
-		/* 63 independent iterations, latency bound when rolled (LDS -> LDG -> IMAD.HI); unrolled
-		 * by 7 the loads of seven coefficients are in flight together */
+/* rebalance, quantsmooth.h:1566-1568, 1823-1848: the two sums over the AC coefficients ... */
+__device__ __forceinline__ void qs_rebalance_sums(const QsQuantDev *__restrict__ qd, const uint16_t *cs, long long &m0, long long &m1) {
+	long long s0 = 0, s1 = 0;
+	/* 63 independent iterations, latency bound when rolled (LDS -> LDG -> IMAD.HI); unrolled
+	 * by 7 the loads of seven coefficients are in flight together */
 #pragma unroll 7
-		for (int k = 1; k < 64; k++) {
-			int c = (short)cs[(k >> 1) * 64 + (k & 1)];
-			int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
-			m0 += c * a0; m1 += a0 * a0;
-		}
+	for (int k = 1; k < 64; k++) {
+		int c = (short)cs[(k >> 1) * 64 + (k & 1)];
+		int a0 = qs_orig_coef(c, __ldg(&qd->q[k]), __ldg(&qd->m31[k]));
+		s0 += c * a0; s1 += a0 * a0;
 	}
+	m0 = s0; m1 = s1;
+}
+/* ... and the rescaling they decide (the smoothing kernel and the LOW_QUALITY kernel keep the
+ * sums up to date while they clamp, qs_coef_update / qs_fdct_clamp_rolled) */
+__device__ __forceinline__ void qs_rebalance(const QsQuantDev *__restrict__ qd, uint16_t *cs, long long m0, long long m1) {
 	if (m1 > m0 && m0 != 0) {
 		int mul = (int)(((m1 << 13) + (m0 >> 1)) / m0);
 #pragma unroll 7
@@ -1161,7 +1206,7 @@ __global__ void __launch_bounds__(QS_SYNC_WPS(SYNC) * 128, 1) qs_smooth_kernel(c
 		QS_PH_MARK(ph, 10);
 
 		if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
-			qs_rebalance<true>(qd, cs, msum);
+			qs_rebalance(qd, cs, msum[0], msum[32]);
 		QS_PH_MARK(ph, 11);
 
 		if (valid) {
@@ -1221,6 +1266,7 @@ __device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, int *
 __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob *__restrict__ jobs, int njobs, int total_tiles,
 		int flags, int clamp_out, const int *__restrict__ bad) {
 	__shared__ uint32_t sm[4 * 32 * 32];
+	__shared__ float sf[4 * 64 * 32];
 	int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int tile = blockIdx.x * 4 + warp;
 	if (tile >= total_tiles) return;
@@ -1243,6 +1289,7 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 			cw[(j * 4 + 2) * 32] = v.z; cw[(j * 4 + 3) * 32] = v.w;
 		}
 	}
+	long long m0 = 0, m1 = 0; bool have_sums = false;
 	if (job->plane2) {                                  /* JOINT_YUV predictor, then straight to rebalance (928) */
 		const uint8_t *img2 = job->plane2 + (size_t)(by * 8 + 1) * stride + QS_PLANE_PAD + bx * 8;
 		qs_joint_predict(img, img2, stride, qd, cs);
@@ -1257,10 +1304,13 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 		if (range > 128.0f) range = 128.0f;
 		range = roundf(range);
 		const float c0 = 2.0f, c1 = FM(2.0f, 0.70710678118654752440f);   /* c0 * sqrtf(0.5f) */
-		float f[64];
 		int r0[10], r1[10], r2[10];
 		qs_lowq_row(img - stride, r0); qs_lowq_row(img, r1);
-#pragma unroll
+		/* rows in a rolled loop (one 8-pixel body instead of 64 pixels of straight-line code),
+		 * the filtered pixels parked in shared memory: 0.554 -> 0.493 ms per 8K launch together
+		 * with the rolled clamp loop (profiles/README.md, GPU call M) */
+		float *f = sf + warp * 2048 + lane;
+#pragma unroll 1
 		for (int y = 0; y < 8; y++) {
 			qs_lowq_row(img + (size_t)(y + 1) * stride, r2);
 #pragma unroll
@@ -1273,15 +1323,21 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 				NB(c1, r2[x]) NB(c0, r2[x + 1]) NB(c1, r2[x + 2])
 #undef NB
 				if (an > 0.0f) a = qs_cvtt_x86(FS((float)a, __fdiv_rn(a0, an)));
-				f[y * 8 + x] = (float)(a - 128);
+				f[(y * 8 + x) * 32] = (float)(a - 128);
 			}
 #pragma unroll
 			for (int k = 0; k < 10; k++) { r0[k] = r1[k]; r1[k] = r2[k]; }
 		}
-		qs_fdct_clamp(f, qd, cs);
+		float fr[64];
+#pragma unroll
+		for (int k = 0; k < 64; k++) fr[k] = f[k * 32];
+		qs_fdct_clamp_rolled(fr, f, qd, cs, m0, m1);
+		have_sums = true;
 	}
-	if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV)))
-		qs_rebalance<false>(qd, cs, NULL);
+	if (!(flags & QS_NO_REBALANCE) && !(!job->luma && (flags & QS_NO_REBALANCE_UV))) {
+		if (!have_sums) qs_rebalance_sums(qd, cs, m0, m1);
+		qs_rebalance(qd, cs, m0, m1);
+	}
 	{
 		int4 *p = (int4 *)cptr;
 #pragma unroll

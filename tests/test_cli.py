@@ -38,6 +38,10 @@ FILES = [
     ("rst", 250, 190, False, dict(quality=80, restart_marker_rows=1)),
     ("progrst", 250, 190, False, dict(quality=80, progressive=True, restart_marker_blocks=7)),
     ("tinyprog", 17, 9, True, dict(quality=60, progressive=True)),
+    # dense blocks with large magnitudes (long codes, the two-step decode path, FF bytes to stuff) and
+    # nearly empty ones (long zero runs, ZRL): the two ends of the block coder's fast paths
+    ("dense444", 320, 200, False, dict(quality=100, subsampling=0)),
+    ("coarse420", 300, 220, False, dict(quality=3)),
 ]
 
 
@@ -91,7 +95,7 @@ def test_codec_is_a_lossless_transcoder(jpegs, tmp_path, name, optimize):
 def test_writer_bytes_do_not_depend_on_the_thread_count(jpegs, tmp_path):
     """The writer codes segments of MCU rows on worker threads and splices their bits: the file
     must be byte for byte the sequential coder's (1 thread), also with -o and odd thread counts."""
-    for name in ("base420", "prog420", "gray", "rst", "base444"):
+    for name in ("base420", "prog420", "gray", "rst", "base444", "dense444", "coarse420"):
         if name not in jpegs:
             continue
         for optimize in ([], ["-o"]):

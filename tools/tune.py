@@ -5,6 +5,7 @@ produces byte-identical output."""
 import argparse
 import hashlib
 import os
+import pickle
 import sys
 
 import numpy as np
@@ -24,7 +25,14 @@ args = ap.parse_args()
 
 ctx = qs.cuda.QsContext(0)
 ctx.set_profiling(True)
-im = qs.synth.make_image(args.width, args.height, "420")
+cache = f"/tmp/qs_tune_{args.width}x{args.height}.pkl"     # the generator takes ~10 s at 8K: keep it between runs of one session
+if os.path.exists(cache):
+    with open(cache, "rb") as fh:
+        im = pickle.load(fh)
+else:
+    im = qs.synth.make_image(args.width, args.height, "420")
+    with open(cache, "wb") as fh:
+        pickle.dump(im, fh, protocol=4)
 dev = torch.device("cuda", 0)
 host = [torch.from_numpy(np.ascontiguousarray(c.coef)) for c in im.comps]
 stream = torch.cuda.current_stream().cuda_stream or 1   # 1 = cudaStreamLegacy
@@ -61,4 +69,4 @@ for v in args.variants.split(","):
     if ref_hash is None:
         ref_hash = h
     print(f"sync={sync} maxn={maxn} wpg={wpg} gs={gs} x2={x2} uni={uni} merge={merge}: smooth {sm / n:.3f} ms/launch, idct pass {1e3 * idm / max(idn, 1):.1f} us/launch, whole run {tot / args.steps:.3f} ms, "
-          f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}", flush=True)
+          f"{args.width * args.height / 1e6 / (tot / args.steps / 1e3):.0f} Mpix/s, same_output={h == ref_hash}, sha1={h[:12]}", flush=True)
