@@ -15,7 +15,9 @@
  *     -c, --copy n       0 = no markers, 1 = comments, 2 = comments + APPn (default)
  *     --batch            (extension) any number of "input output" pairs follow: one process, CUDA
  *                        start-up paid once (it is 1-2 s in a fresh process, 100x the smoothing
- *                        of an 8K image); exit status = the worst of the pairs
+ *                        of an 8K image); reading, smoothing and writing of successive pairs
+ *                        overlap (JPEGQS_NO_PIPELINE=1: one pair after the other); exit status =
+ *                        the worst of the pairs
  *     --ppm              (extension) write the decoded RGB image as binary PPM/PGM instead of a
  *                        JPEG: the device-side equivalent of the reference's example.c
  *                        (JPEG -> pixels through jpegqs_start_decompress)
@@ -69,67 +71,75 @@ static int usage(const char *prog) {
 	return 1;
 }
 
-/* one input -> one output; returns the process exit status for this pair */
-static int run_one(const char *prog, const char *in_name, const char *out_name, jpegqs_control_t *optsp,
-		int copy, int optimize, int verbose, int ppm, int cpu, int warm_ok) {
-	jpegqs_control_t opts = *optsp;
-	char *const *argv = (char *const *)&prog;            /* argv[0] in the messages below */
-	int i, ret, io_err = 0, warnings, warm = 0;
-	double t_start, t_read, t_smooth, t_write;
-	FILE *f; unsigned char *data, *out = NULL; size_t len = 0, outlen = 0;
-	jq_image im; char err[256];
-#ifndef JPEGQS_NO_CUDA_RENDER
-	pthread_t warm_th;
-#endif
-	(void)i; (void)cpu; (void)warm_ok;
-	t_start = now_ms();
-#ifndef JPEGQS_NO_CUDA_RENDER
-	/* CUDA start-up (context + kernel image, a few hundred ms in a fresh process) overlaps with
-	 * reading and Huffman-decoding the input */
-	if (warm_ok && (opts.niter > 0 || (opts.flags & JPEGQS_UPSAMPLE_UV)) && !getenv("JPEGQS_NO_WARMUP")) warm = !pthread_create(&warm_th, NULL, warmup_thread, &opts.flags);
-#endif
-	f = strcmp(in_name, "-") ? fopen(in_name, "rb") : stdin;
-	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", argv[0], in_name); return 1; }
+/* One "input output" pair moves through three stages: read + Huffman-decode, do_quantsmooth,
+ * encode + write.  A single pair runs them in a row; --batch runs them as a pipeline (a reader
+ * thread, the calling thread for the device work, a writer thread), so that with many files the
+ * process moves at the pace of the slowest stage instead of their sum. */
+typedef struct {
+	const char *in_name, *out_name;
+	int state;                           /* stages completed: 0 none, 1 read, 2 smoothed, 3 written */
+	int rc;                              /* exit status of this pair so far (non-zero: later stages are skipped) */
+	int have_im;
+	jq_image im;
+	double t_read, t_smooth, t_write;    /* stage durations, ms */
+} qs_job;
+
+typedef struct {
+	const char *prog;
+	jpegqs_control_t opts;
+	int copy, optimize, verbose, ppm, cpu;
+} qs_cfg;
+
+static void job_read(const qs_cfg *g, qs_job *j) {
+	double t0 = now_ms();
+	FILE *f; unsigned char *data; size_t len = 0; char err[256];
+	f = strcmp(j->in_name, "-") ? fopen(j->in_name, "rb") : stdin;
+	if (!f) { fprintf(stderr, "%s: can't open input file \"%s\"\n", g->prog, j->in_name); j->rc = 1; return; }
 	data = load_all(f, &len);
 	if (f != stdin) fclose(f);
-	if (!data) { fprintf(stderr, "%s: can't read input file \"%s\"\n", argv[0], in_name); return 1; }
-	if (jq_read(data, len, copy, &im, err)) { fprintf(stderr, "%s: %s\n", argv[0], err); free(data); return 1; }
+	if (!data) { fprintf(stderr, "%s: can't read input file \"%s\"\n", g->prog, j->in_name); j->rc = 1; return; }
+	if (jq_read(data, len, g->copy, &j->im, err)) { fprintf(stderr, "%s: %s\n", g->prog, err); free(data); j->rc = 1; return; }
 	free(data);
-	if (verbose)
-		fprintf(stderr, "%s: %ux%u, %d component(s), %s, restart interval %d\n", in_name, im.cinfo.image_width,
-				im.cinfo.image_height, im.cinfo.num_components, im.progressive ? "progressive" : "sequential",
-				im.restart_interval);
+	j->have_im = 1;
+	if (g->verbose)
+		fprintf(stderr, "%s: %ux%u, %d component(s), %s, restart interval %d\n", j->in_name, j->im.cinfo.image_width,
+				j->im.cinfo.image_height, j->im.cinfo.num_components, j->im.progressive ? "progressive" : "sequential",
+				j->im.restart_interval);
+	j->t_read = now_ms() - t0;
+}
 
-	t_read = now_ms();
-	ret = do_quantsmooth(&im.cinfo, im.coef_arrays, &opts);
-#ifndef JPEGQS_NO_CUDA_RENDER
-	if (warm) pthread_join(warm_th, NULL);
-#endif
-	(void)warm;
-	if (ret < 0) { jq_free(&im); return 2; }
-	t_smooth = now_ms();
+static void job_smooth(const qs_cfg *g, qs_job *j) {
+	double t0 = now_ms();
+	jpegqs_control_t opts = g->opts;
+	if (do_quantsmooth(&j->im.cinfo, j->im.coef_arrays, &opts) < 0) j->rc = 2;
+	j->t_smooth = now_ms() - t0;
+}
 
+static void job_write(const qs_cfg *g, qs_job *j) {
+	double t0 = now_ms();
+	jq_image *im = &j->im;
+	FILE *f; unsigned char *out = NULL; size_t outlen = 0; char err[256]; int io_err = 0;
 #ifdef JPEGQS_NO_CUDA_RENDER
-	if (ppm) { fprintf(stderr, "%s: --ppm needs the CUDA back end\n", argv[0]); jq_free(&im); return 1; }
+	if (g->ppm) { fprintf(stderr, "%s: --ppm needs the CUDA back end\n", g->prog); j->rc = 1; return; }
 #else
-	if (ppm) {                                          /* decode to RGB on the device */
-		jpegqs_cuda_ctx *ctx = NULL; jpegqs_cuda_image ci; int c, nc = im.cinfo.num_components, rc;
+	if (g->ppm) {                                       /* decode to RGB on the device */
+		jpegqs_cuda_ctx *ctx = NULL; jpegqs_cuda_image ci; int c, nc = im->cinfo.num_components, rc;
 		int16_t *bufs[MAX_COMPONENTS] = { 0 }; unsigned char *rgb; char hdr[64]; int hl;
-		size_t npx = (size_t)im.cinfo.image_width * im.cinfo.image_height;
-		if (jpegqs_cuda_create(cpu ? cpu - 1 : -1, &ctx)) {
-			fprintf(stderr, "%s: CUDA back end unavailable: %s\n", argv[0], jpegqs_cuda_last_error(NULL));
-			jq_free(&im); return 2;
+		size_t npx = (size_t)im->cinfo.image_width * im->cinfo.image_height;
+		if (jpegqs_cuda_create(g->cpu ? g->cpu - 1 : -1, &ctx)) {
+			fprintf(stderr, "%s: CUDA back end unavailable: %s\n", g->prog, jpegqs_cuda_last_error(NULL));
+			j->rc = 2; return;
 		}
 		memset(&ci, 0, sizeof(ci));
-		ci.ncomp = nc; ci.is_ycbcr = im.cinfo.jpeg_color_space == JCS_YCbCr;
-		ci.image_width = im.cinfo.image_width; ci.image_height = im.cinfo.image_height;
+		ci.ncomp = nc; ci.is_ycbcr = im->cinfo.jpeg_color_space == JCS_YCbCr;
+		ci.image_width = im->cinfo.image_width; ci.image_height = im->cinfo.image_height;
 		for (c = 0; c < nc; c++) {
-			jpeg_component_info *k = &im.cinfo.comp_info[c]; JDIMENSION y;
+			jpeg_component_info *k = &im->cinfo.comp_info[c]; JDIMENSION y;
 			size_t rowb = (size_t)k->width_in_blocks * sizeof(JBLOCK);
 			bufs[c] = (int16_t*)malloc(rowb * k->height_in_blocks + 1);
 			if (bufs[c]) for (y = 0; y < k->height_in_blocks; y++)
-				memcpy((char*)bufs[c] + y * rowb, (*im.cinfo.mem->access_virt_barray)((j_common_ptr)&im.cinfo,
-						im.coef_arrays[c], y, 1, FALSE)[0], rowb);
+				memcpy((char*)bufs[c] + y * rowb, (*im->cinfo.mem->access_virt_barray)((j_common_ptr)&im->cinfo,
+						im->coef_arrays[c], y, 1, FALSE)[0], rowb);
 			ci.comp[c].coef = bufs[c]; ci.comp[c].wblk = k->width_in_blocks; ci.comp[c].hblk = k->height_in_blocks;
 			ci.comp[c].h_samp = k->h_samp_factor; ci.comp[c].v_samp = k->v_samp_factor;
 			ci.comp[c].has_qtbl = k->quant_table != NULL;
@@ -138,42 +148,129 @@ static int run_one(const char *prog, const char *in_name, const char *out_name, 
 		rgb = (unsigned char*)malloc(npx * 3 + 1);
 		for (c = 0; c < nc; c++) if (!bufs[c]) rgb = (free(rgb), (unsigned char*)NULL);
 		if (!rgb) {
-			fprintf(stderr, "%s: out of memory\n", argv[0]);
+			fprintf(stderr, "%s: out of memory\n", g->prog);
 			for (c = 0; c < nc; c++) free(bufs[c]);
-			jpegqs_cuda_destroy(ctx); jq_free(&im); return 1;
+			jpegqs_cuda_destroy(ctx); j->rc = 1; return;
 		}
 		rc = jpegqs_cuda_render_rgb(ctx, &ci, 0, rgb, NULL);
-		if (rc) fprintf(stderr, "%s: render failed (%d): %s\n", argv[0], rc, jpegqs_cuda_last_error(ctx));
+		if (rc) fprintf(stderr, "%s: render failed (%d): %s\n", g->prog, rc, jpegqs_cuda_last_error(ctx));
 		for (c = 0; c < nc; c++) free(bufs[c]);
 		jpegqs_cuda_destroy(ctx);
-		if (rc) { free(rgb); jq_free(&im); return 2; }
+		if (rc) { free(rgb); j->rc = 2; return; }
 		if (nc == 1) { size_t k; for (k = 0; k < npx; k++) rgb[k] = rgb[3 * k]; }
-		hl = snprintf(hdr, sizeof(hdr), "P%d\n%u %u\n255\n", nc == 1 ? 5 : 6, im.cinfo.image_width, im.cinfo.image_height);
+		hl = snprintf(hdr, sizeof(hdr), "P%d\n%u %u\n255\n", nc == 1 ? 5 : 6, im->cinfo.image_width, im->cinfo.image_height);
 		outlen = hl + npx * (nc == 1 ? 1 : 3);
 		out = (unsigned char*)malloc(outlen);
-		if (!out) { fprintf(stderr, "%s: out of memory\n", argv[0]); free(rgb); jq_free(&im); return 1; }
+		if (!out) { fprintf(stderr, "%s: out of memory\n", g->prog); free(rgb); j->rc = 1; return; }
 		memcpy(out, hdr, hl); memcpy(out + hl, rgb, outlen - hl);
 		free(rgb);
 	} else
 #endif
-	if (jq_write(&im, im.coef_arrays, optimize, &out, &outlen, err)) {
-		fprintf(stderr, "%s: %s\n", argv[0], err); jq_free(&im); return 1;
+	if (jq_write(im, im->coef_arrays, g->optimize, &out, &outlen, err)) {
+		fprintf(stderr, "%s: %s\n", g->prog, err); j->rc = 1; return;
 	}
 	/* the output is opened after the input was read, so it may name the same file */
-	f = strcmp(out_name, "-") ? fopen(out_name, "wb") : stdout;
-	if (!f) { fprintf(stderr, "%s: can't open output file \"%s\"\n", argv[0], out_name); free(out); jq_free(&im); return 1; }
+	f = strcmp(j->out_name, "-") ? fopen(j->out_name, "wb") : stdout;
+	if (!f) { fprintf(stderr, "%s: can't open output file \"%s\"\n", g->prog, j->out_name); free(out); j->rc = 1; return; }
 	if (fwrite(out, 1, outlen, f) != outlen) io_err = 1;
 	if (f != stdout ? fclose(f) != 0 : fflush(f) != 0) io_err = 1;      /* ENOSPC shows up at the flush */
-	if (io_err) fprintf(stderr, "%s: error writing \"%s\"\n", argv[0], out_name);
-	t_write = now_ms();
-	if (verbose) fprintf(stderr, "wall time: read + decode %.1f ms, do_quantsmooth %.1f ms (includes waiting for CUDA start-up), "
-			"encode + write %.1f ms\n", t_read - t_start, t_smooth - t_read, t_write - t_smooth);
-	warnings = im.warnings;
-	free(out); jq_free(&im);
+	if (io_err) fprintf(stderr, "%s: error writing \"%s\"\n", g->prog, j->out_name);
+	free(out);
+	j->t_write = now_ms() - t0;
+	if (g->verbose) fprintf(stderr, "wall time: read + decode %.1f ms, do_quantsmooth %.1f ms (includes waiting for CUDA start-up), "
+			"encode + write %.1f ms\n", j->t_read, j->t_smooth, j->t_write);
 	/* the reference's exit status (quantsmooth.c:626): 2 when the codec met recoverable damage
 	 * (libjpeg's num_warnings), else 0 - do_quantsmooth's "stopped early" value is not an error */
-	return io_err ? 1 : warnings ? 2 : 0;
+	j->rc = io_err ? 1 : im->warnings ? 2 : 0;
 }
+
+static void job_release(qs_job *j) { if (j->have_im) { jq_free(&j->im); j->have_im = 0; } }
+
+/* one input -> one output, the stages in a row; returns the process exit status for this pair */
+static int run_one(const qs_cfg *g, qs_job *j, int warm_ok) {
+	int warm = 0;
+#ifndef JPEGQS_NO_CUDA_RENDER
+	pthread_t warm_th; int wflags = g->opts.flags;
+	/* CUDA start-up (context + kernel image, a few hundred ms in a fresh process) overlaps with
+	 * reading and Huffman-decoding the input */
+	if (warm_ok && (g->opts.niter > 0 || (g->opts.flags & JPEGQS_UPSAMPLE_UV)) && !getenv("JPEGQS_NO_WARMUP"))
+		warm = !pthread_create(&warm_th, NULL, warmup_thread, &wflags);
+#endif
+	(void)warm_ok;
+	job_read(g, j);
+	if (!j->rc) job_smooth(g, j);
+#ifndef JPEGQS_NO_CUDA_RENDER
+	if (warm) pthread_join(warm_th, NULL);
+#endif
+	(void)warm;
+	if (!j->rc) job_write(g, j);
+	job_release(j);
+	return j->rc;
+}
+
+#ifndef JPEGQS_NO_CUDA_RENDER
+/* --batch pipeline.  The reader runs at most QS_DEPTH pairs ahead of the writer (an 8K image is
+ * 100 MB of coefficients) and does not open an input that an earlier, unfinished pair is going
+ * to write. */
+#define QS_DEPTH 3
+typedef struct {
+	const qs_cfg *g; qs_job *jobs; int n;
+	pthread_mutex_t mu; pthread_cond_t cv;
+} qs_pipe;
+
+static void pipe_advance(qs_pipe *p, qs_job *j, int state) {
+	pthread_mutex_lock(&p->mu); j->state = state; pthread_cond_broadcast(&p->cv); pthread_mutex_unlock(&p->mu);
+}
+static void pipe_wait(qs_pipe *p, qs_job *j, int state) {
+	pthread_mutex_lock(&p->mu);
+	while (j->state < state) pthread_cond_wait(&p->cv, &p->mu);
+	pthread_mutex_unlock(&p->mu);
+}
+static void *pipe_reader(void *arg) {
+	qs_pipe *p = (qs_pipe*)arg; int i, k;
+	for (i = 0; i < p->n; i++) {
+		if (i >= QS_DEPTH) pipe_wait(p, &p->jobs[i - QS_DEPTH], 3);
+		for (k = 0; k < i; k++)
+			if (strcmp(p->jobs[k].out_name, "-") && !strcmp(p->jobs[k].out_name, p->jobs[i].in_name)) pipe_wait(p, &p->jobs[k], 3);
+		job_read(p->g, &p->jobs[i]);
+		pipe_advance(p, &p->jobs[i], 1);
+	}
+	return NULL;
+}
+static void *pipe_writer(void *arg) {
+	qs_pipe *p = (qs_pipe*)arg; int i;
+	for (i = 0; i < p->n; i++) {
+		pipe_wait(p, &p->jobs[i], 2);
+		if (!p->jobs[i].rc) job_write(p->g, &p->jobs[i]);
+		job_release(&p->jobs[i]);
+		pipe_advance(p, &p->jobs[i], 3);
+	}
+	return NULL;
+}
+/* returns the worst exit status of the pairs, -1 if no thread could be started (nothing done) */
+static int run_pipeline(const qs_cfg *g, qs_job *jobs, int n) {
+	qs_pipe p; pthread_t rd, wr; int i, worst = 0, have_writer;
+	p.g = g; p.jobs = jobs; p.n = n;
+	pthread_mutex_init(&p.mu, NULL); pthread_cond_init(&p.cv, NULL);
+	if (pthread_create(&rd, NULL, pipe_reader, &p)) { pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu); return -1; }
+	have_writer = !pthread_create(&wr, NULL, pipe_writer, &p);
+	for (i = 0; i < n; i++) {
+		pipe_wait(&p, &jobs[i], 1);
+		if (!jobs[i].rc) job_smooth(g, &jobs[i]);
+		if (have_writer) pipe_advance(&p, &jobs[i], 2);
+		else {                                          /* no writer thread: write from here */
+			if (!jobs[i].rc) job_write(g, &jobs[i]);
+			job_release(&jobs[i]);
+			pipe_advance(&p, &jobs[i], 3);
+		}
+	}
+	pthread_join(rd, NULL);
+	if (have_writer) pthread_join(wr, NULL);
+	pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu);
+	for (i = 0; i < n; i++) if (jobs[i].rc > worst) worst = jobs[i].rc;
+	return worst;
+}
+#endif
 
 int main(int argc, char **argv) {
 	int optimize = 0, verbose = 0, info = 15, cpu = 0, copy = 2, quality = 3, niter = -1, cmd_flags = -1, threads = 0;
@@ -226,9 +323,26 @@ int main(int argc, char **argv) {
 
 	/* --batch: any number of "input output" pairs in one process, so that CUDA start-up (1-2 s in a
 	 * fresh process, profiles/README.md) is paid once; the exit status is the worst of the pairs */
-	for (; i + 1 < argc; i += 2) {
-		int rc = run_one(argv[0], argv[i], argv[i + 1], &opts, copy, optimize, verbose, ppm, cpu, status == 0);
-		if (rc > status) status = rc;
+	{
+		qs_cfg g; qs_job *jobs; int n = (argc - i) / 2, k;
+		g.prog = argv[0]; g.opts = opts; g.copy = copy; g.optimize = optimize; g.verbose = verbose; g.ppm = ppm; g.cpu = cpu;
+		jobs = (qs_job*)calloc((size_t)n, sizeof(qs_job));
+		if (!jobs) { fprintf(stderr, "%s: out of memory\n", argv[0]); return 1; }
+		for (k = 0; k < n; k++) { jobs[k].in_name = argv[i + 2 * k]; jobs[k].out_name = argv[i + 2 * k + 1]; }
+		k = 0;
+#ifndef JPEGQS_NO_CUDA_RENDER
+		/* (--ppm renders on the device inside the write stage: those pairs stay in a row) */
+		if (n > 1 && !ppm && !getenv("JPEGQS_NO_PIPELINE")) {
+			int rc;
+			/* the first pair alone, with the CUDA warm-up beside its decode; the rest as a pipeline */
+			status = run_one(&g, &jobs[0], 1);
+			rc = run_pipeline(&g, jobs + 1, n - 1);
+			if (rc > status) status = rc;
+			k = rc < 0 ? 1 : n;
+		}
+#endif
+		for (; k < n; k++) { int rc = run_one(&g, &jobs[k], status == 0); if (rc > status) status = rc; }
+		free(jobs);
 	}
 	return status;
 }

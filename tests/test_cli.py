@@ -183,6 +183,29 @@ def test_batch_mode_equals_single_runs(jpegs, tmp_path):
     assert subprocess.run([EXE, "--batch", jpegs["gray"]], capture_output=True).returncode == 1     # odd count: usage
 
 
+def test_batch_pipeline_keeps_the_order_of_dependent_pairs(jpegs, tmp_path):
+    """--batch runs read / smooth / write as a three-stage pipeline.  A pair whose input is the
+    output of an earlier pair must see the finished file, a failing pair must not disturb the
+    others, and the files must be those of the one-pair-after-the-other mode (JPEGQS_NO_PIPELINE)."""
+    def run(tag, env):
+        a, b, c, d = (str(tmp_path / f"{tag}_{k}.jpg") for k in "abcd")
+        args = [EXE, "-n", "0", "-i", "0", "-t", "3", "--batch",
+                jpegs["base444"], a,              # a
+                a, b,                             # reads what the first pair writes
+                str(tmp_path / "missing.jpg"), str(tmp_path / f"{tag}_x.jpg"),
+                jpegs["prog420"], c,
+                jpegs["dense444"], d,
+                d, d]                             # in place, after the pair before it
+        r = subprocess.run(args, capture_output=True, text=True, env=env)
+        assert r.returncode == 1 and "missing.jpg" in r.stderr
+        assert not os.path.exists(tmp_path / f"{tag}_x.jpg")
+        return [open(f, "rb").read() for f in (a, b, c, d)]
+    piped = run("p", dict(os.environ))
+    plain = run("s", dict(os.environ, JPEGQS_NO_PIPELINE="1"))
+    assert piped == plain
+    assert piped[0] == piped[1]                   # transcoding our own output changes nothing
+
+
 def test_bad_input_and_usage(tmp_path):
     bad = tmp_path / "bad.jpg"
     bad.write_bytes(b"this is not a jpeg")
@@ -247,6 +270,22 @@ def test_smoothed_pixels_equal_decoding_the_smoothed_file(jpegs, tmp_path, name,
     assert subprocess.run([EXE, "-i", "0"] + args + ["--ppm", jpegs[name], ppm]).returncode == 0
     assert subprocess.run([EXE, "-i", "0"] + args + [jpegs[name], jpg]).returncode == 0
     assert np.array_equal(np.asarray(PIL.open(ppm)), np.asarray(PIL.open(jpg)))
+
+
+@pytest.mark.gpu
+def test_batch_pipeline_on_the_device(jpegs, tmp_path):
+    """--batch with real smoothing: the reader and writer threads work on other pairs while the
+    calling thread runs do_quantsmooth; every file equals the one a single-pair process writes."""
+    names = ["base420", "prog444", "gray", "dense444", "opt422", "rst"]
+    args = [EXE, "-q", "3", "-i", "0", "--batch"]
+    for n in names:
+        args += [jpegs[n], str(tmp_path / f"b_{n}.jpg")]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for n in names:
+        single = str(tmp_path / f"s_{n}.jpg")
+        assert subprocess.run([EXE, "-q", "3", "-i", "0", jpegs[n], single]).returncode == 0
+        assert open(single, "rb").read() == open(tmp_path / f"b_{n}.jpg", "rb").read(), n
 
 
 def test_codec_survives_corrupt_input(jpegs, tmp_path):

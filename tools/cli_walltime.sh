@@ -24,10 +24,16 @@ for mode in warm nowarm; do
     echo " | $mode run $i: process total $(python3 -c "print(round($t1 - $t0, 3))") s"
   done
 done
-# one process, four files: start-up amortised
-t0=$(date +%s.%N)
-$E -v 1 -i 0 -q 3 --batch $T/in.jpg $T/o1.jpg $T/in.jpg $T/o2.jpg $T/in.jpg $T/o3.jpg $T/in.jpg $T/o4.jpg 2>&1 | grep "wall time" | sed 's/^/  batch: /'
-t1=$(date +%s.%N)
-echo "batch of 4 files in one process: total $(python3 -c "print(round($t1 - $t0, 3))") s"
-cmp $T/out.jpg $T/o4.jpg && echo "batch output identical to the single-file run"
+# one process, many files: start-up amortised; read / smooth / write of different files overlap
+# (three-stage pipeline), JPEGQS_NO_PIPELINE=1 runs the pairs one after the other
+args=""
+for k in 1 2 3 4 5 6 7 8 9 10 11 12; do args="$args $T/in.jpg $T/o$k.jpg"; done
+for mode in pipeline sequential; do
+  if [ $mode = sequential ]; then export JPEGQS_NO_PIPELINE=1; else unset JPEGQS_NO_PIPELINE; fi
+  t0=$(date +%s.%N)
+  $E -v 1 -i 0 -q 3 --batch $args 2>&1 | grep "wall time" | tail -3 | sed "s/^/  batch ($mode), last 3 of 12: /"
+  t1=$(date +%s.%N)
+  echo "batch of 12 files in one process ($mode): total $(python3 -c "print(round($t1 - $t0, 3))") s"
+  cmp $T/out.jpg $T/o12.jpg && echo "batch output identical to the single-file run"
+done
 rm -rf $T
