@@ -40,6 +40,9 @@
 static void *warmup_thread(void *arg) { jpegqs_warmup(*(int*)arg); return NULL; }
 #endif
 #include <sys/time.h>
+#ifdef __GLIBC__
+#include <malloc.h>
+#endif
 static double now_ms(void) { struct timeval tv; gettimeofday(&tv, NULL); return tv.tv_sec * 1e3 + tv.tv_usec * 1e-3; }
 
 static unsigned char *load_all(FILE *f, size_t *len) {
@@ -330,6 +333,12 @@ int main(int argc, char **argv) {
 		if (!jobs) { fprintf(stderr, "%s: out of memory\n", argv[0]); return 1; }
 		for (k = 0; k < n; k++) { jobs[k].in_name = argv[i + 2 * k]; jobs[k].out_name = argv[i + 2 * k + 1]; }
 		k = 0;
+#ifdef __GLIBC__
+		/* the 100 MB coefficient arrays of one pair become those of the next: kept in the heap
+		 * they are cleared by a memset instead of being unmapped and page-faulted in again
+		 * (one arena: the reader thread's allocations must come from that heap too) */
+		if (n > 1) { mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_ARENA_MAX, 1); }
+#endif
 #ifndef JPEGQS_NO_CUDA_RENDER
 		/* (--ppm renders on the device inside the write stage: those pairs stay in a row) */
 		if (n > 1 && !ppm && !getenv("JPEGQS_NO_PIPELINE")) {
