@@ -1252,12 +1252,12 @@ extern "C" int qs_read_phase_clocks(unsigned long long *out, int reset) {
  * range from the coefficient magnitudes, 8-neighbour one-shot filter, FDCT + clamp,
  * rebalance.  ~10 k instructions and ~420 B of traffic per block: the HBM-bound mode.
  * ------------------------------------------------------------------------------------------ */
-__device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, int *r) {
-	/* 10 pixels x = -1..8 of one plane row; p points at x = 0 (8-byte aligned) */
+__device__ __forceinline__ void qs_lowq_row(const uint8_t *__restrict__ p, float *r) {
+	/* 10 pixels x = -1..8 of one plane row as 1 + px * 2^-15 (qs_px); p points at x = 0 (8-byte aligned) */
 	uint2 w = *(const uint2 *)p;
-	r[0] = p[-1]; r[9] = p[8];
+	r[0] = qs_px((uint32_t)p[-1], 0); r[9] = qs_px((uint32_t)p[8], 0);
 #pragma unroll
-	for (int k = 0; k < 4; k++) { r[1 + k] = (w.x >> (8 * k)) & 0xff; r[5 + k] = (w.y >> (8 * k)) & 0xff; }
+	for (int k = 0; k < 4; k++) { r[1 + k] = qs_px(w.x, k); r[5 + k] = qs_px(w.y, k); }
 }
 
 #ifndef QS_LOWQ_MINB
@@ -1304,7 +1304,13 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 		if (range > 128.0f) range = 128.0f;
 		range = roundf(range);
 		const float c0 = 2.0f, c1 = FM(2.0f, 0.70710678118654752440f);   /* c0 * sqrtf(0.5f) */
-		int r0[10], r1[10], r2[10];
+		/* The same exact rescaling as in the smoothing kernel: pixels as 1 + p * 2^-15, so a
+		 * difference is d * 2^-15 with no int -> float conversion, and with range * 2^-15 the clamp
+		 * max(range - |d|, 0) is one add.sat.  The products carry pure power-of-two factors (2^-75
+		 * in a0, 2^-60 in an, no underflow: tools/lowq_scaling_check.c checks every (range, d) and
+		 * 2e7 random pixels against the plain form); the quotient comes out scaled by 2^-15. */
+		const float rs = FM(range, 3.0517578125e-05f);
+		float r0[10], r1[10], r2[10];
 		qs_lowq_row(img - stride, r0); qs_lowq_row(img, r1);
 		/* rows in a rolled loop (one 8-pixel body instead of 64 pixels of straight-line code),
 		 * the filtered pixels parked in shared memory: 0.554 -> 0.493 ms per 8K launch together
@@ -1315,15 +1321,18 @@ __global__ void __launch_bounds__(128, QS_LOWQ_MINB) qs_lowq_kernel(const QsJob 
 			qs_lowq_row(img + (size_t)(y + 1) * stride, r2);
 #pragma unroll
 			for (int x = 0; x < 8; x++) {
-				int a = r1[x + 1]; float a0 = 0.0f, an = 0.0f;
-#define NB(c_, v_) { float t0 = (float)(a - (v_)), t = FS(range, fabsf(t0)), aw; \
-	t = t < 0.0f ? 0.0f : t; t = FM(t, t); aw = FM(c_, t); a0 = FA(a0, FM(FM(t0, t), aw)); an = FA(an, FM(aw, aw)); }
+				const float ac = r1[x + 1]; float a0 = 0.0f, an = 0.0f;
+#define NB(c_, v_) { float d = FS(ac, v_), t, aw; \
+	asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(t) : "f"(rs), "f"(-fabsf(d))); \
+	t = FM(t, t); aw = FM(c_, t); a0 = FA(a0, FM(FM(d, t), aw)); an = FA(an, FM(aw, aw)); }
 				NB(c1, r0[x]) NB(c0, r0[x + 1]) NB(c1, r0[x + 2])
 				NB(c0, r1[x]) NB(c0, r1[x + 2])
 				NB(c1, r2[x]) NB(c0, r2[x + 1]) NB(c1, r2[x + 2])
 #undef NB
-				if (an > 0.0f) a = qs_cvtt_x86(FS((float)a, __fdiv_rn(a0, an)));
-				f[(y * 8 + x) * 32] = (float)(a - 128);
+				const float af = FM(FS(ac, 1.0f), 32768.0f);            /* (float)pixel, exact */
+				float fv = FS(af, 128.0f);
+				if (an > 0.0f) fv = (float)(qs_cvtt_x86(FS(af, FM(__fdiv_rn(a0, an), 32768.0f))) - 128);
+				f[(y * 8 + x) * 32] = fv;
 			}
 #pragma unroll
 			for (int k = 0; k < 10; k++) { r0[k] = r1[k]; r1[k] = r2[k]; }
