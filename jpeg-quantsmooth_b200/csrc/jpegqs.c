@@ -212,12 +212,14 @@ static int run_one(const qs_cfg *g, qs_job *j, int warm_ok) {
 }
 
 #ifndef JPEGQS_NO_CUDA_RENDER
-/* --batch pipeline.  The reader runs at most QS_DEPTH pairs ahead of the writer (an 8K image is
- * 100 MB of coefficients) and does not open an input that an earlier, unfinished pair is going
- * to write. */
-#define QS_DEPTH 3
+/* --batch pipeline.  Huffman decoding is the slowest stage (one thread per file: an entropy-coded
+ * segment has no entry points), so several reader threads decode different files at once
+ * (JPEGQS_BATCH_READERS, default 3).  Readers stay at most `depth` pairs ahead of the writer (an
+ * 8K image is 100 MB of coefficients) and do not open an input that an earlier, unfinished pair
+ * is going to write. */
+#define QS_MAX_READERS 16
 typedef struct {
-	const qs_cfg *g; qs_job *jobs; int n;
+	const qs_cfg *g; qs_job *jobs; int n, next, depth;
 	pthread_mutex_t mu; pthread_cond_t cv;
 } qs_pipe;
 
@@ -231,8 +233,10 @@ static void pipe_wait(qs_pipe *p, qs_job *j, int state) {
 }
 static void *pipe_reader(void *arg) {
 	qs_pipe *p = (qs_pipe*)arg; int i, k;
-	for (i = 0; i < p->n; i++) {
-		if (i >= QS_DEPTH) pipe_wait(p, &p->jobs[i - QS_DEPTH], 3);
+	for (;;) {
+		pthread_mutex_lock(&p->mu); i = p->next++; pthread_mutex_unlock(&p->mu);
+		if (i >= p->n) break;
+		if (i >= p->depth) pipe_wait(p, &p->jobs[i - p->depth], 3);
 		for (k = 0; k < i; k++)
 			if (strcmp(p->jobs[k].out_name, "-") && !strcmp(p->jobs[k].out_name, p->jobs[i].in_name)) pipe_wait(p, &p->jobs[k], 3);
 		job_read(p->g, &p->jobs[i]);
@@ -252,10 +256,17 @@ static void *pipe_writer(void *arg) {
 }
 /* returns the worst exit status of the pairs, -1 if no thread could be started (nothing done) */
 static int run_pipeline(const qs_cfg *g, qs_job *jobs, int n) {
-	qs_pipe p; pthread_t rd, wr; int i, worst = 0, have_writer;
-	p.g = g; p.jobs = jobs; p.n = n;
+	qs_pipe p; pthread_t rd[QS_MAX_READERS], wr; int i, worst = 0, have_writer, nrd = 3, started = 0;
+	const char *env = getenv("JPEGQS_BATCH_READERS");
+	if (env && atoi(env) > 0) nrd = atoi(env);
+	if (nrd > QS_MAX_READERS) nrd = QS_MAX_READERS;
+	if (nrd > n) nrd = n;
+	/* stdin is read in the order of the pairs: one reader then */
+	for (i = 0; i < n; i++) if (!strcmp(jobs[i].in_name, "-")) nrd = 1;
+	p.g = g; p.jobs = jobs; p.n = n; p.next = 0; p.depth = nrd + 2;
 	pthread_mutex_init(&p.mu, NULL); pthread_cond_init(&p.cv, NULL);
-	if (pthread_create(&rd, NULL, pipe_reader, &p)) { pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu); return -1; }
+	for (i = 0; i < nrd; i++) { if (pthread_create(&rd[started], NULL, pipe_reader, &p)) break; started++; }
+	if (!started) { pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu); return -1; }
 	have_writer = !pthread_create(&wr, NULL, pipe_writer, &p);
 	for (i = 0; i < n; i++) {
 		pipe_wait(&p, &jobs[i], 1);
@@ -267,7 +278,7 @@ static int run_pipeline(const qs_cfg *g, qs_job *jobs, int n) {
 			pipe_advance(&p, &jobs[i], 3);
 		}
 	}
-	pthread_join(rd, NULL);
+	for (i = 0; i < started; i++) pthread_join(rd[i], NULL);
 	if (have_writer) pthread_join(wr, NULL);
 	pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu);
 	for (i = 0; i < n; i++) if (jobs[i].rc > worst) worst = jobs[i].rc;
@@ -344,13 +355,23 @@ int main(int argc, char **argv) {
 		if (n > 1 && !ppm && !getenv("JPEGQS_NO_PIPELINE")) {
 			int rc;
 			/* the first pair alone, with the CUDA warm-up beside its decode; the rest as a pipeline */
+			double t0;
 			status = run_one(&g, &jobs[0], 1);
+			t0 = now_ms();
 			rc = run_pipeline(&g, jobs + 1, n - 1);
 			if (rc > status) status = rc;
 			k = rc < 0 ? 1 : n;
+			if (verbose && rc >= 0) fprintf(stderr, "batch: %d pairs after the first in %.1f ms (pipeline)\n", n - 1, now_ms() - t0);
 		}
 #endif
-		for (; k < n; k++) { int rc = run_one(&g, &jobs[k], status == 0); if (rc > status) status = rc; }
+		if (k < n) {
+			double t0 = 0; int first = k;
+			for (; k < n; k++) {
+				int rc = run_one(&g, &jobs[k], status == 0); if (rc > status) status = rc;
+				if (k == 0) t0 = now_ms();
+			}
+			if (verbose && n > 1 && first == 0) fprintf(stderr, "batch: %d pairs after the first in %.1f ms (one after the other)\n", n - 1, now_ms() - t0);
+		}
 		free(jobs);
 	}
 	return status;

@@ -28,10 +28,12 @@ done
 # (three-stage pipeline), JPEGQS_NO_PIPELINE=1 runs the pairs one after the other
 args=""
 for k in 1 2 3 4 5 6 7 8 9 10 11 12; do args="$args $T/in.jpg $T/o$k.jpg"; done
-for mode in pipeline sequential; do
-  if [ $mode = sequential ]; then export JPEGQS_NO_PIPELINE=1; else unset JPEGQS_NO_PIPELINE; fi
+for mode in pipeline readers1 sequential; do
+  unset JPEGQS_NO_PIPELINE JPEGQS_BATCH_READERS
+  if [ $mode = sequential ]; then export JPEGQS_NO_PIPELINE=1; fi
+  if [ $mode = readers1 ]; then export JPEGQS_BATCH_READERS=1; fi
   t0=$(date +%s.%N)
-  $E -v 1 -i 0 -q 3 --batch $args 2>&1 | grep "wall time" | tail -3 | sed "s/^/  batch ($mode), last 3 of 12: /"
+  $E -v 1 -i 0 -q 3 --batch $args 2>&1 | grep "wall time\|^batch" | tail -3 | sed "s/^/  batch ($mode), last 2 of 12 + steady state: /"
   t1=$(date +%s.%N)
   echo "batch of 12 files in one process ($mode): total $(python3 -c "print(round($t1 - $t0, 3))") s"
   cmp $T/out.jpg $T/o12.jpg && echo "batch output identical to the single-file run"
