@@ -7,6 +7,8 @@ mkdir -p gpurun_out
 OUT=gpurun_out/o; mkdir -p $OUT
 timeout 400 python -m pytest tests/test_cli.py -m gpu -x -q > $OUT/o_pytest_cli.log 2>&1; echo "rc=$?" >> $OUT/o_pytest_cli.log
 tail -3 $OUT/o_pytest_cli.log
+timeout 300 python -m pytest tests/test_golden.py tests/test_gpu_edge.py -m gpu -x -q -k "golden or low_quality" > $OUT/o_pytest_lowq.log 2>&1; echo "rc=$?" >> $OUT/o_pytest_lowq.log
+tail -3 $OUT/o_pytest_lowq.log
 timeout 300 bash tools/cli_walltime.sh > $OUT/o_cli_walltime.txt 2>&1
 cat $OUT/o_cli_walltime.txt
 timeout 300 python bench.py > $OUT/o_bench.json 2> $OUT/o_bench.err
