@@ -125,6 +125,7 @@ typedef struct {
 	uint64_t buf; int nbits;
 	int hit_marker;                      /* a marker (not a stuffed FF00) stopped the feed */
 	int warn;                            /* bad Huffman codes met (decoding goes on, like libjpeg) */
+	uint64_t fed;                        /* data bytes fed so far (an FF00 pair is one): 8 * fed - nbits = bit position */
 } jq_bits;
 
 static void bits_fill(jq_bits *b) {
@@ -136,12 +137,13 @@ static void bits_fill(jq_bits *b) {
 		if (!((nx - 0x0101010101010101ULL) & ~nx & 0x8080808080808080ULL)) {
 			uint64_t be = __builtin_bswap64(x);          /* little-endian hosts only (x86-64, aarch64) */
 			b->buf = k == 8 ? be : (b->buf << (8 * k)) | (be >> (64 - 8 * k));
-			b->p += k; b->nbits += 8 * k;
+			b->p += k; b->nbits += 8 * k; b->fed += (unsigned)k;
 			return;
 		}
 	}
 	while (b->nbits <= 48) {
 		unsigned c = 0;
+		b->fed++;
 		if (!b->hit_marker && b->p < b->end) {
 			c = *b->p;
 			if (c == 0xFF) {
@@ -180,6 +182,7 @@ static inline int extend(unsigned v, int s) {
 }
 
 /* ---------------------------------------------------------------- the reader */
+static int codec_thread_count(void);
 typedef struct {
 	int ncomp, ci[4], td[4], ta[4], Ss, Se, Ah, Al;
 } jq_scan;
@@ -277,6 +280,358 @@ static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEF
 	}
 }
 
+/* ---------------------------------------------------------------- sequential scans on several threads
+ * An entropy-coded segment has no entry points, but Huffman-coded JPEG data re-synchronizes: a
+ * decoder started at an arbitrary byte soon reads the same codes at the same bit positions as the
+ * true one.  A sequential (SOF0/SOF1) scan without restart markers is therefore decoded in
+ * three steps:
+ *   1. the segment is cut into chunks; each thread PARSES its chunk from the first byte as if an
+ *      MCU started there (codes only, no coefficients stored) and notes the bit position of
+ *      every MCU it believes to start;
+ *   2. one thread walks the chunks in order: from the true end of chunk k it parses on until
+ *      its MCU start coincides with one noted by the thread of a later chunk - same bit
+ *      position, same decoder state (start of an MCU; DC predictors do not influence parsing),
+ *      so from there on that thread's notes are the truth, and the MCU number of that point is
+ *      known;
+ *   3. each thread decodes for real, from one synchronization point to the next, into the
+ *      coefficient arrays (MCU numbers are known now), with DC predictors starting at 0; the
+ *      DC values of a range are then shifted by the predictors the ranges before it end with.
+ * With restart markers (DRI) the intervals are independent by definition: step 3 alone, one
+ * range per interval, nothing to guess.
+ * Anything unexpected (a marker inside the data, positions that do not line up, too few bits,
+ * restart markers missing or out of sequence) abandons the attempt: the arrays of the scan are
+ * cleared and the plain decoder runs, so damaged files behave as before.  A chunk that never
+ * synchronizes is simply decoded by its predecessor.  Results are identical to the one-thread
+ * decoder by construction (step 3 runs the same block decoder on the same bits); tests/test_cli.py
+ * compares the files on every flavour and thread count. */
+#define PAR_MIN_BYTES (128 << 10)        /* shorter segments are not worth the threads (JPEGQS_PAR_MIN_BYTES: test knob) */
+#define PAR_MIN_THREADS 4                /* steps 1 + 3 read the data twice: two threads would be slower than one */
+#define PAR_MAX_CHUNKS 64
+
+typedef struct { const jq_dhuff *dc, *ac; int k, h, v, hs, vs; } jq_mcu_blk;    /* scan component k, block (h, v) of the MCU */
+
+typedef struct {
+	const unsigned char *p, *end;        /* raw bytes of the range */
+	int skip_bits;                       /* bits of the first byte that belong to the MCU before */
+	uint64_t fed0;                       /* data-byte index of p (bit positions are 8 * fed - nbits) */
+	uint64_t m0, m1;                     /* MCUs [m0, m1) */
+	uint64_t end_pos;                    /* bit position the range must end at (0: not checked) */
+	int endpred[MAX_COMPONENTS], warn;
+} jq_range;
+
+typedef struct {
+	jq_dec *d; const jq_scan *s;
+	const unsigned char *seg, *segend;               /* entropy-coded bytes, up to the next marker */
+	jq_mcu_blk blk[MAX_COMPONENTS * 16]; int nblk;   /* the blocks of one MCU */
+	JDIMENSION nx; uint64_t nmcu;
+	int nchunk;
+	const unsigned char *cstart[PAR_MAX_CHUNKS + 1]; /* raw chunk starts (cstart[nchunk] = segend) */
+	uint64_t cbase[PAR_MAX_CHUNKS + 1];              /* data-byte index of each chunk start */
+	uint64_t *pos[PAR_MAX_CHUNKS]; size_t npos[PAR_MAX_CHUNKS];   /* step 1: MCU start bit positions */
+	jq_range *range; int nrange;
+	int carry[MAX_COMPONENTS];                       /* used per range in the DC shift */
+	int phase;                                       /* what the workers do: 1 parse, 3 decode, 4 shift DC */
+	uint64_t stitched;                               /* MCUs the stitching thread had to parse itself */
+	volatile int next, fail;
+} jq_par;
+
+static inline uint64_t par_pos(const jq_bits *b) { return 8 * b->fed - (unsigned)b->nbits; }
+
+/* parses one block without storing anything (same table walk as dec_block_seq) */
+static inline void skip_block(jq_bits *b, const jq_dhuff *dc, const jq_dhuff *h) {
+	uint64_t buf; int nbits, i, t;
+	t = huff_decode(b, dc);
+	bits_get(b, t & 15);
+	buf = b->buf; nbits = b->nbits;
+	for (i = 1; i < 64; ) {
+		unsigned look, e; int rs, r, sz, f;
+		if (nbits < 32) { b->buf = buf; b->nbits = nbits; bits_fill(b); buf = b->buf; nbits = b->nbits; }
+		look = (unsigned)(buf >> (nbits - 16)) & 0xFFFF;
+		f = h->fast[look >> (16 - FAST_BITS)];
+		if (f) { i += ((f >> 4) & 15) + 1; nbits -= f & 15; continue; }
+		e = h->look[look >> 7];
+		if (e) { nbits -= (int)(e >> 8); rs = (int)(e & 255); }
+		else { b->buf = buf; b->nbits = nbits; rs = huff_decode(b, h); nbits = b->nbits; }
+		r = rs >> 4; sz = rs & 15;
+		if (!sz) { if (r != 15) break; i += 16; continue; }
+		i += r + 1; nbits -= sz;
+	}
+	b->buf = buf; b->nbits = nbits;
+}
+static inline void skip_mcu(const jq_par *q, jq_bits *b) {
+	int k;
+	for (k = 0; k < q->nblk; k++) skip_block(b, q->blk[k].dc, q->blk[k].ac);
+}
+
+/* a reader at bit position pos, reached from the start of chunk c (which must not lie behind it) */
+static int par_reader_at(const jq_par *q, int c, uint64_t pos, jq_bits *b, const unsigned char **raw) {
+	const unsigned char *p = q->cstart[c]; uint64_t idx = q->cbase[c], want = pos >> 3;
+	if (want < idx) return -1;
+	while (idx < want) {                                /* an FF00 pair is one data byte */
+		if (p >= q->segend) return -1;
+		p += p[0] == 0xFF ? 2 : 1; idx++;
+	}
+	if (raw) *raw = p;
+	if (b) {
+		memset(b, 0, sizeof(*b));
+		b->p = p; b->end = q->segend; b->fed = idx;
+		if (pos & 7) bits_get(b, (int)(pos & 7));
+	}
+	return 0;
+}
+
+/* step 1 */
+static void par_parse_chunk(jq_par *q, int c) {
+	jq_bits b; size_t cap = 4096, n = 0; uint64_t *v = (uint64_t*)malloc(cap * sizeof(*v)), limit = 8 * q->cbase[c + 1];
+	memset(&b, 0, sizeof(b)); b.p = q->cstart[c]; b.end = q->segend; b.fed = q->cbase[c];
+	while (v) {
+		uint64_t pos = par_pos(&b);
+		if (n == cap) { uint64_t *w = (uint64_t*)realloc(v, (cap *= 2) * sizeof(*v)); if (!w) { free(v); v = NULL; break; } v = w; }
+		v[n++] = pos;                                   /* the last entry: first MCU start at or beyond the chunk end */
+		if (pos >= limit) break;
+		skip_mcu(q, &b);
+	}
+	if (!v) { q->fail = 1; n = 0; }
+	q->pos[c] = v; q->npos[c] = n;
+}
+
+/* step 2: fills q->range; returns 0, or -1 if the data does not hold nmcu MCUs */
+static int par_stitch(jq_par *q) {
+	uint64_t endbits = 8 * q->cbase[q->nchunk], m = 0;
+	int cur = 0; size_t idx = 0; jq_range *r;
+	q->nrange = 0;
+	r = &q->range[q->nrange++];
+	memset(r, 0, sizeof(*r)); r->p = q->seg; r->end = q->segend; r->m0 = 0;
+	for (;;) {
+		/* the notes of chunk `cur` are true from entry idx (= MCU m) to the last one */
+		uint64_t E, mE; jq_bits b; int j; size_t pj;
+		if (!q->npos[cur]) return -1;
+		E = q->pos[cur][q->npos[cur] - 1]; mE = m + (uint64_t)(q->npos[cur] - 1 - idx);
+		if (mE >= q->nmcu) break;                       /* the image ends inside this chunk */
+		if (E > endbits) return -1;
+		for (j = cur + 1; j < q->nchunk && E >= 8 * q->cbase[j + 1]; j++);
+		if (j >= q->nchunk) return -1;                  /* MCUs are missing and no data is left */
+		if (par_reader_at(q, j, E, &b, NULL)) return -1;
+		m = mE; pj = 0;
+		for (;;) {
+			uint64_t P = par_pos(&b);
+			if (P > endbits) return -1;
+			while (j + 1 < q->nchunk && P >= 8 * q->cbase[j + 1]) { j++; pj = 0; }
+			while (pj < q->npos[j] && q->pos[j][pj] < P) pj++;
+			if (pj < q->npos[j] && q->pos[j][pj] == P) break;           /* synchronized with chunk j */
+			if (m >= q->nmcu) break;
+			skip_mcu(q, &b); m++; q->stitched++;
+		}
+		if (m >= q->nmcu) break;                        /* this one thread parsed to the end of the image */
+		{                                               /* a new range starts at chunk j's entry pj = MCU m */
+			uint64_t P = q->pos[j][pj]; const unsigned char *raw;
+			if (par_reader_at(q, j, P, NULL, &raw)) return -1;
+			r->m1 = m; r->end_pos = P;
+			r = &q->range[q->nrange++];
+			memset(r, 0, sizeof(*r));
+			r->p = raw; r->end = q->segend; r->skip_bits = (int)(P & 7); r->fed0 = P >> 3; r->m0 = m;
+			cur = j; idx = pj;
+		}
+	}
+	r->m1 = q->nmcu;
+	return 0;
+}
+
+static inline JCOEFPTR par_block(const jq_par *q, const jq_mcu_blk *mb, JDIMENSION x, JDIMENSION y) {
+	return q->d->im->coef_arrays[q->s->ci[mb->k]]->rows[y * (JDIMENSION)mb->vs + (JDIMENSION)mb->v][x * (JDIMENSION)mb->hs + (JDIMENSION)mb->h];
+}
+
+/* step 3 */
+static void par_decode_range(jq_par *q, jq_range *r) {
+	jq_dec *ld = (jq_dec*)malloc(sizeof(*ld)); jq_bits b; uint64_t m; int k;
+	if (!ld) { q->fail = 1; return; }
+	memcpy(ld, q->d, sizeof(*ld));
+	memset(ld->pred, 0, sizeof(ld->pred));
+	memset(&b, 0, sizeof(b)); b.p = r->p; b.end = r->end; b.fed = r->fed0;
+	if (r->skip_bits) bits_get(&b, r->skip_bits);
+	for (m = r->m0; m < r->m1; m++) {
+		JDIMENSION y = (JDIMENSION)(m / q->nx), x = (JDIMENSION)(m % q->nx);
+		for (k = 0; k < q->nblk; k++) dec_block_seq(ld, &b, q->s, q->blk[k].k, par_block(q, &q->blk[k], x, y));
+	}
+	if (r->end_pos && par_pos(&b) != r->end_pos) q->fail = 1;
+	memcpy(r->endpred, ld->pred, sizeof(r->endpred));
+	r->warn = b.warn;
+	free(ld);
+}
+
+/* DC values of a range + the predictors at its start (only ranges after the first need it) */
+static void par_shift_dc(jq_par *q, jq_range *r, const int *carry) {
+	uint64_t m; int k, any = 0;
+	for (k = 0; k < MAX_COMPONENTS; k++) any |= carry[k];
+	if (!any) return;
+	for (m = r->m0; m < r->m1; m++) {
+		JDIMENSION y = (JDIMENSION)(m / q->nx), x = (JDIMENSION)(m % q->nx);
+		for (k = 0; k < q->nblk; k++) {
+			JCOEFPTR blk = par_block(q, &q->blk[k], x, y);
+			blk[0] = (JCOEF)(blk[0] + carry[q->s->ci[q->blk[k].k]]);
+		}
+	}
+}
+
+static void *par_worker(void *arg) {
+	jq_par *q = (jq_par*)arg;
+	for (;;) {
+		int i = __sync_fetch_and_add(&q->next, 1);
+		if (q->phase == 1) { if (i >= q->nchunk) break; par_parse_chunk(q, i); }
+		else if (q->phase == 3) { if (i >= q->nrange) break; par_decode_range(q, &q->range[i]); }
+		else {
+			if (i >= q->nrange) break;
+			/* carry of range i = sum of the end predictors of the ranges before it (prefix kept in range[].endpred after step 3b) */
+			par_shift_dc(q, &q->range[i], q->range[i].endpred);
+		}
+	}
+	return NULL;
+}
+static void par_run(jq_par *q, int phase, int nthr) {
+	pthread_t tid[64]; int i, started = 0;
+	q->phase = phase; q->next = 0;
+	for (i = 1; i < nthr && i < 64; i++) { if (pthread_create(&tid[started], NULL, par_worker, q)) break; started++; }
+	par_worker(q);
+	for (i = 0; i < started; i++) pthread_join(tid[i], NULL);
+}
+
+/* 1 = the scan was decoded here (*next set), 0 = not applicable / abandoned (arrays of the scan cleared
+ * again): the caller runs the plain decoder */
+static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p, const unsigned char *end,
+		const unsigned char **next) {
+	jq_image *im = d->im; jq_par *q; int nthr = codec_thread_count(), k, h, v, ri = im->restart_interval, ok = 0, i;
+	const unsigned char *t, *segend = NULL; uint64_t stuffed = 0; size_t len, min_bytes = PAR_MIN_BYTES, chunk_min;
+	const char *env = getenv("JPEGQS_PAR_MIN_BYTES");
+	JDIMENSION ny;
+	if (env && atoi(env) > 0) min_bytes = (size_t)atoi(env);
+	chunk_min = min_bytes / 4 < 64 ? 64 : min_bytes / 4;
+	if (im->progressive || nthr < PAR_MIN_THREADS || (size_t)(end - p) < min_bytes || getenv("JPEGQS_SERIAL_DECODE")) return 0;
+	q = (jq_par*)calloc(1, sizeof(*q));
+	if (!q) return 0;
+	q->d = d; q->s = s; q->seg = p;
+	/* the blocks of an MCU (A.2.3; a one-component scan is not interleaved: MCU = one block) */
+	if (s->ncomp == 1) {
+		jpeg_component_info *c = &im->cinfo.comp_info[s->ci[0]];
+		q->nx = c->width_in_blocks; ny = c->height_in_blocks;
+		q->blk[0].dc = &d->dc[s->td[0]]; q->blk[0].ac = &d->ac[s->ta[0]]; q->blk[0].hs = q->blk[0].vs = 1;
+		q->nblk = 1;
+	} else {
+		q->nx = d->mcux; ny = d->mcuy;
+		for (k = 0; k < s->ncomp; k++) {
+			jpeg_component_info *c = &im->cinfo.comp_info[s->ci[k]];
+			for (v = 0; v < c->v_samp_factor; v++) for (h = 0; h < c->h_samp_factor; h++) {
+				jq_mcu_blk *mb;
+				if (q->nblk >= (int)(sizeof(q->blk) / sizeof(q->blk[0]))) goto out;
+				mb = &q->blk[q->nblk++];
+				mb->dc = &d->dc[s->td[k]]; mb->ac = &d->ac[s->ta[k]]; mb->k = k; mb->h = h; mb->v = v;
+				mb->hs = c->h_samp_factor; mb->vs = c->v_samp_factor;
+			}
+		}
+	}
+	q->nmcu = (uint64_t)q->nx * ny;
+	if (!q->nmcu) goto out;
+
+	if (ri) {
+		/* restart intervals: ceil(nmcu / ri) - 1 markers RST0, RST1, ... RST7, RST0 ... and nothing else */
+		uint64_t nint = (q->nmcu + (unsigned)ri - 1) / (unsigned)ri, j = 0;
+		if (nint > (1u << 24)) goto out;
+		q->range = (jq_range*)calloc((size_t)nint, sizeof(jq_range));
+		if (!q->range) goto out;
+		q->range[0].p = p;
+		for (t = p; (t = (const unsigned char*)memchr(t, 0xFF, (size_t)(end - t))) != NULL; ) {
+			if (t + 1 >= end) { segend = t; break; }
+			if (t[1] == 0) { t += 2; continue; }
+			if ((t[1] & 0xF8) == 0xD0) {
+				if (j + 1 >= nint || (unsigned)(t[1] & 7) != (unsigned)(j & 7)) goto out;
+				q->range[j].end = t; j++; q->range[j].p = t + 2;
+				t += 2; continue;
+			}
+			segend = t; break;
+		}
+		if (!segend || j + 1 != nint || segend[0] != 0xFF || (segend + 1 < end && segend[1] == 0xFF)) goto out;
+		q->range[j].end = segend;
+		for (j = 0; j < nint; j++) {
+			q->range[j].m0 = j * (unsigned)ri;
+			q->range[j].m1 = (j + 1) * (unsigned)ri < q->nmcu ? (j + 1) * (unsigned)ri : q->nmcu;
+		}
+		q->nrange = (int)nint; q->segend = segend;
+		par_run(q, 3, nthr);
+		if (q->fail) goto clear;
+		for (i = 0; i < q->nrange; i++) im->warnings += q->range[i].warn;
+		if (getenv("JPEGQS_CODEC_TRACE"))
+			fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d restart intervals\n", nthr, q->nrange);
+		*next = segend; ok = 1;
+		goto out;
+	}
+
+	/* the segment ends at the first FF that is not followed by 00; it must be a real marker */
+	for (t = p; (t = (const unsigned char*)memchr(t, 0xFF, (size_t)(end - t))) != NULL; ) {
+		if (t + 1 < end && t[1] == 0) { t += 2; continue; }
+		segend = t; break;
+	}
+	if (!segend || segend + 1 >= end || segend[1] == 0xFF || (segend[1] & 0xF8) == 0xD0) goto out;
+	len = (size_t)(segend - p);
+	if (len < min_bytes) goto out;
+	q->segend = segend;
+	q->nchunk = nthr * 2 < PAR_MAX_CHUNKS ? nthr * 2 : PAR_MAX_CHUNKS;
+	if ((size_t)q->nchunk > len / chunk_min) q->nchunk = (int)(len / chunk_min);
+	if (q->nchunk < 2) goto out;
+	/* chunk starts: never between the FF and the 00 of a stuffed byte; data-byte index of each */
+	t = p;
+	for (i = 0; i < q->nchunk; i++) {
+		const unsigned char *c = p + (size_t)((uint64_t)len * (unsigned)i / (unsigned)q->nchunk);
+		if (c < t) c = t;
+		while (c > p && c < segend && c[-1] == 0xFF) c++;
+		for (; t < c; ) {                               /* stuffed bytes before c */
+			const unsigned char *f = (const unsigned char*)memchr(t, 0xFF, (size_t)(c - t));
+			if (!f) break;
+			stuffed++; t = f + 2;                       /* inside the segment every FF is followed by 00 */
+		}
+		if (t < c) t = c;
+		q->cstart[i] = c; q->cbase[i] = (uint64_t)(c - p) - stuffed;
+	}
+	for (; t < segend; ) {
+		const unsigned char *f = (const unsigned char*)memchr(t, 0xFF, (size_t)(segend - t));
+		if (!f) break;
+		stuffed++; t = f + 2;
+	}
+	q->cstart[q->nchunk] = segend; q->cbase[q->nchunk] = (uint64_t)len - stuffed;
+	for (i = 0; i < q->nchunk; i++) if (q->cbase[i + 1] <= q->cbase[i]) goto out;
+
+	q->range = (jq_range*)calloc((size_t)q->nchunk + 1, sizeof(jq_range));
+	if (!q->range) goto out;
+	par_run(q, 1, nthr);
+	if (q->fail || par_stitch(q)) goto out;             /* nothing was written to the arrays yet */
+	par_run(q, 3, nthr);
+	if (q->fail) goto clear;
+	{                                                   /* DC predictors at the start of each range */
+		int carry[MAX_COMPONENTS] = { 0 }, endp[MAX_COMPONENTS];
+		for (i = 0; i < q->nrange; i++) {
+			im->warnings += q->range[i].warn;
+			memcpy(endp, q->range[i].endpred, sizeof(endp));
+			memcpy(q->range[i].endpred, carry, sizeof(carry));       /* from here on: the range's carry-in */
+			for (k = 0; k < MAX_COMPONENTS; k++) carry[k] += endp[k];
+		}
+		par_run(q, 4, nthr);
+	}
+	if (getenv("JPEGQS_CODEC_TRACE"))
+		fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d chunks, %d ranges, %llu of %llu MCUs parsed while stitching\n",
+				nthr, q->nchunk, q->nrange, (unsigned long long)q->stitched, (unsigned long long)q->nmcu);
+	*next = segend; ok = 1;
+	goto out;
+clear:
+	if (getenv("JPEGQS_CODEC_TRACE")) fprintf(stderr, "jpegcoef: threaded decode abandoned, decoding again on one thread\n");
+	for (k = 0; k < s->ncomp; k++) {
+		jvirt_barray_ptr a = im->coef_arrays[s->ci[k]];
+		memset(a->data, 0, (size_t)a->w * a->h * sizeof(JBLOCK));
+	}
+out:
+	for (i = 0; i < PAR_MAX_CHUNKS; i++) free(q->pos[i]);
+	free(q->range); free(q);
+	return ok;
+}
+
+
 static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const unsigned char *end,
 		const unsigned char **next, char *err) {
 	jq_image *im = d->im; jq_bits b; int prog = im->progressive, k, ri = im->restart_interval;
@@ -289,6 +644,7 @@ static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const u
 			snprintf(err, 256, "scan uses an undefined Huffman table"); return -1;
 		}
 	}
+	if (dec_scan_parallel(d, s, p, end, next)) return 0;
 	if (s->ncomp == 1) {
 		jpeg_component_info *c = &im->cinfo.comp_info[s->ci[0]];
 		nx = c->width_in_blocks; ny = c->height_in_blocks;
@@ -752,12 +1108,16 @@ static void *enc_worker(void *arg) {
 	return NULL;
 }
 
-static int enc_thread_count(JDIMENSION mcuy) {
+static int codec_thread_count(void) {
 	int n = jq_threads_wanted;
 	const char *env = getenv("JPEGQS_CODEC_THREADS");
 	if (env && atoi(env) > 0) n = atoi(env);
 	if (n <= 0) { long c = sysconf(_SC_NPROCESSORS_ONLN); n = c > 0 ? (int)c : 1; if (n > 16) n = 16; }
 	if (n > 64) n = 64;
+	return n < 1 ? 1 : n;
+}
+static int enc_thread_count(JDIMENSION mcuy) {
+	int n = codec_thread_count();
 	if ((JDIMENSION)n > mcuy) n = (int)mcuy;
 	return n < 1 ? 1 : n;
 }

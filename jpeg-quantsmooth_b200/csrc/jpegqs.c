@@ -5,8 +5,8 @@
  *   jpegqs [options] input.jpg output.jpg        ("-" = stdin / stdout)
  *     -q, --quality n    0..6, default 3 (mapped to flags exactly like quantsmooth.c:380-393)
  *     -n, --niter n      number of iterations (default 3)
- *     -t, --threads n    worker threads of the JPEG writer's entropy coder (the reference: OpenMP
- *                        threads of the smoothing loop, which runs on the GPU here)
+ *     -t, --threads n    worker threads of the JPEG reader's and writer's entropy coding (the
+ *                        reference: OpenMP threads of the smoothing loop, which runs on the GPU here)
  *     -o, --optimize     optimal Huffman tables in the output
  *     -v, --verbose n    codec diagnostics
  *     -i, --info n       info bit mask (JPEGQS_INFO_*), default 15
@@ -62,7 +62,7 @@ static int usage(const char *prog) {
 		"Usage:\n  %s [options] input.jpg output.jpg\n\nOptions:\n"
 		"  -q, --quality n   Quality setting (0-6, default is 3)\n"
 		"  -n, --niter n     Number of iterations (default is 3)\n"
-		"  -t, --threads n   Worker threads of the JPEG writer (the reference: OpenMP threads)\n"
+		"  -t, --threads n   Worker threads of the JPEG reader and writer (the reference: OpenMP threads)\n"
 		"  -o, --optimize    Optimize Huffman table\n"
 		"  -v, --verbose n   Print codec debug messages\n"
 		"  -i, --info n      Print quantsmooth debug messages (default is 15)\n"

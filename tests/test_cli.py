@@ -114,6 +114,47 @@ def test_writer_bytes_do_not_depend_on_the_thread_count(jpegs, tmp_path):
             assert open(out, "rb").read() == want
 
 
+def _big_picture(w, h, seed, **kw):
+    rng = np.random.RandomState(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    a = np.stack([128 + 70 * np.sin(x / 31.0) + 40 * np.cos(y / 19.0), 128 + 60 * np.cos((x + y) / 47.0),
+                  128 + 80 * np.sin((x - y) / 23.0)], -1) + rng.normal(0, 9, (h, w, 3))
+    return PIL.fromarray(a.clip(0, 255).astype(np.uint8), "RGB")
+
+
+@pytest.mark.parametrize("name", ["base420", "base444", "gray", "opt422", "rst", "dense444", "coarse420", "big420", "big444rst",
+                                  "biggray", "big422opt"])
+def test_threaded_decoder_equals_the_serial_one(jpegs, tmp_path, name):
+    """Sequential scans are decoded on several threads (speculative parsing of chunks, stitched at
+    the points where they synchronize; restart intervals as they are).  The result must be the
+    one-thread decoder's for every chunk and thread count; the trace says which path ran."""
+    big = {"big420": (1400, 900, dict(quality=85)), "big444rst": (900, 700, dict(quality=92, subsampling=0, restart_marker_rows=2)),
+           "biggray": (1100, 800, dict(quality=70)), "big422opt": (1000, 640, dict(quality=60, subsampling=1, optimize=True))}
+    if name in big:
+        w, h, kw = big[name]
+        src = str(tmp_path / (name + ".jpg"))
+        im = _big_picture(w, h, len(name))
+        (im.convert("L") if name == "biggray" else im).save(src, **kw)
+    else:
+        src = jpegs[name]
+    ref = str(tmp_path / "serial.jpg")
+    env = dict(os.environ, JPEGQS_SERIAL_DECODE="1")
+    assert subprocess.run([EXE, "-n", "0", "-i", "0", src, ref], env=env).returncode == 0
+    want = open(ref, "rb").read()
+    for threads, min_bytes in (("4", "300"), ("7", "300"), ("16", "2000"), ("5", None)):
+        out = str(tmp_path / f"t{threads}.jpg")
+        env = dict(os.environ, JPEGQS_CODEC_THREADS=threads, JPEGQS_CODEC_TRACE="1")
+        if min_bytes:
+            env["JPEGQS_PAR_MIN_BYTES"] = min_bytes
+        r = subprocess.run([EXE, "-n", "0", "-i", "0", src, out], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out, "rb").read() == want, (name, threads)
+        if name in big and min_bytes:        # (with the default threshold only segments of 128 KB and more take the threaded path)
+            assert "decoded on" in r.stderr and "abandoned" not in r.stderr, r.stderr
+            if "rst" in name:
+                assert "restart intervals" in r.stderr
+
+
 def test_marker_copy_levels(jpegs, tmp_path):
     """-c selects the COPIED markers; the JFIF APP0 is not one of them: libjpeg writes it itself
     for every grayscale / YCbCr output (jcmarker.c write_file_header) with the source's version
@@ -304,7 +345,7 @@ def test_codec_survives_corrupt_input(jpegs, tmp_path):
     if r.returncode:
         pytest.skip("sanitizer build unavailable: " + r.stderr[-200:])
     rng = np.random.RandomState(7)
-    seeds = [open(jpegs[n], "rb").read() for n in ("base420", "prog420", "gray", "rst", "tinyprog")]
+    seeds = [open(jpegs[n], "rb").read() for n in ("base420", "prog420", "gray", "rst", "tinyprog", "base444", "opt422")]
     for it in range(300):
         d = bytearray(seeds[it % len(seeds)])
         mode = rng.randint(4)
@@ -321,6 +362,18 @@ def test_codec_survives_corrupt_input(jpegs, tmp_path):
             d = d[:i] + bytes(rng.randint(0, 256, rng.randint(1, 40)).tolist()) + d[i:]
         f = tmp_path / "f.jpg"
         f.write_bytes(bytes(d))
-        r = subprocess.run([exe, "-n", "0", "-i", "0", str(f), str(tmp_path / "o.jpg")], capture_output=True, timeout=60)
+        out = tmp_path / "o.jpg"
+        if out.exists():
+            out.unlink()
+        env = dict(os.environ, JPEGQS_SERIAL_DECODE="1")
+        r = subprocess.run([exe, "-n", "0", "-i", "0", str(f), str(out)], capture_output=True, timeout=60, env=env)
         # 0 decoded, 1 rejected, 2 decoded with recoverable damage (the reference's warning status)
         assert r.returncode in (0, 1, 2), (it, r.returncode, r.stderr.decode()[-800:])
+        # the threaded decoder (forced onto these small files) must give up or agree: same status, same bytes
+        want = out.read_bytes() if out.exists() else None
+        if out.exists():
+            out.unlink()
+        env = dict(os.environ, JPEGQS_PAR_MIN_BYTES="200", JPEGQS_CODEC_THREADS=str(4 + it % 5))
+        r2 = subprocess.run([exe, "-n", "0", "-i", "0", str(f), str(out)], capture_output=True, timeout=60, env=env)
+        assert r2.returncode == r.returncode, (it, r.returncode, r2.returncode, r2.stderr.decode()[-800:])
+        assert (out.read_bytes() if out.exists() else None) == want, it
