@@ -16,6 +16,9 @@
 #endif
 #include "jpegcoef.h"
 
+#include <time.h>
+static double trace_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
 /* zig-zag index -> natural (row-major) index, T.81 figure A.6 */
 static const unsigned char zz_nat[64 + 16] = {
 	0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
@@ -1157,10 +1160,115 @@ static void out_segment(jq_out *o, const jq_seg *sg) {
 	if (sg->nacc) out_bits(o, (unsigned)sg->acc & ((1u << sg->nacc) - 1), sg->nacc);
 }
 
+/* The splice on the worker threads.  Once every segment is coded its position in the scan's bit
+ * stream is known (S = bits of the segments before it).  Output byte j belongs to the segment that
+ * holds its first bit; that segment's thread shifts its bits into byte phase, takes the few bits the
+ * last byte needs from the next segment, stuffs FF bytes, all into a buffer of its own.  What is
+ * left for one thread is copying those buffers one after the other.  The bits after the last
+ * whole byte of the scan stay pending in the output's accumulator, as out_segment leaves them. */
+typedef struct {
+	jq_seg *seg; int nseg;
+	uint64_t *start;                     /* [nseg + 1] bit position of each segment in the scan */
+	unsigned char **buf; size_t *len;    /* [nseg] stuffed bytes of each segment */
+	volatile int next, fail;
+} jq_splice;
+
+/* bit t (0 = first) .. t+7 of segment i followed by the segments after it; zero beyond the scan */
+static unsigned splice_byte(const jq_splice *sp, int i, uint64_t t) {
+	unsigned v = 0; int got = 0;
+	while (got < 8 && i < sp->nseg) {
+		const jq_seg *sg = &sp->seg[i]; uint64_t L = 8 * (uint64_t)sg->n + (unsigned)sg->nacc;
+		if (t >= L) { t -= L; i++; continue; }
+		{
+			unsigned bit;
+			if (t < 8 * (uint64_t)sg->n) bit = (sg->p[t >> 3] >> (7 - (t & 7))) & 1;
+			else bit = (unsigned)(sg->acc >> (sg->nacc - 1 - (int)(t - 8 * (uint64_t)sg->n))) & 1;
+			v = v << 1 | bit; got++; t++;
+		}
+	}
+	return v << (8 - got);
+}
+
+static void splice_segment(jq_splice *sp, int i) {
+	const jq_seg *sg = &sp->seg[i];
+	uint64_t S = sp->start[i], E = sp->start[i + 1];
+	uint64_t j0 = (S + 7) >> 3, j1 = i + 1 < sp->nseg ? (E + 7) >> 3 : E >> 3;     /* owned bytes [j0, j1) */
+	size_t nout = j1 > j0 ? (size_t)(j1 - j0) : 0, b = 0;
+	unsigned o = (unsigned)(8 * j0 - S);                 /* leading bits that belong to the byte before */
+	unsigned char *w, *dst = (unsigned char*)malloc(2 * nout + 16);
+	if (!dst) { sp->fail = 1; return; }
+	w = dst;
+	/* eight bytes at a time while nine source bytes are there */
+	for (; b + 8 <= nout && b + 9 <= sg->n; b += 8) {
+		uint64_t x, v; int j;
+		memcpy(&x, sg->p + b, 8); x = __builtin_bswap64(x);
+		v = o ? x << o | (uint64_t)(sg->p[b + 8] >> (8 - o)) : x;
+		if (!((~v - 0x0101010101010101ULL) & v & 0x8080808080808080ULL)) {
+			uint64_t be = __builtin_bswap64(v); memcpy(w, &be, 8); w += 8;
+		} else for (j = 56; j >= 0; j -= 8) {
+			unsigned c = (unsigned)(v >> j) & 255;
+			*w++ = (unsigned char)c; if (c == 0xFF) *w++ = 0;
+		}
+	}
+	for (; b < nout; b++) {                              /* the end of the segment, bit by bit */
+		unsigned c = splice_byte(sp, i, 8 * (uint64_t)b + o);
+		*w++ = (unsigned char)c; if (c == 0xFF) *w++ = 0;
+	}
+	sp->buf[i] = dst; sp->len[i] = (size_t)(w - dst);
+}
+static void *splice_worker(void *arg) {
+	jq_splice *sp = (jq_splice*)arg;
+	for (;;) {
+		int i = __sync_fetch_and_add(&sp->next, 1);
+		if (i >= sp->nseg) break;
+		splice_segment(sp, i);
+	}
+	return NULL;
+}
+
+/* 0 = done, -1 = not applicable or out of memory (nothing written: the caller splices serially) */
+static int out_segments_parallel(jq_out *o, jq_seg *seg, int nseg, int nthr) {
+	jq_splice sp; pthread_t tid[64]; int i, started = 0, rc = -1; size_t total = 0; uint64_t bits;
+	if (nseg < 2 || nthr < 2 || o->nacc) return -1;
+	memset(&sp, 0, sizeof(sp));
+	sp.seg = seg; sp.nseg = nseg;
+	sp.start = (uint64_t*)calloc((size_t)nseg + 1, sizeof(uint64_t));
+	sp.buf = (unsigned char**)calloc((size_t)nseg, sizeof(*sp.buf));
+	sp.len = (size_t*)calloc((size_t)nseg, sizeof(size_t));
+	if (!sp.start || !sp.buf || !sp.len) goto out;
+	for (i = 0; i < nseg; i++) {
+		uint64_t L = 8 * (uint64_t)seg[i].n + (unsigned)seg[i].nacc;
+		if (L < 64) goto out;                            /* a byte must not span more than two segments */
+		sp.start[i + 1] = sp.start[i] + L;
+	}
+	for (i = 1; i < nthr && i < 64; i++) { if (pthread_create(&tid[started], NULL, splice_worker, &sp)) break; started++; }
+	splice_worker(&sp);
+	for (i = 0; i < started; i++) pthread_join(tid[i], NULL);
+	if (sp.fail) goto out;
+	for (i = 0; i < nseg; i++) total += sp.len[i];
+	if (o->cap - o->n < total + 16) {
+		size_t nc = o->cap ? o->cap : 1 << 16; unsigned char *q;
+		while (nc < o->n + total + 16) nc *= 2;
+		q = (unsigned char*)realloc(o->p, nc);
+		if (!q) goto out;
+		o->p = q; o->cap = nc;
+	}
+	for (i = 0; i < nseg; i++) { memcpy(o->p + o->n, sp.buf[i], sp.len[i]); o->n += sp.len[i]; }
+	bits = sp.start[nseg] & 7;                           /* after the last whole byte */
+	o->nacc = (int)bits;
+	o->acc = bits ? splice_byte(&sp, nseg - 1, sp.start[nseg] - sp.start[nseg - 1] - bits) >> (8 - bits) : 0;
+	rc = 0;
+out:
+	if (sp.buf) for (i = 0; i < nseg; i++) free(sp.buf[i]);
+	free(sp.start); free(sp.buf); free(sp.len);
+	return rc;
+}
+
 /* counts symbols into dc/ac[].freq (o == NULL) or writes the entropy-coded segment to o */
 static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff *dc, jq_ehuff *ac) {
 	struct jpeg_decompress_struct *ci = &im->cinfo;
 	int maxh = ci->max_h_samp_factor, maxv = ci->max_v_samp_factor, nthr, i, j, k, rc = -1;
+	int trace = getenv("JPEGQS_CODEC_TRACE") != NULL; double t_start = 0, t_coded = 0;
 	jq_enc e; pthread_t tid[64];
 	memset(&e, 0, sizeof(e));
 	e.im = im; e.arrays = arrays;
@@ -1168,6 +1276,7 @@ static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff 
 	if (!e.mcuy || !e.mcux) return 0;
 	for (k = 0; k < ci->num_components; k++) if (ci->comp_info[k].v_samp_factor > 4) return -1;
 	pthread_once(&zz_mask_once, zz_mask_init);
+	t_start = trace ? trace_ms() : 0;
 	nthr = enc_thread_count(e.mcuy);
 	e.nseg = nthr == 1 ? 1 : nthr * 4;
 	if ((JDIMENSION)e.nseg > e.mcuy) e.nseg = (int)e.mcuy;
@@ -1177,10 +1286,15 @@ static int enc_pass(jq_image *im, jvirt_barray_ptr *arrays, jq_out *o, jq_ehuff 
 	nthr = i;                                            /* threads that really started (+ this one) */
 	enc_worker(&e);
 	for (i = 1; i < nthr; i++) pthread_join(tid[i], NULL);
+	t_coded = trace ? trace_ms() : 0;
 	if (!e.range_error) {
 		rc = 0;
 		if (o) {
-			for (i = 0; i < e.nseg; i++) { if (e.seg[i].fail) { o->fail = 1; break; } out_segment(o, &e.seg[i]); }
+			for (i = 0; i < e.nseg; i++) if (e.seg[i].fail) o->fail = 1;
+			if (!o->fail && out_segments_parallel(o, e.seg, e.nseg, nthr))
+				for (i = 0; i < e.nseg; i++) out_segment(o, &e.seg[i]);
+			if (trace) fprintf(stderr, "jpegcoef: scan coded on %d threads in %.1f ms (%d segments), spliced in %.1f ms (%zu bytes)\n",
+					nthr, t_coded - t_start, e.nseg, trace_ms() - t_coded, o->n);
 		} else for (i = 0; i < e.nseg; i++) for (j = 0; j < 257; j++) {
 			dc[0].freq[j] += e.freq[i][0][j]; ac[0].freq[j] += e.freq[i][1][j];
 			dc[1].freq[j] += e.freq[i][2][j]; ac[1].freq[j] += e.freq[i][3][j];
