@@ -297,8 +297,9 @@ static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEF
  *      so from there on that thread's notes are the truth, and the MCU number of that point is
  *      known;
  *   3. each thread decodes for real, from one synchronization point to the next, into the
- *      coefficient arrays (MCU numbers are known now), with DC predictors starting at 0; the
- *      DC values of a range are then shifted by the predictors the ranges before it end with.
+ *      coefficient arrays: the MCU numbers are known now, and so are the DC predictors (steps 1
+ *      and 2 add up the DC differences they pass; the sums are checked against what step 3
+ *      arrives at).
  * With restart markers (DRI) the intervals are independent by definition: step 3 alone, one
  * range per interval, nothing to guess.
  * Anything unexpected (a marker inside the data, positions that do not line up, too few bits,
@@ -319,7 +320,8 @@ typedef struct {
 	uint64_t fed0;                       /* data-byte index of p (bit positions are 8 * fed - nbits) */
 	uint64_t m0, m1;                     /* MCUs [m0, m1) */
 	uint64_t end_pos;                    /* bit position the range must end at (0: not checked) */
-	int endpred[MAX_COMPONENTS], warn;
+	int pred0[4];                        /* DC predictors of the scan's components at m0 */
+	int endpred[4], check_pred, warn;    /* ... and at m1 (must be the next range's pred0 if check_pred) */
 } jq_range;
 
 typedef struct {
@@ -330,10 +332,10 @@ typedef struct {
 	int nchunk;
 	const unsigned char *cstart[PAR_MAX_CHUNKS + 1]; /* raw chunk starts (cstart[nchunk] = segend) */
 	uint64_t cbase[PAR_MAX_CHUNKS + 1];              /* data-byte index of each chunk start */
-	uint64_t *pos[PAR_MAX_CHUNKS]; size_t npos[PAR_MAX_CHUNKS];   /* step 1: MCU start bit positions */
+	uint64_t *pos[PAR_MAX_CHUNKS]; size_t npos[PAR_MAX_CHUNKS];   /* step 1: MCU start bit positions ... */
+	int32_t *dcs[PAR_MAX_CHUNKS];                    /* ... and the sums of the DC differences up to each (4 per entry) */
 	jq_range *range; int nrange;
-	int carry[MAX_COMPONENTS];                       /* used per range in the DC shift */
-	int phase;                                       /* what the workers do: 1 parse, 3 decode, 4 shift DC */
+	int phase;                                       /* what the workers do: 1 parse, 3 decode */
 	uint64_t stitched;                               /* MCUs the stitching thread had to parse itself */
 	volatile int next, fail;
 } jq_par;
@@ -341,10 +343,10 @@ typedef struct {
 static inline uint64_t par_pos(const jq_bits *b) { return 8 * b->fed - (unsigned)b->nbits; }
 
 /* parses one block without storing anything (same table walk as dec_block_seq) */
-static inline void skip_block(jq_bits *b, const jq_dhuff *dc, const jq_dhuff *h) {
-	uint64_t buf; int nbits, i, t;
+static inline int skip_block(jq_bits *b, const jq_dhuff *dc, const jq_dhuff *h) {
+	uint64_t buf; int nbits, i, t, diff;
 	t = huff_decode(b, dc);
-	bits_get(b, t & 15);
+	diff = extend(bits_get(b, t & 15), t & 15);
 	buf = b->buf; nbits = b->nbits;
 	for (i = 1; i < 64; ) {
 		unsigned look, e; int rs, r, sz, f;
@@ -360,10 +362,12 @@ static inline void skip_block(jq_bits *b, const jq_dhuff *dc, const jq_dhuff *h)
 		i += r + 1; nbits -= sz;
 	}
 	b->buf = buf; b->nbits = nbits;
+	return diff;
 }
-static inline void skip_mcu(const jq_par *q, jq_bits *b) {
+/* parses one MCU; dc[k] += the DC differences of the scan's component k */
+static inline void skip_mcu(const jq_par *q, jq_bits *b, int32_t *dc) {
 	int k;
-	for (k = 0; k < q->nblk; k++) skip_block(b, q->blk[k].dc, q->blk[k].ac);
+	for (k = 0; k < q->nblk; k++) dc[q->blk[k].k] += skip_block(b, q->blk[k].dc, q->blk[k].ac);
 }
 
 /* a reader at bit position pos, reached from the start of chunk c (which must not lie behind it) */
@@ -386,31 +390,42 @@ static int par_reader_at(const jq_par *q, int c, uint64_t pos, jq_bits *b, const
 /* step 1 */
 static void par_parse_chunk(jq_par *q, int c) {
 	jq_bits b; size_t cap = 4096, n = 0; uint64_t *v = (uint64_t*)malloc(cap * sizeof(*v)), limit = 8 * q->cbase[c + 1];
+	int32_t *s = (int32_t*)malloc(cap * 4 * sizeof(*s)), cum[4] = { 0, 0, 0, 0 };
 	memset(&b, 0, sizeof(b)); b.p = q->cstart[c]; b.end = q->segend; b.fed = q->cbase[c];
-	while (v) {
+	while (v && s) {
 		uint64_t pos = par_pos(&b);
-		if (n == cap) { uint64_t *w = (uint64_t*)realloc(v, (cap *= 2) * sizeof(*v)); if (!w) { free(v); v = NULL; break; } v = w; }
+		if (n == cap) {
+			uint64_t *w = (uint64_t*)realloc(v, 2 * cap * sizeof(*v)); int32_t *t;
+			if (!w) { free(v); v = NULL; break; }
+			v = w;
+			t = (int32_t*)realloc(s, 2 * cap * 4 * sizeof(*s));
+			if (!t) { free(s); s = NULL; break; }
+			s = t; cap *= 2;
+		}
+		memcpy(s + 4 * n, cum, sizeof(cum));
 		v[n++] = pos;                                   /* the last entry: first MCU start at or beyond the chunk end */
 		if (pos >= limit) break;
-		skip_mcu(q, &b);
+		skip_mcu(q, &b, cum);
 	}
-	if (!v) { q->fail = 1; n = 0; }
-	q->pos[c] = v; q->npos[c] = n;
+	if (!v || !s) { free(v); free(s); v = NULL; s = NULL; q->fail = 1; n = 0; }
+	q->pos[c] = v; q->dcs[c] = s; q->npos[c] = n;
 }
 
 /* step 2: fills q->range; returns 0, or -1 if the data does not hold nmcu MCUs */
 static int par_stitch(jq_par *q) {
 	uint64_t endbits = 8 * q->cbase[q->nchunk], m = 0;
-	int cur = 0; size_t idx = 0; jq_range *r;
+	int cur = 0, k; size_t idx = 0; jq_range *r; int32_t pred[4] = { 0, 0, 0, 0 };      /* DC predictors at MCU m */
 	q->nrange = 0;
 	r = &q->range[q->nrange++];
 	memset(r, 0, sizeof(*r)); r->p = q->seg; r->end = q->segend; r->m0 = 0;
 	for (;;) {
 		/* the notes of chunk `cur` are true from entry idx (= MCU m) to the last one */
-		uint64_t E, mE; jq_bits b; int j; size_t pj;
+		uint64_t E, mE; jq_bits b; int j; size_t pj, last;
 		if (!q->npos[cur]) return -1;
-		E = q->pos[cur][q->npos[cur] - 1]; mE = m + (uint64_t)(q->npos[cur] - 1 - idx);
+		last = q->npos[cur] - 1;
+		E = q->pos[cur][last]; mE = m + (uint64_t)(last - idx);
 		if (mE >= q->nmcu) break;                       /* the image ends inside this chunk */
+		for (k = 0; k < 4; k++) pred[k] += q->dcs[cur][4 * last + k] - q->dcs[cur][4 * idx + k];
 		if (E > endbits) return -1;
 		for (j = cur + 1; j < q->nchunk && E >= 8 * q->cbase[j + 1]; j++);
 		if (j >= q->nchunk) return -1;                  /* MCUs are missing and no data is left */
@@ -423,16 +438,17 @@ static int par_stitch(jq_par *q) {
 			while (pj < q->npos[j] && q->pos[j][pj] < P) pj++;
 			if (pj < q->npos[j] && q->pos[j][pj] == P) break;           /* synchronized with chunk j */
 			if (m >= q->nmcu) break;
-			skip_mcu(q, &b); m++; q->stitched++;
+			skip_mcu(q, &b, pred); m++; q->stitched++;
 		}
 		if (m >= q->nmcu) break;                        /* this one thread parsed to the end of the image */
 		{                                               /* a new range starts at chunk j's entry pj = MCU m */
 			uint64_t P = q->pos[j][pj]; const unsigned char *raw;
 			if (par_reader_at(q, j, P, NULL, &raw)) return -1;
-			r->m1 = m; r->end_pos = P;
+			r->m1 = m; r->end_pos = P; r->check_pred = 1;
 			r = &q->range[q->nrange++];
 			memset(r, 0, sizeof(*r));
 			r->p = raw; r->end = q->segend; r->skip_bits = (int)(P & 7); r->fed0 = P >> 3; r->m0 = m;
+			for (k = 0; k < 4; k++) r->pred0[k] = pred[k];
 			cur = j; idx = pj;
 		}
 	}
@@ -450,6 +466,7 @@ static void par_decode_range(jq_par *q, jq_range *r) {
 	if (!ld) { q->fail = 1; return; }
 	memcpy(ld, q->d, sizeof(*ld));
 	memset(ld->pred, 0, sizeof(ld->pred));
+	for (k = 0; k < q->s->ncomp; k++) ld->pred[q->s->ci[k]] = r->pred0[k];
 	memset(&b, 0, sizeof(b)); b.p = r->p; b.end = r->end; b.fed = r->fed0;
 	if (r->skip_bits) bits_get(&b, r->skip_bits);
 	for (m = r->m0; m < r->m1; m++) {
@@ -457,23 +474,9 @@ static void par_decode_range(jq_par *q, jq_range *r) {
 		for (k = 0; k < q->nblk; k++) dec_block_seq(ld, &b, q->s, q->blk[k].k, par_block(q, &q->blk[k], x, y));
 	}
 	if (r->end_pos && par_pos(&b) != r->end_pos) q->fail = 1;
-	memcpy(r->endpred, ld->pred, sizeof(r->endpred));
+	for (k = 0; k < q->s->ncomp; k++) r->endpred[k] = ld->pred[q->s->ci[k]];
 	r->warn = b.warn;
 	free(ld);
-}
-
-/* DC values of a range + the predictors at its start (only ranges after the first need it) */
-static void par_shift_dc(jq_par *q, jq_range *r, const int *carry) {
-	uint64_t m; int k, any = 0;
-	for (k = 0; k < MAX_COMPONENTS; k++) any |= carry[k];
-	if (!any) return;
-	for (m = r->m0; m < r->m1; m++) {
-		JDIMENSION y = (JDIMENSION)(m / q->nx), x = (JDIMENSION)(m % q->nx);
-		for (k = 0; k < q->nblk; k++) {
-			JCOEFPTR blk = par_block(q, &q->blk[k], x, y);
-			blk[0] = (JCOEF)(blk[0] + carry[q->s->ci[q->blk[k].k]]);
-		}
-	}
 }
 
 static void *par_worker(void *arg) {
@@ -481,12 +484,7 @@ static void *par_worker(void *arg) {
 	for (;;) {
 		int i = __sync_fetch_and_add(&q->next, 1);
 		if (q->phase == 1) { if (i >= q->nchunk) break; par_parse_chunk(q, i); }
-		else if (q->phase == 3) { if (i >= q->nrange) break; par_decode_range(q, &q->range[i]); }
-		else {
-			if (i >= q->nrange) break;
-			/* carry of range i = sum of the end predictors of the ranges before it (prefix kept in range[].endpred after step 3b) */
-			par_shift_dc(q, &q->range[i], q->range[i].endpred);
-		}
+		else { if (i >= q->nrange) break; par_decode_range(q, &q->range[i]); }
 	}
 	return NULL;
 }
@@ -504,7 +502,7 @@ static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p
 		const unsigned char **next) {
 	jq_image *im = d->im; jq_par *q; int nthr = codec_thread_count(), k, h, v, ri = im->restart_interval, ok = 0, i;
 	const unsigned char *t, *segend = NULL; uint64_t stuffed = 0; size_t len, min_bytes = PAR_MIN_BYTES, chunk_min;
-	const char *env = getenv("JPEGQS_PAR_MIN_BYTES");
+	const char *env = getenv("JPEGQS_PAR_MIN_BYTES"); double tm[4] = { 0 };
 	JDIMENSION ny;
 	if (env && atoi(env) > 0) min_bytes = (size_t)atoi(env);
 	chunk_min = min_bytes / 4 < 64 ? 64 : min_bytes / 4;
@@ -603,23 +601,24 @@ static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p
 
 	q->range = (jq_range*)calloc((size_t)q->nchunk + 1, sizeof(jq_range));
 	if (!q->range) goto out;
+	tm[0] = trace_ms();
 	par_run(q, 1, nthr);
+	tm[1] = trace_ms();
 	if (q->fail || par_stitch(q)) goto out;             /* nothing was written to the arrays yet */
+	tm[2] = trace_ms();
 	par_run(q, 3, nthr);
+	tm[3] = trace_ms();
 	if (q->fail) goto clear;
-	{                                                   /* DC predictors at the start of each range */
-		int carry[MAX_COMPONENTS] = { 0 }, endp[MAX_COMPONENTS];
-		for (i = 0; i < q->nrange; i++) {
-			im->warnings += q->range[i].warn;
-			memcpy(endp, q->range[i].endpred, sizeof(endp));
-			memcpy(q->range[i].endpred, carry, sizeof(carry));       /* from here on: the range's carry-in */
-			for (k = 0; k < MAX_COMPONENTS; k++) carry[k] += endp[k];
-		}
-		par_run(q, 4, nthr);
+	for (i = 0; i < q->nrange; i++) {                   /* the predictors step 2 worked out must be the ones step 3 arrived at */
+		if (i + 1 < q->nrange && q->range[i].check_pred)
+			for (k = 0; k < s->ncomp; k++) if (q->range[i].endpred[k] != q->range[i + 1].pred0[k]) goto clear;
+		im->warnings += q->range[i].warn;
 	}
 	if (getenv("JPEGQS_CODEC_TRACE"))
-		fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d chunks, %d ranges, %llu of %llu MCUs parsed while stitching\n",
-				nthr, q->nchunk, q->nrange, (unsigned long long)q->stitched, (unsigned long long)q->nmcu);
+		fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d chunks, %d ranges, %llu of %llu MCUs parsed while stitching; "
+				"parse %.1f ms, stitch %.1f ms, decode %.1f ms\n",
+				nthr, q->nchunk, q->nrange, (unsigned long long)q->stitched, (unsigned long long)q->nmcu,
+				tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2]);
 	*next = segend; ok = 1;
 	goto out;
 clear:
@@ -629,7 +628,7 @@ clear:
 		memset(a->data, 0, (size_t)a->w * a->h * sizeof(JBLOCK));
 	}
 out:
-	for (i = 0; i < PAR_MAX_CHUNKS; i++) free(q->pos[i]);
+	for (i = 0; i < PAR_MAX_CHUNKS; i++) { free(q->pos[i]); free(q->dcs[i]); }
 	free(q->range); free(q);
 	return ok;
 }
