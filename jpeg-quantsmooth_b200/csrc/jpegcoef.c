@@ -438,6 +438,7 @@ static int par_stitch(jq_par *q) {
 			while (pj < q->npos[j] && q->pos[j][pj] < P) pj++;
 			if (pj < q->npos[j] && q->pos[j][pj] == P) break;           /* synchronized with chunk j */
 			if (m >= q->nmcu) break;
+			if (q->stitched > q->nmcu / 8 + 256) return -1;             /* the chunks do not synchronize: not worth it */
 			skip_mcu(q, &b, pred); m++; q->stitched++;
 		}
 		if (m >= q->nmcu) break;                        /* this one thread parsed to the end of the image */
@@ -531,6 +532,22 @@ static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p
 	}
 	q->nmcu = (uint64_t)q->nx * ny;
 	if (!q->nmcu) goto out;
+	if (!ri) {
+		/* A parser that starts inside an MCU finds its place because the blocks of an MCU do not all
+		 * use the same Huffman tables: with the wrong block phase it soon reads nonsense and falls
+		 * back into step at an MCU start.  If the table sequence of the MCU repeats with a shorter
+		 * period (CMYK or RGB files with one table pair, say) it would stay in step with the bits
+		 * and out of phase with the MCUs for good: those scans are left to the one-thread decoder. */
+		int per;
+		for (per = 1; per < q->nblk; per++) {
+			if (q->nblk % per) continue;
+			for (k = per; k < q->nblk; k++) {
+				const jq_dhuff *a = q->blk[k].dc, *b = q->blk[k - per].dc, *c = q->blk[k].ac, *e = q->blk[k - per].ac;
+				if (memcmp(a->bits, b->bits, 17) || memcmp(a->val, b->val, 256) || memcmp(c->bits, e->bits, 17) || memcmp(c->val, e->val, 256)) break;
+			}
+			if (k == q->nblk) goto out;
+		}
+	}
 
 	if (ri) {
 		/* restart intervals: ceil(nmcu / ri) - 1 markers RST0, RST1, ... RST7, RST0 ... and nothing else */

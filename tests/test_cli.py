@@ -123,18 +123,23 @@ def _big_picture(w, h, seed, **kw):
 
 
 @pytest.mark.parametrize("name", ["base420", "base444", "gray", "opt422", "rst", "dense444", "coarse420", "big420", "big444rst",
-                                  "biggray", "big422opt"])
+                                  "biggray", "big422opt", "bigcmyk"])
 def test_threaded_decoder_equals_the_serial_one(jpegs, tmp_path, name):
     """Sequential scans are decoded on several threads (speculative parsing of chunks, stitched at
     the points where they synchronize; restart intervals as they are).  The result must be the
     one-thread decoder's for every chunk and thread count; the trace says which path ran."""
     big = {"big420": (1400, 900, dict(quality=85)), "big444rst": (900, 700, dict(quality=92, subsampling=0, restart_marker_rows=2)),
            "biggray": (1100, 800, dict(quality=70)), "big422opt": (1000, 640, dict(quality=60, subsampling=1, optimize=True))}
+    big["bigcmyk"] = (640, 480, dict(quality=85))       # one Huffman table pair for all four components: stays on one thread
     if name in big:
         w, h, kw = big[name]
         src = str(tmp_path / (name + ".jpg"))
         im = _big_picture(w, h, len(name))
-        (im.convert("L") if name == "biggray" else im).save(src, **kw)
+        if name == "biggray":
+            im = im.convert("L")
+        if name == "bigcmyk":
+            im = PIL.fromarray(np.dstack([np.asarray(im), np.asarray(im)[:, ::-1, 0]]), "CMYK")
+        im.save(src, **kw)
     else:
         src = jpegs[name]
     ref = str(tmp_path / "serial.jpg")
@@ -149,7 +154,9 @@ def test_threaded_decoder_equals_the_serial_one(jpegs, tmp_path, name):
         r = subprocess.run([EXE, "-n", "0", "-i", "0", src, out], env=env, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(out, "rb").read() == want, (name, threads)
-        if name in big and min_bytes:        # (with the default threshold only segments of 128 KB and more take the threaded path)
+        if name == "bigcmyk":
+            assert "decoded on" not in r.stderr, r.stderr
+        elif name in big and min_bytes:      # (with the default threshold only segments of 128 KB and more take the threaded path)
             assert "decoded on" in r.stderr and "abandoned" not in r.stderr, r.stderr
             if "rst" in name:
                 assert "restart intervals" in r.stderr
