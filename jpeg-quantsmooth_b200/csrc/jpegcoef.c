@@ -27,6 +27,41 @@ static const unsigned char zz_nat[64 + 16] = {
 	63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63       /* guard for corrupt run lengths */
 };
 
+/* Which coefficients of a block are not zero, as a bit mask in ZIG-ZAG order (bit k = k-th
+ * coefficient of the scan): the block coder and the
+ * progressive refinement decoder then walk the set bits instead of testing 63 coefficients.  Natural-order mask by 16-bit compares (SSE2 when the target has it), turned
+ * into zig-zag order with one table look-up per block row. */
+static uint64_t zz_mask_tab[8][256];
+static pthread_once_t zz_mask_once = PTHREAD_ONCE_INIT;
+static void zz_mask_init(void) {
+	int r, b, c, k; unsigned char nat_zz[64];
+	for (k = 0; k < 64; k++) nat_zz[zz_nat[k]] = (unsigned char)k;
+	for (r = 0; r < 8; r++) for (b = 0; b < 256; b++) {
+		uint64_t m = 0;
+		for (c = 0; c < 8; c++) if (b >> c & 1) m |= 1ULL << nat_zz[r * 8 + c];
+		zz_mask_tab[r][b] = m;
+	}
+}
+static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
+	uint64_t m = 0; int r;
+#ifdef __SSE2__
+	const __m128i z = _mm_setzero_si128();
+	for (r = 0; r < 8; r += 2) {
+		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
+		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
+		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));     /* bit set = coefficient not zero */
+		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
+	}
+#else
+	for (r = 0; r < 8; r++) {
+		unsigned k = 0; int c;
+		for (c = 0; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
+		m |= zz_mask_tab[r][k];
+	}
+#endif
+	return m;
+}
+
 /* ---------------------------------------------------------------- in-memory "virtual" arrays */
 struct jvirt_barray_control {
 	JDIMENSION w, h;
@@ -255,31 +290,38 @@ static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEF
 		return;
 	}
 	{                                                   /* AC refinement scan, G.1.2.3 */
-		int p1 = 1 << Al, m1 = -(1 << Al);
+		/* The coefficients that are already non-zero (they take a correction bit each) come from a
+		 * bit mask of the block instead of a walk over up to 63 positions: in these scans most
+		 * blocks are visited only to pass an end-of-band run or a handful of coefficients. */
+		int p1 = 1 << Al, m1 = -(1 << Al), Se = s->Se;
+		const uint64_t range = (Se == 63 ? ~0ULL : (1ULL << (Se + 1)) - 1) & (~0ULL << s->Ss);
+		const uint64_t nz = nonzero_mask_zz(blk) & range;
+		uint64_t w;
+#define REFINE(w_) while (w_) { JCOEFPTR cp = blk + zz_nat[__builtin_ctzll(w_)]; w_ &= w_ - 1; \
+		if (bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1); }
 		i = s->Ss;
 		if (!d->eobrun) {
-			while (i <= s->Se) {
-				int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15, val = 0;
+			while (i <= Se) {
+				int rs = huff_decode(b, &d->ac[s->ta[k]]), r = rs >> 4, sz = rs & 15, val = 0, t;
+				uint64_t zeros;
 				if (sz) val = bits_get(b, 1) ? p1 : m1;
 				else if (r != 15) { d->eobrun = (1u << r) + bits_get(b, r); break; }
-				/* skip r zero-history coefficients; already-nonzero ones take a correction bit */
-				for (; i <= s->Se; i++) {
-					JCOEFPTR cp = blk + zz_nat[i];
-					if (*cp) {
-						if (bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1);
-					} else if (--r < 0) break;
-				}
-				if (val && i <= s->Se) blk[zz_nat[i]] = (JCOEF)val;
+				/* skip r zero-history coefficients; the non-zero ones on the way take a correction bit */
+				zeros = ~nz & range & (~0ULL << i);
+				for (; r > 0 && zeros; r--) zeros &= zeros - 1;
+				t = zeros ? __builtin_ctzll(zeros) : Se + 1;             /* where the new coefficient goes */
+				w = nz & (~0ULL << i) & (t > 63 ? ~0ULL : (1ULL << t) - 1);
+				REFINE(w)
+				i = t;
+				if (val && i <= Se) blk[zz_nat[i]] = (JCOEF)val;
 				i++;
 			}
 		}
 		if (d->eobrun) {
-			for (; i <= s->Se; i++) {
-				JCOEFPTR cp = blk + zz_nat[i];
-				if (*cp && bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1);
-			}
+			if (i <= Se) { w = nz & (~0ULL << i); REFINE(w) }
 			d->eobrun--;
 		}
+#undef REFINE
 	}
 }
 
@@ -709,6 +751,7 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 	memset(im, 0, sizeof(*im));
 	err[0] = 0;
 	if (len < 4 || p[0] != 0xFF || p[1] != 0xD8) { snprintf(err, 256, "not a JPEG file (no SOI)"); return -1; }
+	pthread_once(&zz_mask_once, zz_mask_init);
 	pv = (jq_priv*)calloc(1, sizeof(*pv));
 	d = (jq_dec*)calloc(1, sizeof(*d));
 	if (!pv || !d) { free(pv); free(d); snprintf(err, 256, "out of memory"); return -1; }
@@ -986,41 +1029,6 @@ typedef struct {
  * pending before a put, a put adds at most 27 (a 16-bit code + 11 value bits) */
 #define SEG_PUT(code, size) do { acc = (acc << (size)) | (uint64_t)(code); nacc += (size); \
 	if (nacc >= 32) { uint32_t x_ = __builtin_bswap32((uint32_t)(acc >> (nacc - 32))); memcpy(w, &x_, 4); w += 4; nacc -= 32; } } while (0)
-
-/* Which coefficients of a block are not zero, as a bit mask in ZIG-ZAG order (bit k = k-th
- * coefficient of the scan): the block coder then walks the set bits instead of testing 63
- * coefficients.  Natural-order mask by 16-bit compares (SSE2 when the target has it), turned
- * into zig-zag order with one table look-up per block row. */
-static uint64_t zz_mask_tab[8][256];
-static pthread_once_t zz_mask_once = PTHREAD_ONCE_INIT;
-static void zz_mask_init(void) {
-	int r, b, c, k; unsigned char nat_zz[64];
-	for (k = 0; k < 64; k++) nat_zz[zz_nat[k]] = (unsigned char)k;
-	for (r = 0; r < 8; r++) for (b = 0; b < 256; b++) {
-		uint64_t m = 0;
-		for (c = 0; c < 8; c++) if (b >> c & 1) m |= 1ULL << nat_zz[r * 8 + c];
-		zz_mask_tab[r][b] = m;
-	}
-}
-static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
-	uint64_t m = 0; int r;
-#ifdef __SSE2__
-	const __m128i z = _mm_setzero_si128();
-	for (r = 0; r < 8; r += 2) {
-		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
-		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
-		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));     /* bit set = coefficient not zero */
-		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
-	}
-#else
-	for (r = 0; r < 8; r++) {
-		unsigned k = 0; int c;
-		for (c = 0; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
-		m |= zz_mask_tab[r][k];
-	}
-#endif
-	return m;
-}
 
 /* one block: counts symbols (sg == NULL) or appends its code bits to the segment */
 static inline int enc_block(jq_seg *sg, const JCOEF *blk, int *pred, const jq_ehuff *dc, const jq_ehuff *ac,
