@@ -122,6 +122,17 @@ def test_reference_cli_on_real_libjpeg_writes_this_codecs_bytes(jpegs, tmp_path)
             assert open(a, "rb").read() == open(b, "rb").read(), (name, args)
 
 
+@pytest.mark.skipif(not _have("refcli_cpu"), reason="oracle/_ref not built")
+def test_random_files_one_thread_threaded_and_libjpeg_turbo_agree(tmp_path):
+    """A short run of tools/codec_difftest.py: random size / quality / sub-sampling / optimised tables /
+    restart intervals / progressive files; the lossless transcode must give libjpeg-turbo's bytes with the
+    one-thread reader and with the threaded reader (random thread count and chunk size)."""
+    r = subprocess.run([os.sys.executable, os.path.join(ROOT, "tools", "codec_difftest.py"), "77", "30"], cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "done 30 bad 0" in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not _have("refcli_cpu", "refcli_b200"), reason="oracle/_ref not built")
 @pytest.mark.parametrize("args", [["-q", "3"], ["-q", "4", "-n", "2"], ["-q", "5", "-n", "2"], ["-q", "6"], ["-q", "1"], ["-q", "3", "-o"]])

@@ -7,7 +7,8 @@ reader (random thread count and chunk size) and with the reference's own quantsm
 Round 2: seeds 1-3, 800 files, 0 mismatches."""
 import os, subprocess, sys, numpy as np
 from PIL import Image
-E="/root/repo/jpeg-quantsmooth_b200/csrc/jpegqs"; R="/root/repo/oracle/_ref/refcli_cpu"
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+E=os.path.join(ROOT,"jpeg-quantsmooth_b200","csrc","jpegqs"); R=os.path.join(ROOT,"oracle","_ref","refcli_cpu")
 rng=np.random.RandomState(int(sys.argv[1]) if len(sys.argv)>1 else 1)
 N=int(sys.argv[2]) if len(sys.argv)>2 else 200
 bad=0
@@ -43,3 +44,4 @@ for it in range(N):
         bad+=1; print("MISMATCH",it,w,h,gray,kw,th,mb,a==b,a==c); os.rename("in.jpg",f"bad{it}.jpg")
     if "abandoned" in p.stderr: print("abandoned:",it,kw,th,mb)
 print("done",N,"bad",bad)
+sys.exit(1 if bad else 0)
