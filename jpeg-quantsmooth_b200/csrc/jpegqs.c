@@ -212,14 +212,14 @@ static int run_one(const qs_cfg *g, qs_job *j, int warm_ok) {
 }
 
 #ifndef JPEGQS_NO_CUDA_RENDER
-/* --batch pipeline.  Huffman decoding is the slowest stage (one thread per file: an entropy-coded
- * segment has no entry points), so several reader threads decode different files at once
- * (JPEGQS_BATCH_READERS, default 3).  Readers stay at most `depth` pairs ahead of the writer (an
- * 8K image is 100 MB of coefficients) and do not open an input that an earlier, unfinished pair
- * is going to write. */
+/* --batch pipeline.  Reading and writing a file take longer than smoothing it, so several reader
+ * threads (JPEGQS_BATCH_READERS, default 3) and writer threads (JPEGQS_BATCH_WRITERS, default 2)
+ * work on different files at once while the calling thread keeps the device busy.  Readers stay
+ * at most `depth` pairs ahead of the last written one (an 8K image is 100 MB of coefficients) and
+ * do not open an input that an earlier, unfinished pair is going to write. */
 #define QS_MAX_READERS 16
 typedef struct {
-	const qs_cfg *g; qs_job *jobs; int n, next, depth;
+	const qs_cfg *g; qs_job *jobs; int n, next, wnext, depth;
 	pthread_mutex_t mu; pthread_cond_t cv;
 } qs_pipe;
 
@@ -245,9 +245,13 @@ static void *pipe_reader(void *arg) {
 	return NULL;
 }
 static void *pipe_writer(void *arg) {
-	qs_pipe *p = (qs_pipe*)arg; int i;
-	for (i = 0; i < p->n; i++) {
+	qs_pipe *p = (qs_pipe*)arg; int i, k;
+	for (;;) {
+		pthread_mutex_lock(&p->mu); i = p->wnext++; pthread_mutex_unlock(&p->mu);
+		if (i >= p->n) break;
 		pipe_wait(p, &p->jobs[i], 2);
+		/* two pairs that name the same output are written in their order */
+		for (k = 0; k < i; k++) if (!strcmp(p->jobs[k].out_name, p->jobs[i].out_name)) pipe_wait(p, &p->jobs[k], 3);
 		if (!p->jobs[i].rc) job_write(p->g, &p->jobs[i]);
 		job_release(&p->jobs[i]);
 		pipe_advance(p, &p->jobs[i], 3);
@@ -256,22 +260,26 @@ static void *pipe_writer(void *arg) {
 }
 /* returns the worst exit status of the pairs, -1 if no thread could be started (nothing done) */
 static int run_pipeline(const qs_cfg *g, qs_job *jobs, int n) {
-	qs_pipe p; pthread_t rd[QS_MAX_READERS], wr; int i, worst = 0, have_writer, nrd = 3, started = 0;
+	qs_pipe p; pthread_t rd[QS_MAX_READERS], wr[QS_MAX_READERS]; int i, worst = 0, nrd = 3, nwr = 2, started = 0, writers = 0;
 	const char *env = getenv("JPEGQS_BATCH_READERS");
 	if (env && atoi(env) > 0) nrd = atoi(env);
+	env = getenv("JPEGQS_BATCH_WRITERS");
+	if (env && atoi(env) > 0) nwr = atoi(env);
 	if (nrd > QS_MAX_READERS) nrd = QS_MAX_READERS;
+	if (nwr > QS_MAX_READERS) nwr = QS_MAX_READERS;
 	if (nrd > n) nrd = n;
-	/* stdin is read in the order of the pairs: one reader then */
-	for (i = 0; i < n; i++) if (!strcmp(jobs[i].in_name, "-")) nrd = 1;
-	p.g = g; p.jobs = jobs; p.n = n; p.next = 0; p.depth = nrd + 2;
+	if (nwr > n) nwr = n;
+	/* stdin is read and stdout written in the order of the pairs: one thread on that side then */
+	for (i = 0; i < n; i++) { if (!strcmp(jobs[i].in_name, "-")) nrd = 1; if (!strcmp(jobs[i].out_name, "-")) nwr = 1; }
+	p.g = g; p.jobs = jobs; p.n = n; p.next = 0; p.wnext = 0; p.depth = nrd + nwr + 1;
 	pthread_mutex_init(&p.mu, NULL); pthread_cond_init(&p.cv, NULL);
 	for (i = 0; i < nrd; i++) { if (pthread_create(&rd[started], NULL, pipe_reader, &p)) break; started++; }
 	if (!started) { pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu); return -1; }
-	have_writer = !pthread_create(&wr, NULL, pipe_writer, &p);
+	for (i = 0; i < nwr; i++) { if (pthread_create(&wr[writers], NULL, pipe_writer, &p)) break; writers++; }
 	for (i = 0; i < n; i++) {
 		pipe_wait(&p, &jobs[i], 1);
 		if (!jobs[i].rc) job_smooth(g, &jobs[i]);
-		if (have_writer) pipe_advance(&p, &jobs[i], 2);
+		if (writers) pipe_advance(&p, &jobs[i], 2);
 		else {                                          /* no writer thread: write from here */
 			if (!jobs[i].rc) job_write(g, &jobs[i]);
 			job_release(&jobs[i]);
@@ -279,7 +287,7 @@ static int run_pipeline(const qs_cfg *g, qs_job *jobs, int n) {
 		}
 	}
 	for (i = 0; i < started; i++) pthread_join(rd[i], NULL);
-	if (have_writer) pthread_join(wr, NULL);
+	for (i = 0; i < writers; i++) pthread_join(wr[i], NULL);
 	pthread_cond_destroy(&p.cv); pthread_mutex_destroy(&p.mu);
 	for (i = 0; i < n; i++) if (jobs[i].rc > worst) worst = jobs[i].rc;
 	return worst;

@@ -236,22 +236,26 @@ def test_batch_pipeline_keeps_the_order_of_dependent_pairs(jpegs, tmp_path):
     output of an earlier pair must see the finished file, a failing pair must not disturb the
     others, and the files must be those of the one-pair-after-the-other mode (JPEGQS_NO_PIPELINE)."""
     def run(tag, env):
-        a, b, c, d = (str(tmp_path / f"{tag}_{k}.jpg") for k in "abcd")
+        a, b, c, d, e = (str(tmp_path / f"{tag}_{k}.jpg") for k in "abcde")
         args = [EXE, "-n", "0", "-i", "0", "-t", "3", "--batch",
                 jpegs["base444"], a,              # a
                 a, b,                             # reads what the first pair writes
                 str(tmp_path / "missing.jpg"), str(tmp_path / f"{tag}_x.jpg"),
                 jpegs["prog420"], c,
                 jpegs["dense444"], d,
-                d, d]                             # in place, after the pair before it
+                d, d,                             # in place, after the pair before it
+                jpegs["gray"], e, jpegs["base420"], e]     # the same output twice: the later pair's stays
         r = subprocess.run(args, capture_output=True, text=True, env=env)
         assert r.returncode == 1 and "missing.jpg" in r.stderr
         assert not os.path.exists(tmp_path / f"{tag}_x.jpg")
-        return [open(f, "rb").read() for f in (a, b, c, d)]
+        return [open(f, "rb").read() for f in (a, b, c, d, e)]
     piped = run("p", dict(os.environ))
     plain = run("s", dict(os.environ, JPEGQS_NO_PIPELINE="1"))
     assert piped == plain
     assert piped[0] == piped[1]                   # transcoding our own output changes nothing
+    single = str(tmp_path / "single.jpg")
+    assert subprocess.run([EXE, "-n", "0", "-i", "0", "-t", "3", jpegs["base420"], single]).returncode == 0
+    assert piped[4] == open(single, "rb").read()
 
 
 def test_bad_input_and_usage(tmp_path):
