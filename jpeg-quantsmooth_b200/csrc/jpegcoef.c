@@ -42,6 +42,33 @@ static void zz_mask_init(void) {
 		zz_mask_tab[r][b] = m;
 	}
 }
+/* the same for the AC coefficients only, without reading blk[0]: a DC scan may be writing it on
+ * another thread while a refinement scan of the AC band walks the block (scans in parallel, below) */
+static inline uint64_t nonzero_mask_zz_ac(const JCOEF *blk) {
+	uint64_t m = 0; int r;
+#ifdef __SSE2__
+	const __m128i z = _mm_setzero_si128();
+	{
+		__m128i a = _mm_cmpeq_epi16(_mm_slli_si128(_mm_loadu_si128((const __m128i*)(blk + 1)), 2), z);      /* 0, c1 .. c7 */
+		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + 8)), z);
+		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));
+		m |= zz_mask_tab[0][k & 254] | zz_mask_tab[1][k >> 8 & 255];
+	}
+	for (r = 2; r < 8; r += 2) {
+		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
+		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
+		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));
+		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
+	}
+#else
+	for (r = 0; r < 8; r++) {
+		unsigned k = 0; int c;
+		for (c = r ? 0 : 1; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
+		m |= zz_mask_tab[r][k];
+	}
+#endif
+	return m;
+}
 static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
 	uint64_t m = 0; int r;
 #ifdef __SSE2__
@@ -231,6 +258,8 @@ typedef struct {
 	int pred[MAX_COMPONENTS];
 	unsigned eobrun;
 	JDIMENSION mcux, mcuy;
+	int ri;                              /* restart interval in force for the scan being decoded */
+	int warn;                            /* recoverable anomalies met while decoding (added to jq_image.warnings by jq_read) */
 } jq_dec;
 
 static void dec_block_seq(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEFPTR blk) {
@@ -295,7 +324,7 @@ static void dec_block_prog(jq_dec *d, jq_bits *b, const jq_scan *s, int k, JCOEF
 		 * blocks are visited only to pass an end-of-band run or a handful of coefficients. */
 		int p1 = 1 << Al, m1 = -(1 << Al), Se = s->Se;
 		const uint64_t range = (Se == 63 ? ~0ULL : (1ULL << (Se + 1)) - 1) & (~0ULL << s->Ss);
-		const uint64_t nz = nonzero_mask_zz(blk) & range;
+		const uint64_t nz = nonzero_mask_zz_ac(blk) & range;
 		uint64_t w;
 #define REFINE(w_) while (w_) { JCOEFPTR cp = blk + zz_nat[__builtin_ctzll(w_)]; w_ &= w_ - 1; \
 		if (bits_get(b, 1) && !(*cp & p1)) *cp += (JCOEF)(*cp >= 0 ? p1 : m1); }
@@ -543,7 +572,7 @@ static void par_run(jq_par *q, int phase, int nthr) {
  * again): the caller runs the plain decoder */
 static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p, const unsigned char *end,
 		const unsigned char **next) {
-	jq_image *im = d->im; jq_par *q; int nthr = codec_thread_count(), k, h, v, ri = im->restart_interval, ok = 0, i;
+	jq_image *im = d->im; jq_par *q; int nthr = codec_thread_count(), k, h, v, ri = d->ri, ok = 0, i;
 	const unsigned char *t, *segend = NULL; uint64_t stuffed = 0; size_t len, min_bytes = PAR_MIN_BYTES, chunk_min;
 	const char *env = getenv("JPEGQS_PAR_MIN_BYTES"); double tm[4] = { 0 };
 	JDIMENSION ny;
@@ -617,7 +646,7 @@ static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p
 		q->nrange = (int)nint; q->segend = segend;
 		par_run(q, 3, nthr);
 		if (q->fail) goto clear;
-		for (i = 0; i < q->nrange; i++) im->warnings += q->range[i].warn;
+		for (i = 0; i < q->nrange; i++) d->warn += q->range[i].warn;
 		if (getenv("JPEGQS_CODEC_TRACE"))
 			fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d restart intervals\n", nthr, q->nrange);
 		*next = segend; ok = 1;
@@ -671,7 +700,7 @@ static int dec_scan_parallel(jq_dec *d, const jq_scan *s, const unsigned char *p
 	for (i = 0; i < q->nrange; i++) {                   /* the predictors step 2 worked out must be the ones step 3 arrived at */
 		if (i + 1 < q->nrange && q->range[i].check_pred)
 			for (k = 0; k < s->ncomp; k++) if (q->range[i].endpred[k] != q->range[i + 1].pred0[k]) goto clear;
-		im->warnings += q->range[i].warn;
+		d->warn += q->range[i].warn;
 	}
 	if (getenv("JPEGQS_CODEC_TRACE"))
 		fprintf(stderr, "jpegcoef: scan decoded on %d threads: %d chunks, %d ranges, %llu of %llu MCUs parsed while stitching; "
@@ -695,7 +724,7 @@ out:
 
 static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const unsigned char *end,
 		const unsigned char **next, char *err) {
-	jq_image *im = d->im; jq_bits b; int prog = im->progressive, k, ri = im->restart_interval;
+	jq_image *im = d->im; jq_bits b; int prog = im->progressive, k, ri = d->ri;
 	JDIMENSION nx, ny, x, y; unsigned count = 0, rst = 0;
 	memset(&b, 0, sizeof(b)); b.p = p; b.end = end;
 	memset(d->pred, 0, sizeof(d->pred)); d->eobrun = 0;
@@ -739,15 +768,98 @@ static int dec_scan(jq_dec *d, const jq_scan *s, const unsigned char *p, const u
 		*next = q;
 	} else *next = b.p;
 	(void)rst;
-	im->warnings += b.warn;
+	d->warn += b.warn;
 	return 0;
+}
+
+
+/* ---------------------------------------------------------------- progressive scans side by side
+ * The scans of a progressive file are independent unless they touch the same coefficients: a
+ * scan waits for the earlier scans of one of its components whose band [Ss, Se] overlaps its own
+ * (the first scan of a band, then its refinements), and an AC refinement scan - which looks at
+ * the whole AC part of a block to find the coefficients that are already non-zero - is ordered
+ * against every other AC scan of its component.  jq_read first only RECORDS the scans (the
+ * Huffman tables and restart interval in force, the bytes up to the next marker), then worker
+ * threads decode them as they become ready.  If a scan does not end where the next marker was
+ * found, or anything else goes wrong, the file is read again the plain way, scan after scan, so
+ * damaged files keep their behaviour (and their messages). */
+#define JQ_MAX_DEFER 64
+typedef struct {
+	jq_scan s; jq_dec *d;                /* d: a copy of the decoder state (tables) at the scan's SOS */
+	const unsigned char *p, *segend;
+	uint64_t deps;                       /* earlier scans that must be complete */
+	int started, done, rc;
+} jq_dscan;
+typedef struct {
+	jq_dscan *sc; int n; const unsigned char *end;
+	pthread_mutex_t mu; pthread_cond_t cv;
+	int bad;
+} jq_sched;
+
+static void *sched_worker(void *arg) {
+	jq_sched *q = (jq_sched*)arg; int i; char err[256];
+	pthread_mutex_lock(&q->mu);
+	for (;;) {
+		int pick = -1, unstarted = 0;
+		for (i = 0; i < q->n; i++) {
+			uint64_t dm = q->sc[i].deps; int k, ready = 1;
+			if (q->sc[i].started) continue;
+			unstarted = 1;
+			for (k = 0; k < i && ready; k++) if ((dm >> k & 1) && !q->sc[k].done) ready = 0;
+			if (ready) { pick = i; break; }
+		}
+		if (pick < 0) {
+			if (!unstarted || q->bad) break;
+			pthread_cond_wait(&q->cv, &q->mu);
+			continue;
+		}
+		q->sc[pick].started = 1;
+		pthread_mutex_unlock(&q->mu);
+		{
+			jq_dscan *c = &q->sc[pick]; const unsigned char *next = NULL;
+			c->rc = dec_scan(c->d, &c->s, c->p, q->end, &next, err);
+			if (c->rc || next != c->segend) c->rc = -1;
+		}
+		pthread_mutex_lock(&q->mu);
+		q->sc[pick].done = 1;
+		if (q->sc[pick].rc) q->bad = 1;
+		pthread_cond_broadcast(&q->cv);
+	}
+	pthread_mutex_unlock(&q->mu);
+	return NULL;
+}
+
+/* 0 = all scans decoded as recorded (warnings added up), -1 = read the file again the plain way */
+static int sched_run(jq_image *im, jq_dscan *sc, int n, const unsigned char *end) {
+	jq_sched q; pthread_t tid[64]; int i, j, k, nthr = codec_thread_count(), started = 0, rc = 0;
+	memset(&q, 0, sizeof(q));
+	q.sc = sc; q.n = n; q.end = end;
+	for (j = 0; j < n; j++) for (i = 0; i < j; i++) {
+		const jq_scan *a = &sc[i].s, *b = &sc[j].s; int share = 0;
+		for (k = 0; k < a->ncomp; k++) { int m; for (m = 0; m < b->ncomp; m++) if (a->ci[k] == b->ci[m]) share = 1; }
+		if (!share) continue;
+		if ((a->Ss <= b->Se && b->Ss <= a->Se) ||
+				(a->Ss > 0 && b->Ss > 0 && (a->Ah > 0 || b->Ah > 0))) sc[j].deps |= 1ULL << i;
+	}
+	pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.cv, NULL);
+	if (nthr > n) nthr = n;
+	for (i = 1; i < nthr && i < 64; i++) { if (pthread_create(&tid[started], NULL, sched_worker, &q)) break; started++; }
+	sched_worker(&q);
+	for (i = 0; i < started; i++) pthread_join(tid[i], NULL);
+	pthread_cond_destroy(&q.cv); pthread_mutex_destroy(&q.mu);
+	for (i = 0; i < n; i++) { if (!sc[i].done || sc[i].rc) rc = -1; else im->warnings += sc[i].d->warn; }
+	if (!rc && getenv("JPEGQS_CODEC_TRACE")) fprintf(stderr, "jpegcoef: %d progressive scans decoded on %d threads\n", n, started + 1);
+	return rc;
 }
 
 static unsigned be16(const unsigned char *p) { return (unsigned)p[0] << 8 | p[1]; }
 
-int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char *err) {
+/* defer: progressive scans are recorded and decoded side by side at the end (returns 1 if that did
+ * not work out: the caller reads the file again with defer = 0) */
+static int jq_read_impl(const unsigned char *data, size_t len, int copy, jq_image *im, char *err, int defer) {
 	const unsigned char *p = data, *end = data + len;
 	jq_priv *pv; jq_dec *d; jq_marker **tail; int have_frame = 0, i, done = 0, adobe = -1;
+	jq_dscan *dsc = NULL; int ndsc = 0, retry = 0;
 	memset(im, 0, sizeof(*im));
 	err[0] = 0;
 	if (len < 4 || p[0] != 0xFF || p[1] != 0xD8) { snprintf(err, 256, "not a JPEG file (no SOI)"); return -1; }
@@ -858,7 +970,22 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 			s.Ss = seg[1 + 2 * ns]; s.Se = seg[2 + 2 * ns]; s.Ah = seg[3 + 2 * ns] >> 4; s.Al = seg[3 + 2 * ns] & 15;
 			if (!im->progressive) { s.Ss = 0; s.Se = 63; s.Ah = s.Al = 0; }
 			if (s.Ss > s.Se || s.Se > 63 || s.Al > 13 || (s.Ss > 0 && ns != 1)) { snprintf(err, 256, "bad scan parameters"); goto fail; }
+			d->ri = im->restart_interval;
+			if (defer && im->progressive) {                 /* record the scan, find the next marker */
+				const unsigned char *q = p; jq_dscan *c;
+				if (ndsc == JQ_MAX_DEFER) { retry = 1; goto fail; }
+				if (!dsc) dsc = (jq_dscan*)calloc(JQ_MAX_DEFER, sizeof(*dsc));
+				c = dsc ? &dsc[ndsc] : NULL;
+				if (!c || !(c->d = (jq_dec*)malloc(sizeof(*d)))) { retry = 1; goto fail; }
+				ndsc++;
+				memcpy(c->d, d, sizeof(*d)); c->d->warn = 0;
+				c->s = s; c->p = p;
+				while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0 && q[1] != 0xFF && (q[1] & 0xF8) != 0xD0)) q++;
+				c->segend = q; p = q;
+				continue;
+			}
 			if (dec_scan(d, &s, p, end, &p, err)) goto fail;
+			im->warnings += d->warn; d->warn = 0;
 		} else if ((code >= 0xE0 && code <= 0xEF) || code == 0xFE) {
 			int want = code == 0xFE ? copy > 0 : copy > 1;
 			if (code == 0xEE && seglen >= 12 && !memcmp(seg, "Adobe", 5)) {       /* transform flag, jdmarker.c */
@@ -878,6 +1005,7 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 		}
 	}
 	if (!have_frame) { snprintf(err, 256, "no frame header found"); goto fail; }
+	if (ndsc && sched_run(im, dsc, ndsc, end)) { retry = 1; goto fail; }
 	if (im->saw_jfif && im->cinfo.num_components == 3) im->cinfo.jpeg_color_space = JCS_YCbCr;
 	if (adobe >= 0 && !(im->saw_jfif && im->cinfo.num_components == 3)) {      /* jdapimin.c default_decompress_parms */
 		if (im->cinfo.num_components == 3) im->cinfo.jpeg_color_space = adobe == 0 ? JCS_RGB : JCS_YCbCr;
@@ -888,12 +1016,24 @@ int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char 
 		c->quant_table = im->cinfo.quant_tbl_ptrs[c->quant_tbl_no];
 		if (!c->quant_table) { snprintf(err, 256, "component %d uses an undefined quantization table", i); goto fail; }
 	}
-	free(d);
+	for (i = 0; i < ndsc; i++) free(dsc[i].d);
+	free(dsc); free(d);
 	return 0;
 fail:
-	free(d);
+	for (i = 0; i < ndsc; i++) free(dsc[i].d);
+	free(dsc); free(d);
 	jq_free(im);
-	return -1;
+	/* in deferred mode every failure is looked at again by the plain reader: it decides and words it */
+	return retry || defer ? 1 : -1;
+}
+
+int jq_read(const unsigned char *data, size_t len, int copy, jq_image *im, char *err) {
+	if (codec_thread_count() >= 2 && !getenv("JPEGQS_SERIAL_DECODE")) {
+		int rc = jq_read_impl(data, len, copy, im, err, 1);
+		if (rc <= 0) return rc;
+		if (getenv("JPEGQS_CODEC_TRACE")) fprintf(stderr, "jpegcoef: reading the file again, scan after scan\n");
+	}
+	return jq_read_impl(data, len, copy, im, err, 0) ? -1 : 0;
 }
 
 /* ---------------------------------------------------------------- the writer */

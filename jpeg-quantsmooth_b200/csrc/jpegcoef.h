@@ -57,7 +57,8 @@ void jq_free(jq_image *im);
 /* worker threads of the codec: 0 = one per processor (at most 16).  The writer codes segments of
  * MCU rows on them; the reader decodes sequential (SOF0/SOF1) scans on them - restart intervals as
  * they are, scans without restart markers by speculative parsing of chunks that are stitched where
- * they synchronize (jpegcoef.c) - from four threads up.  Neither the coefficients read nor the
+ * they synchronize (jpegcoef.c) - from four threads up, and the scans of a progressive file side by
+ * side where they touch different coefficients.  Neither the coefficients read nor the
  * bytes written depend on the number.  The environment variable JPEGQS_CODEC_THREADS overrides;
  * JPEGQS_SERIAL_DECODE=1 keeps the reader on one thread, JPEGQS_CODEC_TRACE=1 reports the path taken. */
 void jq_set_threads(int n);
