@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <time.h>
 #include <pthread.h>
 #include <unistd.h>
 #ifdef __SSE2__
@@ -16,7 +17,7 @@
 #endif
 #include "jpegcoef.h"
 
-#include <time.h>
+/* for the JPEGQS_CODEC_TRACE=1 lines (which path ran, how long it took) */
 static double trace_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
 /* zig-zag index -> natural (row-major) index, T.81 figure A.6 */
@@ -28,9 +29,9 @@ static const unsigned char zz_nat[64 + 16] = {
 };
 
 /* Which coefficients of a block are not zero, as a bit mask in ZIG-ZAG order (bit k = k-th
- * coefficient of the scan): the block coder and the
- * progressive refinement decoder then walk the set bits instead of testing 63 coefficients.  Natural-order mask by 16-bit compares (SSE2 when the target has it), turned
- * into zig-zag order with one table look-up per block row. */
+ * coefficient of the scan): the block coder and the progressive refinement decoder walk the set
+ * bits instead of testing 63 coefficients.  Natural-order mask by 16-bit compares (SSE2 when the
+ * target has it), turned into zig-zag order with one table look-up per block row. */
 static uint64_t zz_mask_tab[8][256];
 static pthread_once_t zz_mask_once = PTHREAD_ONCE_INIT;
 static void zz_mask_init(void) {
@@ -42,8 +43,28 @@ static void zz_mask_init(void) {
 		zz_mask_tab[r][b] = m;
 	}
 }
-/* the same for the AC coefficients only, without reading blk[0]: a DC scan may be writing it on
- * another thread while a refinement scan of the AC band walks the block (scans in parallel, below) */
+static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
+	uint64_t m = 0; int r;
+#ifdef __SSE2__
+	const __m128i z = _mm_setzero_si128();
+	for (r = 0; r < 8; r += 2) {
+		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
+		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
+		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));     /* bit set = coefficient not zero */
+		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
+	}
+#else
+	for (r = 0; r < 8; r++) {
+		unsigned k = 0; int c;
+		for (c = 0; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
+		m |= zz_mask_tab[r][k];
+	}
+#endif
+	return m;
+}
+/* The same for the AC coefficients only, WITHOUT reading blk[0]: a DC scan may be writing it on
+ * another thread while a refinement scan of the AC band walks the block ("progressive scans side
+ * by side" below). */
 static inline uint64_t nonzero_mask_zz_ac(const JCOEF *blk) {
 	uint64_t m = 0; int r;
 #ifdef __SSE2__
@@ -64,25 +85,6 @@ static inline uint64_t nonzero_mask_zz_ac(const JCOEF *blk) {
 	for (r = 0; r < 8; r++) {
 		unsigned k = 0; int c;
 		for (c = r ? 0 : 1; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
-		m |= zz_mask_tab[r][k];
-	}
-#endif
-	return m;
-}
-static inline uint64_t nonzero_mask_zz(const JCOEF *blk) {
-	uint64_t m = 0; int r;
-#ifdef __SSE2__
-	const __m128i z = _mm_setzero_si128();
-	for (r = 0; r < 8; r += 2) {
-		__m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8)), z);
-		__m128i b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i*)(blk + r * 8 + 8)), z);
-		unsigned k = ~(unsigned)_mm_movemask_epi8(_mm_packs_epi16(a, b));     /* bit set = coefficient not zero */
-		m |= zz_mask_tab[r][k & 255] | zz_mask_tab[r + 1][k >> 8 & 255];
-	}
-#else
-	for (r = 0; r < 8; r++) {
-		unsigned k = 0; int c;
-		for (c = 0; c < 8; c++) k |= (unsigned)(blk[r * 8 + c] != 0) << c;
 		m |= zz_mask_tab[r][k];
 	}
 #endif
