@@ -478,6 +478,8 @@ static void par_parse_chunk(jq_par *q, int c) {
 		memcpy(s + 4 * n, cum, sizeof(cum));
 		v[n++] = pos;                                   /* the last entry: first MCU start at or beyond the chunk end */
 		if (pos >= limit) break;
+		/* a chunk with 16 times its share of the image's MCUs is crafted or nonsense: bound the notes */
+		if (n > 16 * (q->nmcu / (unsigned)q->nchunk) + 4096) { free(v); v = NULL; break; }
 		skip_mcu(q, &b, cum);
 	}
 	if (!v || !s) { free(v); free(s); v = NULL; s = NULL; q->fail = 1; n = 0; }
