@@ -537,10 +537,9 @@ static inline JCOEFPTR par_block(const jq_par *q, const jq_mcu_blk *mb, JDIMENSI
 }
 
 /* step 3 */
-static void par_decode_range(jq_par *q, jq_range *r) {
-	jq_dec *ld = (jq_dec*)malloc(sizeof(*ld)); jq_bits b; uint64_t m; int k;
-	if (!ld) { q->fail = 1; return; }
-	memcpy(ld, q->d, sizeof(*ld));
+/* ld: the worker's private copy of the decoder state (tables + predictors) */
+static void par_decode_range(jq_par *q, jq_range *r, jq_dec *ld) {
+	jq_bits b; uint64_t m; int k;
 	memset(ld->pred, 0, sizeof(ld->pred));
 	for (k = 0; k < q->s->ncomp; k++) ld->pred[q->s->ci[k]] = r->pred0[k];
 	memset(&b, 0, sizeof(b)); b.p = r->p; b.end = r->end; b.fed = r->fed0;
@@ -552,16 +551,21 @@ static void par_decode_range(jq_par *q, jq_range *r) {
 	if (r->end_pos && par_pos(&b) != r->end_pos) q->fail = 1;
 	for (k = 0; k < q->s->ncomp; k++) r->endpred[k] = ld->pred[q->s->ci[k]];
 	r->warn = b.warn;
-	free(ld);
 }
 
 static void *par_worker(void *arg) {
-	jq_par *q = (jq_par*)arg;
+	jq_par *q = (jq_par*)arg; jq_dec *ld = NULL;
+	if (q->phase == 3) {
+		ld = (jq_dec*)malloc(sizeof(*ld));
+		if (!ld) { q->fail = 1; return NULL; }
+		memcpy(ld, q->d, sizeof(*ld));
+	}
 	for (;;) {
 		int i = __sync_fetch_and_add(&q->next, 1);
 		if (q->phase == 1) { if (i >= q->nchunk) break; par_parse_chunk(q, i); }
-		else { if (i >= q->nrange) break; par_decode_range(q, &q->range[i]); }
+		else { if (i >= q->nrange) break; par_decode_range(q, &q->range[i], ld); }
 	}
+	free(ld);
 	return NULL;
 }
 static void par_run(jq_par *q, int phase, int nthr) {
