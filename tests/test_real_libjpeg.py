@@ -137,7 +137,11 @@ def test_random_files_one_thread_threaded_and_libjpeg_turbo_agree(tmp_path):
 @pytest.mark.skipif(not _have("refcli_cpu", "refcli_b200"), reason="oracle/_ref not built")
 @pytest.mark.parametrize("args", [["-q", "3"], ["-q", "4", "-n", "2"], ["-q", "5", "-n", "2"], ["-q", "6"], ["-q", "1"], ["-q", "3", "-o"]])
 def test_unmodified_reference_cli_runs_on_the_cuda_back_end(jpegs, tmp_path, args):
-    names = ("mcu420", "mcuprog", "mcu422") if "6" in args else ("base420", "prog420", "gray", "opt422", "rst", "mcu420", "base444")
+    # each file costs a fresh process with its CUDA start-up: the flavours are spread over the argument sets
+    # (q6 on MCU-multiple sizes only, see the fixture)
+    names = {"-q 3": ("base420", "prog420", "gray", "rst"), "-q 4 -n 2": ("prog420", "opt422", "base444"),
+             "-q 5 -n 2": ("base420", "mcu420", "base444"), "-q 6": ("mcu420", "mcuprog", "mcu422"),
+             "-q 1": ("gray", "opt422", "rst"), "-q 3 -o": ("base420", "prog420", "opt422")}[" ".join(args)]
     for name in names:
         a, b = str(tmp_path / "cpu.jpg"), str(tmp_path / "b200.jpg")
         r1 = subprocess.run([os.path.join(REFDIR, "refcli_cpu"), "-i", "0"] + args + [jpegs[name], a], capture_output=True, text=True)
